@@ -1,0 +1,8 @@
+"""gpu-olap-engine_b200: B200-native (sm_100a) execution core for gpu-olap-engine's data-parallel hot path.
+
+The compute path is the AOT-compiled CUDA library ``libolap_b200.so`` behind the C ABI in ``include/olap_b200.h``;
+this package is the host-side mirror of the reference's operator / kernel-wrapper interface above it.
+"""
+from ._lib import LIB_PATH, OlapError, load  # noqa: F401
+from .core import (AVG, COUNT, EQ, F64, GE, GT, I64, JOIN_AUTO, JOIN_BROADCAST, JOIN_RADIX, JOIN_SORT_MERGE, LE, LT, MAX, MIN,  # noqa: F401
+                   NE, SUM, Context, DeviceBuffer, Term, typed_agg_results)

@@ -1,0 +1,92 @@
+"""ctypes binding of include/olap_b200.h.  There is no fallback: if libolap_b200.so is missing the import fails."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libolap_b200.so")
+
+OK, ERR_BAD_ARG, ERR_OOM, ERR_OVERFLOW, ERR_CUDA, ERR_UNSUPPORTED, ERR_CAPACITY = range(7)
+_STATUS_NAMES = ["OK", "BAD_ARG", "OOM", "OVERFLOW", "CUDA", "UNSUPPORTED", "CAPACITY"]
+
+
+class OlapError(RuntimeError):
+    """Mirror of the anyhow::Error the Rust wrapper would raise; carries the C status code."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"olap_b200 status {status} ({_STATUS_NAMES[status] if 0 <= status < 7 else '?'}): {message}")
+        self.status = status
+        self.message = message
+
+
+class FilterTerm(C.Structure):
+    _fields_ = [("lhs", C.c_void_p), ("rhs", C.c_void_p), ("literal_bits", C.c_int64), ("op", C.c_int32), ("type", C.c_int32)]
+
+
+class AggSpec(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("func", C.c_int32), ("value_type", C.c_int32)]
+
+
+# name -> (restype, argtypes); the test-suite checks that every OLAP_API symbol of the header is listed here
+vp, u64, i64, i32, u32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32
+pu64, pvp = C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "olap_ctx_create": (i32, [i32, u64, i32, pvp]),
+    "olap_ctx_destroy": (i32, [vp]),
+    "olap_ctx_synchronize": (i32, [vp]),
+    "olap_ctx_stream": (vp, [vp, i32]),
+    "olap_last_error": (C.c_char_p, []),
+    "olap_version": (C.c_char_p, []),
+    "olap_pool_alloc": (i32, [vp, u64, vp, pvp]),
+    "olap_pool_free": (i32, [vp, vp, vp]),
+    "olap_pool_stats": (i32, [vp, pu64, pu64, pu64]),
+    "olap_host_alloc": (i32, [u64, pvp]),
+    "olap_host_free": (i32, [vp]),
+    "olap_memcpy_h2d": (i32, [vp, vp, vp, u64, vp]),
+    "olap_memcpy_d2h": (i32, [vp, vp, vp, u64, vp]),
+    "olap_stream_synchronize": (i32, [vp, vp]),
+    "olap_column_upload": (i32, [vp, vp, u64, i32, vp, u64, vp, vp, vp]),
+    "olap_filter": (i32, [vp, C.POINTER(FilterTerm), i32, u64, vp, vp, vp, pu64, vp]),
+    "olap_filter_i64": (i32, [vp, vp, u64, i32, i64, vp, vp, vp, pu64, vp]),
+    "olap_gather_8b": (i32, [vp, vp, vp, u64, vp, vp]),
+    "olap_filter_compact": (i32, [vp, C.POINTER(FilterTerm), i32, u64, pvp, i32, pvp, vp, pu64, vp]),
+    "olap_project_i64": (i32, [vp, vp, vp, i64, C.c_char, u64, vp, vp]),
+    "olap_project_f64": (i32, [vp, vp, vp, C.c_double, C.c_char, u64, vp, vp]),
+    "olap_hash_join_i64": (i32, [vp, vp, u64, vp, u64, vp, u64, vp, pu64, i32, vp]),
+    "olap_choose_join_strategy": (i32, [u64]),
+    "olap_radix_partition_i64": (i32, [vp, vp, vp, u64, i32, vp, vp, vp, vp]),
+    "olap_partition_of": (u32, [i64, i32]),
+    "olap_group_by_i64": (i32, [vp, vp, C.POINTER(AggSpec), i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
+    "olap_agg_identity": (i64, [i32]),
+    "olap_compute_launch_params": (None, [u64, C.POINTER(u32), C.POINTER(u32)]),
+    "olap_generate": (i32, [vp, vp, u64, i32, u64, u64, u64, vp]),
+    "olap_set_profiling": (i32, [vp, i32]),
+    "olap_last_phase_times": (i32, [vp, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_float)), C.POINTER(i32)]),
+    "olap_launch_count": (u64, [vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C gpu-olap-engine_b200/csrc`). "
+                "There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != OK:
+        raise OlapError(status, load().olap_last_error().decode(errors="replace"))

@@ -1,0 +1,190 @@
+// Shared host/device helpers of the B200 execution core.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/olap_b200.h"
+
+namespace olap {
+
+constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// --------------------------------------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+olap_status cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define OLAP_CUDA(expr)                                                        \
+  do {                                                                         \
+    cudaError_t _e = (expr);                                                   \
+    if (_e != cudaSuccess) return ::olap::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+#define OLAP_TRY(expr)                         \
+  do {                                         \
+    olap_status _s = (expr);                   \
+    if (_s != OLAP_OK) return _s;              \
+  } while (0)
+#define OLAP_REQUIRE(cond, msg)                                  \
+  do {                                                           \
+    if (!(cond)) { ::olap::set_error("bad argument: %s", msg); return OLAP_ERR_BAD_ARG; } \
+  } while (0)
+
+}  // namespace olap
+
+// --------------------------------------------------------------------------------------------- context
+struct olap_ctx {
+  int device = 0;
+  int sm_count = olap::kSMs;
+  size_t smem_optin = 0;
+  cudaMemPool_t pool = nullptr;
+  std::vector<cudaStream_t> streams;
+  std::mutex mu;
+  std::unordered_map<void*, uint64_t> live;  // pool allocations -> bytes
+  uint64_t used = 0, high_water = 0, max_bytes = 0;
+  uint64_t launches = 0;
+  // profiling of the last multi-phase operator
+  bool profiling = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  std::string phase_names;
+  std::vector<float> phase_ms;
+  // cached scratch that survives across calls (hash-table arena reused by the join, zeroed once)
+  void* table_arena = nullptr;
+  uint64_t table_arena_bytes = 0;
+  uint32_t table_generation = 0;
+  cudaEvent_t fork_ev = nullptr, join_ev[8] = {};
+
+  cudaStream_t stream_of(void* s) const { return s ? (cudaStream_t)s : streams[0]; }
+};
+
+namespace olap {
+
+// RAII scratch allocation from the context's stream-ordered pool (freed on the same stream).
+olap_status pool_alloc(olap_ctx* ctx, uint64_t bytes, cudaStream_t s, void** out);
+olap_status pool_free(olap_ctx* ctx, void* p, cudaStream_t s);
+
+struct Scratch {
+  olap_ctx* ctx; cudaStream_t s; std::vector<void*> ptrs;
+  Scratch(olap_ctx* c, cudaStream_t st) : ctx(c), s(st) {}
+  ~Scratch() { for (void* p : ptrs) pool_free(ctx, p, s); }
+  template <class T> olap_status get(uint64_t count, T** out) {
+    void* p = nullptr;
+    olap_status st = pool_alloc(ctx, count * sizeof(T) + 16, s, &p);
+    if (st == OLAP_OK) { ptrs.push_back(p); *out = (T*)p; }
+    return st;
+  }
+};
+
+void phase_begin(olap_ctx* ctx, cudaStream_t s);
+void phase_mark(olap_ctx* ctx, cudaStream_t s, const char* name);
+void phase_end(olap_ctx* ctx, cudaStream_t s);
+
+inline void count_launch(olap_ctx* ctx, uint64_t n = 1) { ctx->launches += n; }
+
+// --------------------------------------------------------------------------------------------- device helpers
+// murmur3 fmix64: a bijection on 64-bit words.  High bits pick the radix partition, low bits the table slot.
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + (i + 1) * 0x9e3779b97f4a7c15ULL;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+  return z ^ (z >> 31);
+}
+
+// Streaming loads: read-only path, no L1 allocation.  The 256-bit form (sm_100a LDG.E.256) additionally marks the
+// line evict-first in L2 so that scans do not push the L2-resident hash tables / partition write fronts out of
+// the 126 MB L2 (ptxas only accepts .L2::evict_first on 256-bit accesses).  Needs 32-byte alignment.
+struct u64x4 { uint64_t a, b, c, d; };
+__device__ __forceinline__ u64x4 ld_stream_u64x4(const void* p) {
+  u64x4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream_u64x4(void* p, u64x4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v.a), "l"(v.b), "l"(v.c), "l"(v.d) : "memory");
+}
+__device__ __forceinline__ ulonglong2 ld_stream_u64x2(const void* p) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint64_t ld_stream_u64(const void* p) {
+  uint64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_stream_u32x4(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+// Streaming stores: written once, not re-read by this kernel.
+__device__ __forceinline__ void st_stream_u64(void* p, uint64_t v) {
+  asm volatile("st.global.L1::no_allocate.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_u32(void* p, uint32_t v) {
+  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_u64x2(void* p, ulonglong2 v) {
+  asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+
+// comparison shared by filter / fused kernels; op outside EQ..GE matches nothing (executor.rs:464)
+template <class T>
+__device__ __forceinline__ bool cmp_op(T l, T r, int op) {
+  switch (op) {
+    case OLAP_EQ: return l == r;
+    case OLAP_NE: return l != r;
+    case OLAP_LT: return l < r;
+    case OLAP_LE: return l <= r;
+    case OLAP_GT: return l > r;
+    case OLAP_GE: return l >= r;
+    default: return false;
+  }
+}
+
+// Filter conjunction passed by value to kernels (up to 8 terms).
+constexpr int kMaxTerms = 8;
+struct TermPack {
+  const uint64_t* lhs[kMaxTerms];
+  const uint64_t* rhs[kMaxTerms];
+  int64_t lit[kMaxTerms];
+  int8_t op[kMaxTerms];
+  int8_t type[kMaxTerms];
+  int n;
+};
+
+__device__ __forceinline__ bool eval_term(const TermPack& t, int k, uint64_t l, uint64_t r) {
+  if (t.type[k] == OLAP_F64) return cmp_op<double>(__longlong_as_double((long long)l), __longlong_as_double((long long)r), t.op[k]);
+  return cmp_op<long long>((long long)l, (long long)r, t.op[k]);
+}
+__device__ __forceinline__ bool eval_terms_row(const TermPack& t, uint64_t row) {
+  bool pass = true;
+#pragma unroll 1
+  for (int k = 0; k < t.n; k++) {
+    uint64_t l = ld_stream_u64(t.lhs[k] + row);
+    uint64_t r = t.rhs[k] ? ld_stream_u64(t.rhs[k] + row) : (uint64_t)t.lit[k];
+    pass = pass && eval_term(t, k, l, r);
+  }
+  return pass;
+}
+olap_status pack_terms(const olap_filter_term* terms, int32_t n_terms, TermPack* out);
+
+}  // namespace olap

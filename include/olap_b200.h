@@ -1,0 +1,198 @@
+/*
+ * olap_b200.h -- C ABI of the B200-native execution core for gpu-olap-engine's data-parallel hot path.
+ *
+ * This is the seam the reference's Rust executor binds (see INTEGRATION.md for the -sys crate stub).  Every
+ * entry point names the reference interface it replaces (path:line under the reference checkout).  Plain C:
+ * pointers, sizes, POD structs; no C++/torch types; no exceptions cross it.  Every function returns an
+ * olap_status; olap_last_error() gives the thread-local message (maps 1:1 onto anyhow::Error in Rust).
+ *
+ * Conventions
+ *   - "dptr" arguments are device addresses (what the reference passes as u64 in JoinParams/FilterParams/
+ *     AggregateParams); all columns are packed little-endian 8-byte values (arrow-interop column_buffer.rs:19-21).
+ *   - stream is a cudaStream_t passed as void* (NULL = the context's stream 0).  Calls are asynchronous on that
+ *     stream unless a host out-parameter (uint64_t* host_*) is non-NULL, in which case the call synchronises the
+ *     stream before returning so the value is valid.
+ *   - One olap_ctx per GPU.  Calls on one ctx from several host threads are serialised by an internal mutex;
+ *     distinct ctxs are independent.
+ *   - There is no CPU fallback anywhere behind this header.
+ */
+#ifndef OLAP_B200_H
+#define OLAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OLAP_API __attribute__((visibility("default")))
+
+typedef struct olap_ctx olap_ctx;
+typedef int32_t olap_status;
+
+enum {
+  OLAP_OK = 0,
+  OLAP_ERR_BAD_ARG = 1,
+  OLAP_ERR_OOM = 2,
+  OLAP_ERR_OVERFLOW = 3, /* join produced more pairs than max_matches (count is still exact) */
+  OLAP_ERR_CUDA = 4,
+  OLAP_ERR_UNSUPPORTED = 5,
+  OLAP_ERR_CAPACITY = 6  /* more groups than out_capacity */
+};
+
+/* CmpOp, gpu-kernel-compiler/src/codegen.rs:10 (declaration order) */
+enum { OLAP_EQ = 0, OLAP_NE = 1, OLAP_LT = 2, OLAP_LE = 3, OLAP_GT = 4, OLAP_GE = 5 };
+/* AggFunc, gpu-kernel-compiler/src/aggregate_kernel.rs:17-25 */
+enum { OLAP_SUM = 0, OLAP_COUNT = 1, OLAP_MIN = 2, OLAP_MAX = 3, OLAP_AVG = 4 };
+/* GpuDataType, arrow-interop/src/column_buffer.rs:8-15 (the two arithmetic layouts) */
+enum { OLAP_I64 = 0, OLAP_F64 = 1 };
+/* JoinStrategy, gpu-kernel-compiler/src/join_kernel.rs:13-18; AUTO applies choose_strategy (:71-77) */
+enum { OLAP_JOIN_AUTO = -1, OLAP_JOIN_RADIX = 0, OLAP_JOIN_SORT_MERGE = 1, OLAP_JOIN_BROADCAST = 2 };
+/* Arrow source types accepted by olap_column_upload (record_batch_convert.rs:42-98) */
+enum { OLAP_SRC_I8 = 0, OLAP_SRC_I16, OLAP_SRC_I32, OLAP_SRC_I64, OLAP_SRC_U8, OLAP_SRC_U16, OLAP_SRC_U32, OLAP_SRC_U64,
+       OLAP_SRC_F32, OLAP_SRC_F64 };
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Lifecycle.  Replaces EngineConfig (gpu-olap-core/src/lib.rs:20-43) + TransferQueue::new
+ * (gpu-memory-manager/src/transfer_queue.rs:36-52).  max_gpu_memory caps the stream-ordered pool (0 = no cap);
+ * use_unified_memory has no equivalent: device pools replace managed memory by design.
+ * ------------------------------------------------------------------------------------------------------- */
+OLAP_API olap_status olap_ctx_create(int32_t device_ordinal, uint64_t max_gpu_memory, int32_t num_streams, olap_ctx** out);
+OLAP_API olap_status olap_ctx_destroy(olap_ctx* ctx);
+OLAP_API olap_status olap_ctx_synchronize(olap_ctx* ctx);               /* TransferQueue::synchronize, :133-139 */
+OLAP_API void* olap_ctx_stream(olap_ctx* ctx, int32_t stream_id);       /* stream_id % num_streams, :72 */
+OLAP_API const char* olap_last_error(void);
+OLAP_API const char* olap_version(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Memory.  Replaces SlabAllocator::allocate/free (gpu-memory-manager/src/slab_allocator.rs:50-93) with a
+ * stream-ordered cudaMemPool, and TransferQueue::enqueue_transfer (transfer_queue.rs:55-79).
+ * ------------------------------------------------------------------------------------------------------- */
+OLAP_API olap_status olap_pool_alloc(olap_ctx* ctx, uint64_t bytes, void* stream, void** out_dptr);
+OLAP_API olap_status olap_pool_free(olap_ctx* ctx, void* dptr, void* stream);
+OLAP_API olap_status olap_pool_stats(olap_ctx* ctx, uint64_t* used_bytes, uint64_t* high_water_bytes, uint64_t* reserved_bytes);
+OLAP_API olap_status olap_host_alloc(uint64_t bytes, void** out_hptr);  /* pinned */
+OLAP_API olap_status olap_host_free(void* hptr);
+OLAP_API olap_status olap_memcpy_h2d(olap_ctx* ctx, void* dptr, const void* hptr, uint64_t bytes, void* stream);
+OLAP_API olap_status olap_memcpy_d2h(olap_ctx* ctx, void* hptr, const void* dptr, uint64_t bytes, void* stream);
+OLAP_API olap_status olap_stream_synchronize(olap_ctx* ctx, void* stream);
+
+/* record_batch_to_gpu_buffers / column_to_buffer (arrow-interop/src/record_batch_convert.rs:22-110): copy an
+ * Arrow values buffer to the device and widen it to 8 bytes per row THERE.  Int64/Float64 without nulls is a
+ * straight async copy from the Arrow buffer.  validity_bitmap is Arrow's bit-per-row bitmap (LSB first) or
+ * NULL; null rows become 0 / 0.0 (:103, :108); out_validity_bytes (nullable dptr, 1 byte per row, :37-41).
+ * bit_offset is the Arrow array offset applied to both buffers.                                            */
+OLAP_API olap_status olap_column_upload(olap_ctx* ctx, const void* host_values, uint64_t n_rows, int32_t src_type,
+                                        const uint8_t* validity_bitmap, uint64_t bit_offset, void* out_dptr,
+                                        uint8_t* out_validity_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Filter.  Replaces FilterParams/FilterKernel::launch (gpu-kernel-compiler/src/filter_kernel.rs:17-72) and the
+ * per-predicate PTX JIT (codegen.rs:36-47): (op, literal) are kernel arguments of one AOT kernel.  Semantics:
+ * eval_filter_mask (gpu-olap-core/src/executor.rs:443-476).  A conjunction is evaluated in one pass.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* lhs;      /* dptr, 8-byte column */
+  const void* rhs;      /* dptr of a second column, or NULL to compare with the literal */
+  int64_t literal_bits; /* i64 literal, or the bit pattern of an f64 literal when type == OLAP_F64 */
+  int32_t op;           /* OLAP_EQ..OLAP_GE; any other value matches no row (executor.rs:464) */
+  int32_t type;         /* OLAP_I64 (reference behaviour) or OLAP_F64 (extension) */
+} olap_filter_term;
+
+/* out_mask: u8 per row, 1 = pass (filter_kernel.rs:3-5), nullable.  out_sel: u32 row ids of passing rows in
+ * row order (the "prefix-sum + scatter" pass, fused), nullable.  out_count_dptr: u64 on device, nullable.
+ * host_count: nullable (synchronises).                                                                      */
+OLAP_API olap_status olap_filter(olap_ctx* ctx, const olap_filter_term* terms, int32_t n_terms, uint64_t n_rows,
+                                 uint8_t* out_mask, uint32_t* out_sel, uint64_t* out_count_dptr, uint64_t* host_count,
+                                 void* stream);
+/* FilterPredicate{col, op, literal:i64} convenience form (codegen.rs:23-28) */
+OLAP_API olap_status olap_filter_i64(olap_ctx* ctx, const int64_t* col, uint64_t n_rows, int32_t op, int64_t literal,
+                                     uint8_t* out_mask, uint32_t* out_sel, uint64_t* out_count_dptr, uint64_t* host_count,
+                                     void* stream);
+/* take_int64 (executor.rs:496-507): out[i] = col[sel[i]] for any 8-byte column */
+OLAP_API olap_status olap_gather_8b(olap_ctx* ctx, const void* col, const uint32_t* sel, uint64_t n_sel, void* out, void* stream);
+/* filter_record_batch (executor.rs:478-494) fused: evaluate the conjunction and compact n_cols 8-byte columns
+ * in one pass, row order preserved.  out_cols[i] must hold n_rows values.                                   */
+OLAP_API olap_status olap_filter_compact(olap_ctx* ctx, const olap_filter_term* terms, int32_t n_terms, uint64_t n_rows,
+                                         const void* const* cols, int32_t n_cols, void* const* out_cols,
+                                         uint64_t* out_count_dptr, uint64_t* host_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Projection.  eval_binary_expr (executor.rs:411-441): op in "+-*" wraps, '/' by zero gives 0, any other op 0.
+ * rhs == NULL uses the literal.                                                                             */
+OLAP_API olap_status olap_project_i64(olap_ctx* ctx, const int64_t* lhs, const int64_t* rhs, int64_t literal, char op,
+                                      uint64_t n_rows, int64_t* out, void* stream);
+/* f64 arithmetic extension (the reference errors at executor.rs:416-424) */
+OLAP_API olap_status olap_project_f64(olap_ctx* ctx, const double* lhs, const double* rhs, double literal, char op,
+                                      uint64_t n_rows, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Hash join.  Replaces JoinParams/JoinKernel::join (gpu-kernel-compiler/src/join_kernel.rs:20-68) and the
+ * kernels radix_partition_kernel / build_hash_table_kernel / probe_hash_table_kernel
+ * (kernels/join_kernels.cuh:45-166).  Inner equi-join on int64 keys; build side = left (executor.rs:238-253).
+ * Output: (left_row, right_row) pairs in unspecified order (compare sorted), exact match count.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct { uint32_t left_row, right_row; } olap_pair;
+
+/* out_pairs may be NULL (count only).  If count > max_matches the first max_matches reservations are written,
+ * the count stays exact (join_kernels.cuh:155-160) and -- when host_count is given -- the call returns
+ * OLAP_ERR_OVERFLOW instead of the reference's silent truncation.                                           */
+OLAP_API olap_status olap_hash_join_i64(olap_ctx* ctx, const int64_t* build_keys, uint64_t n_build,
+                                        const int64_t* probe_keys, uint64_t n_probe, olap_pair* out_pairs,
+                                        uint64_t max_matches, uint64_t* out_count_dptr, uint64_t* host_count,
+                                        int32_t strategy, void* stream);
+/* JoinKernel::choose_strategy (join_kernel.rs:71-77) */
+OLAP_API int32_t olap_choose_join_strategy(uint64_t n_build);
+
+/* radix_partition_kernel (join_kernels.cuh:45-76) as a unit: partitions (key, row id) into 2^bits partitions by
+ * the high bits of the core's own 64-bit mixer (partition ids are not externally visible).
+ * row_ids NULL = implicit 0..n-1.  out_part_begin: dptr to 2^bits + 1 u32 offsets.                          */
+OLAP_API olap_status olap_radix_partition_i64(olap_ctx* ctx, const int64_t* keys, const uint32_t* row_ids, uint64_t n_rows,
+                                              int32_t bits, int64_t* out_keys, uint32_t* out_row_ids,
+                                              uint32_t* out_part_begin, void* stream);
+/* the partition a key lands in (host helper for tests) */
+OLAP_API uint32_t olap_partition_of(int64_t key, int32_t bits);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Aggregation.  Replaces AggregateParams/AggregateSpec/AggregateKernel::aggregate
+ * (gpu-kernel-compiler/src/aggregate_kernel.rs:37-125) and hash_aggregate_kernel (join_kernels.cuh:216-240).
+ * keys == NULL: one global group (what execute_aggregate does today, executor.rs:307).  Output: out_keys[g],
+ * and agg-major 8-byte slots out_aggs[i * out_capacity + g] (aggregate_kernel.rs:98) typed per aggregate:
+ * COUNT i64; SUM/MIN/MAX in the value's type (i64 SUM wraps); AVG finalised f64 (sum/count, 0.0 if count = 0).
+ * Groups come out in unspecified order.  n_groups_hint is the caller's upper bound (AggregateParams.n_groups);
+ * a wrong hint costs speed, never correctness.  Optional filter terms are fused into the same pass.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* values;  /* dptr, 8-byte column (ignored for COUNT; may be NULL) */
+  int32_t func;        /* OLAP_SUM.. */
+  int32_t value_type;  /* OLAP_I64 / OLAP_F64 */
+} olap_agg_spec;
+
+OLAP_API olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, const olap_agg_spec* specs, int32_t n_aggs,
+                                       uint64_t n_rows, uint64_t n_groups_hint, const olap_filter_term* terms,
+                                       int32_t n_terms, int64_t* out_keys, void* out_aggs, uint64_t out_capacity,
+                                       uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream);
+/* AggFunc::identity_value (aggregate_kernel.rs:27-33) */
+OLAP_API int64_t olap_agg_identity(int32_t func);
+/* compute_launch_params (filter_kernel.rs:75-79, aggregate_kernel.rs:127-131), without the u32 truncation bug */
+OLAP_API void olap_compute_launch_params(uint64_t n_rows, uint32_t* grid, uint32_t* block);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Synthetic data on the device (counter-based splitmix64(seed, row); any shard can generate
+ * its slice).  kind: 0 uniform i64 in [0, domain); 1 permutation of [0, domain) evaluated at row0 + i;
+ * 2 dyadic f64 = (u % domain) / 1024; 3 uniform f64 in [0, 1).                                              */
+OLAP_API olap_status olap_generate(olap_ctx* ctx, void* out_dptr, uint64_t n_rows, int32_t kind, uint64_t seed,
+                                   uint64_t row0, uint64_t domain, void* stream);
+
+/* per-phase device timings of the last join / group-by on this ctx (ms, CUDA events on the call's stream);
+ * names is a ';'-separated list valid until the next call.  Enabled by olap_set_profiling(ctx, 1).          */
+OLAP_API olap_status olap_set_profiling(olap_ctx* ctx, int32_t enabled);
+OLAP_API olap_status olap_last_phase_times(olap_ctx* ctx, const char** names, const float** ms, int32_t* n);
+/* number of kernels launched by this ctx since creation (bench.py's gpu_launches) */
+OLAP_API uint64_t olap_launch_count(olap_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OLAP_B200_H */

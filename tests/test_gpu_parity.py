@@ -1,0 +1,299 @@
+"""GPU parity tests: every call goes through the C ABI (include/olap_b200.h) into the sm_100a library and is
+compared with the CPU oracle on the same seeded inputs.  Bit-exact for masks, selections, row-id pairs, counts
+and integer/min/max aggregates; f64 SUM/AVG bit-exact on dyadic data and <= 1e-12 relative on random data."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+F64_RTOL = 1e-12  # north_star tolerance for floating-point SUM/AVG
+
+
+def dev(ctx, arr):
+    return ctx.upload_raw(np.ascontiguousarray(arr))
+
+
+# ------------------------------------------------------------------------------------------------- generators
+def test_device_generators_match_oracle(ctx):
+    for kind, fn, dom in [(0, O.gen_uniform_i64, 1000), (0, O.gen_uniform_i64, 2**27), (1, O.gen_perm_i64, 100000),
+                          (1, O.gen_perm_i64, 1 << 16), (2, O.gen_dyadic_f64, 1 << 20)]:
+        got = ctx.generate(50001, kind, 7, dom, row0=123).to_numpy()
+        assert (got == fn(50001, 7, dom, row0=123)).all()
+    assert (ctx.generate(1000, 3, 9).to_numpy() == O.gen_unit_f64(1000, 9)).all()
+
+
+# ------------------------------------------------------------------------------------------------- filter
+def test_filter_reference_vector(ctx):
+    # executor.rs:553-570
+    col = dev(ctx, np.array([5, 15, 25], np.int64))
+    cnt, mask, sel = ctx.filter_i64(col, 3, O.GT, 10)
+    assert cnt == 2 and mask.to_numpy().tolist() == [0, 1, 1] and sel.to_numpy(cnt).tolist() == [1, 2]
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 2047, 2048, 2049, 100003, 1 << 20])
+@pytest.mark.parametrize("op", [O.EQ, O.NE, O.LT, O.LE, O.GT, O.GE, 9])
+def test_filter_i64_all_ops(ctx, n, op):
+    col = O.gen_uniform_i64(n, 1, 1000) - 500
+    d = dev(ctx, col)
+    cnt, mask, sel = ctx.filter_i64(d, n, op, 3)
+    exp = O.filter_mask_i64(col, op, literal=3)
+    assert (mask.to_numpy() == exp).all()
+    idx = O.mask_to_indices(exp)
+    assert cnt == len(idx) and (sel.to_numpy(cnt) == idx).all()  # row order preserved
+
+
+def test_filter_conjunction_columns_f64_and_unaligned(ctx):
+    import gpu_olap_engine_b200 as g
+    n = 300001
+    a = O.gen_uniform_i64(n + 1, 2, 1 << 20); b = O.gen_uniform_i64(n + 1, 3, 1 << 20); f = O.gen_dyadic_f64(n + 1, 4, 1 << 20)
+    da, db, df = dev(ctx, a), dev(ctx, b), dev(ctx, f)
+    for off in (0, 1):  # off = 1: pointers are only 8-byte aligned -> scalar-load variant
+        terms = [g.Term(da.ptr + 8 * off, g.GT, 1 << 19), g.Term(da.ptr + 8 * off, g.LE, rhs=db.ptr + 8 * off),
+                 g.Term(df.ptr + 8 * off, g.LT, 600.25, type=g.F64)]
+        cnt, mask, sel = ctx.filter(terms, n)
+        aa, bb, ff = a[off:off + n], b[off:off + n], f[off:off + n]
+        exp = O.filter_mask_i64(aa, O.GT, literal=1 << 19)
+        O.lib().orc_mask_and(exp.ctypes.data, O.filter_mask_i64(aa, O.LE, rhs=bb).ctypes.data, n)
+        exp &= (ff < 600.25).astype(np.uint8)
+        assert (mask.to_numpy() == exp).all() and cnt == exp.sum()
+        assert (sel.to_numpy(cnt) == O.mask_to_indices(exp)).all()
+
+
+def test_filter_compact_and_gather(ctx):
+    import gpu_olap_engine_b200 as g
+    n = 250000
+    k = O.gen_uniform_i64(n, 5, 1000); v = O.gen_uniform_i64(n, 6, 1 << 20); f = O.gen_dyadic_f64(n, 7, 1 << 20)
+    dk, dv, df = dev(ctx, k), dev(ctx, v), dev(ctx, f)
+    exp = O.filter_mask_i64(v, O.GT, literal=1 << 19); idx = O.mask_to_indices(exp)
+    cnt, outs = ctx.filter_compact([g.Term(dv, g.GT, 1 << 19)], n, [dk, dv, df], [np.int64, np.int64, np.float64])
+    assert cnt == len(idx)
+    for o, src in zip(outs, (k, v, f)):
+        assert (o.to_numpy(cnt) == O.take(src, idx)).all()  # filter_record_batch (executor.rs:478-494)
+    _, _, sel = ctx.filter_i64(dv, n, g.GT, 1 << 19, want_mask=False)
+    assert (ctx.gather(df, sel, cnt, np.float64).to_numpy() == O.take(f, idx)).all()
+
+
+# ------------------------------------------------------------------------------------------------- projection
+@pytest.mark.parametrize("op", ["+", "-", "*", "/", "%"])
+def test_project_i64(ctx, op):
+    n = 100001
+    a = O.gen_uniform_i64(n, 8, 2**62) - 2**61; b = O.gen_uniform_i64(n, 9, 7) - 3
+    a[:4] = [-2**63, 2**63 - 1, -2**63, 5]; b[:4] = [-1, 1, 0, 0]
+    da, db = dev(ctx, a), dev(ctx, b)
+    assert (ctx.project_i64(da, op, n, rhs=db).to_numpy() == O.project_i64(a, op, b)).all()
+    assert (ctx.project_i64(da, op, n, literal=-7).to_numpy() == O.project_i64(a, op, literal=-7)).all()
+
+
+def test_project_f64_extension(ctx):
+    n = 4097
+    a = O.gen_dyadic_f64(n, 1, 1 << 20); b = O.gen_dyadic_f64(n, 2, 1 << 10) + 1
+    da, db = dev(ctx, a), dev(ctx, b)
+    assert (ctx.project_f64(da, "*", n, rhs=db).to_numpy() == a * b).all()
+    assert (ctx.project_f64(da, "-", n, literal=1.0).to_numpy() == a - 1.0).all()
+
+
+# ------------------------------------------------------------------------------------------------- arrow layout
+def test_upload_widens_on_device(ctx):
+    rng = np.random.default_rng(0)
+    for dt in (np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64, np.float32, np.float64):
+        if np.issubdtype(dt, np.floating):
+            a = rng.standard_normal(1001).astype(dt)
+        else:
+            info = np.iinfo(dt); a = rng.integers(info.min, info.max, 1001, dtype=dt, endpoint=True)
+        assert (ctx.upload(a).to_numpy() == O.widen_column(a)).all()
+    a = np.arange(100, dtype=np.int32); valid = (np.arange(100) % 3 != 0)
+    bitmap = np.packbits(valid, bitorder="little")
+    col, v = ctx.upload(a, validity_bitmap=bitmap, want_validity=True)
+    assert (col.to_numpy() == O.widen_column(a, validity=valid.astype(np.uint8))).all()
+    assert (v.to_numpy() == valid).all()
+
+
+# ------------------------------------------------------------------------------------------------- join
+def check_join(ctx, b, p, strategy, max_matches=None):
+    import gpu_olap_engine_b200 as g
+    db, dp = dev(ctx, b), dev(ctx, p)
+    exp_c, exp_pairs = O.hash_join_i64(b, p)
+    mm = max_matches if max_matches is not None else max(exp_c, 1)
+    cnt, pairs = ctx.hash_join_i64(db, len(b), dp, len(p), max_matches=mm, strategy=strategy)
+    assert cnt == exp_c
+    got = pairs.to_numpy(2 * cnt).reshape(-1, 2)
+    assert (O.sort_pairs(got) == exp_pairs).all()
+    c2, _ = ctx.hash_join_i64(db, len(b), dp, len(p), strategy=strategy, want_pairs=False)
+    assert c2 == exp_c
+
+
+@pytest.mark.parametrize("strategy", [2, 0])  # BroadcastHashJoin, RadixHashJoin
+@pytest.mark.parametrize("nb,npb,dom", [(0, 100, 10), (100, 0, 10), (1, 1, 1), (1000, 5000, 300), (5000, 1000, 100000),
+                                        (4096, 4096, 17), (100000, 1000000, 100000), (300000, 70000, 50)])
+def test_join_matches_oracle(ctx, strategy, nb, npb, dom):
+    b = O.gen_uniform_i64(nb, 11, dom); p = O.gen_uniform_i64(npb, 12, dom)
+    if nb * npb // max(dom, 1) > 40_000_000:
+        pytest.skip("too many matches for a test")
+    check_join(ctx, b, p, strategy)
+
+
+@pytest.mark.parametrize("strategy", [2, 0])
+def test_join_c1b_shape(ctx, strategy):
+    # BASELINE config 1: 100 K unique build keys (permutation) joined with 1 M FK probes
+    b = O.gen_perm_i64(100000, 2, 100000); p = O.gen_uniform_i64(1000000, 22, 100000)
+    check_join(ctx, b, p, strategy)
+
+
+@pytest.mark.parametrize("strategy", [2, 0])
+def test_join_edge_keys(ctx, strategy):
+    b = np.array([-1, 2**32 + 1, 0, 2**63 - 1, -2**63, 2**32, 1, 1, 1], np.int64)
+    p = np.array([0, -1, 1, 2**32, 2**32 + 1, -2**63, 2**63 - 1, 99, 1], np.int64)
+    check_join(ctx, b, p, strategy)
+    check_join(ctx, np.full(3000, 7, np.int64), np.full(500, 7, np.int64), strategy)  # all-same key: 1.5 M pairs
+
+
+def test_join_overflow_is_reported(ctx):
+    import gpu_olap_engine_b200 as g
+    b = np.arange(1000, dtype=np.int64); p = np.arange(1000, dtype=np.int64)
+    db, dp = dev(ctx, b), dev(ctx, p)
+    with pytest.raises(g.OlapError) as ei:
+        ctx.hash_join_i64(db, 1000, dp, 1000, max_matches=10)
+    assert ei.value.status == 3 and ei.value.count == 1000  # OLAP_ERR_OVERFLOW, count still exact (join_kernels.cuh:155-160)
+
+
+def test_join_large_radix_fk(ctx):
+    # 4 Mi unique build keys, 16 Mi FK probes: several partitions, every probe row matches exactly once
+    nb, npb = 1 << 22, 1 << 24
+    db = ctx.generate(nb, 1, 3, nb); dp = ctx.generate(npb, 0, 33, nb)
+    cnt, pairs = ctx.hash_join_i64(db, nb, dp, npb, max_matches=npb, strategy=0)
+    assert cnt == npb
+    got = pairs.to_numpy(2 * cnt).reshape(-1, 2)
+    bk = db.to_numpy(); pk = dp.to_numpy()
+    assert (np.sort(got[:, 1]) == np.arange(npb, dtype=np.uint32)).all()     # every probe row exactly once
+    assert (bk[got[:, 0]] == pk[got[:, 1]]).all()                            # and with an equal build key
+    exp_c, exp_pairs = O.hash_join_i64(bk, pk, threads=8)
+    assert exp_c == cnt and (O.sort_pairs(got) == O.sort_pairs(exp_pairs)).all()
+
+
+@pytest.mark.parametrize("bits", [1, 4, 8])
+def test_radix_partition_unit(ctx, bits):
+    import gpu_olap_engine_b200 as g
+    n = 300007
+    keys = O.gen_uniform_i64(n, 13, 2**40) - 2**39
+    dk = dev(ctx, keys)
+    ok, oi, begin = ctx.radix_partition_i64(dk, n, bits)
+    ok, oi, begin = ok.to_numpy(), oi.to_numpy(), begin.to_numpy()
+    P = 1 << bits
+    assert begin[0] == 0 and begin[P] == n and (np.diff(begin.astype(np.int64)) >= 0).all()
+    assert (keys[oi] == ok).all() and (np.sort(oi) == np.arange(n)).all()     # a permutation of the input rows
+    part = np.array([g.load().olap_partition_of(int(k), bits) for k in ok[::997]])
+    pos = np.arange(n)[::997]
+    assert ((begin[part] <= pos) & (pos < begin[part + 1])).all()           # every row sits in its hash partition
+
+
+# ------------------------------------------------------------------------------------------------- group-by
+def check_group_by(ctx, keys, cols, funcs, hint, terms_fn=None, mask=None, rtol=0.0):
+    import gpu_olap_engine_b200 as g
+    n = len(cols[0]) if cols else len(keys)
+    dk = None if keys is None else dev(ctx, keys)
+    dcols = [dev(ctx, c) for c in cols]
+    aggs = [(f, d, g.F64 if c.dtype == np.float64 else g.I64) for f, d, c in zip(funcs, dcols, cols)]
+    terms = terms_fn(dcols) if terms_fn else None
+    ng, ok, oa, cap = ctx.group_by_i64(dk, n, aggs, hint, out_capacity=max(hint, 1 << 16), terms=terms)
+    gk = ok.to_numpy(ng); res = g.typed_agg_results(oa.to_numpy(), cap, ng, aggs)
+    order = np.argsort(gk, kind="stable")
+    if mask is not None:
+        sel = mask.astype(bool)
+        ek, eres = O.group_by_i64(None if keys is None else keys[sel], [c[sel] for c in cols], funcs)
+    else:
+        ek, eres = O.group_by_i64(keys, cols, funcs)
+    assert ng == len(ek) and (gk[order] == ek).all()
+    for got, exp, f, c in zip(res, eres, funcs, cols):
+        got = got[order]
+        if got.dtype == np.float64 and rtol:
+            assert np.allclose(got, exp, rtol=rtol, atol=0), f
+        else:
+            assert (got == exp).all(), (f, c.dtype)
+    return ng
+
+
+ALL5 = [O.SUM, O.COUNT, O.MIN, O.MAX, O.AVG]
+
+
+@pytest.mark.parametrize("G,hint", [(1, 1), (7, 7), (100, 100), (1000, 1000), (3000, 3000), (1000, 10), (50000, 50000), (50000, 64)])
+def test_group_by_i64_regimes(ctx, G, hint):
+    # hint == G: the intended regime; hint << G: the hint is wrong and correctness must not depend on it
+    n = 400003
+    k = O.gen_uniform_i64(n, 4, G) * 7919 - 1000; v = O.gen_uniform_i64(n, 5, 1 << 20) - (1 << 19)
+    check_group_by(ctx, k, [v] * 5, ALL5, hint)
+
+
+def test_group_by_f64_dyadic_bit_exact_and_random_tolerance(ctx):
+    n = 300000
+    k = O.gen_uniform_i64(n, 4, 500); f = O.gen_dyadic_f64(n, 6, 1 << 20); r = O.gen_unit_f64(n, 7) - 0.5
+    check_group_by(ctx, k, [f] * 5, ALL5, 500)                               # bit-exact: sums are order-independent
+    import gpu_olap_engine_b200 as g
+    dk, dr = dev(ctx, k), dev(ctx, r)
+    aggs = [(g.SUM, dr, g.F64), (g.AVG, dr, g.F64), (g.MIN, dr, g.F64), (g.MAX, dr, g.F64)]
+    ng, ok, oa, cap = ctx.group_by_i64(dk, n, aggs, 500)
+    gk = ok.to_numpy(ng); res = g.typed_agg_results(oa.to_numpy(), cap, ng, aggs); order = np.argsort(gk)
+    ek, eres = O.group_by_i64(k, [r] * 4, [O.SUM, O.AVG, O.MIN, O.MAX], compensated=True)
+    scale = np.array([np.abs(r[k == kk]).sum() for kk in ek])               # relative to the magnitude summed
+    assert (np.abs(res[0][order] - eres[0]) <= F64_RTOL * scale).all()
+    assert (np.abs(res[1][order] - eres[1]) <= F64_RTOL * scale).all()
+    assert (res[2][order] == eres[2]).all() and (res[3][order] == eres[3]).all()
+
+
+def test_group_by_global_matches_reference_execution(ctx):
+    # what execute_aggregate actually computes today (executor.rs:307-346): one global group
+    n = 1 << 20
+    v = O.gen_uniform_i64(n, 5, 1 << 20); f = O.gen_dyadic_f64(n, 6, 1 << 20)
+    check_group_by(ctx, None, [v] * 5 + [f] * 5, ALL5 + ALL5, 1)
+    import gpu_olap_engine_b200 as g
+    dv = dev(ctx, v)
+    aggs = [(fn, dv, g.I64) for fn in ALL5]
+    ng, ok, oa, cap = ctx.group_by_i64(None, n, aggs, 1)
+    res = g.typed_agg_results(oa.to_numpy(), cap, ng, aggs)
+    ref = O.GlobalAgg(); ref.update(v)
+    for got, fn in zip(res, ALL5):
+        assert float(got[0]) == ref.final(fn)      # reference-compat view: identical while magnitudes < 2^53
+    # empty input: SUM 0, COUNT 0, AVG 0.0, MIN/MAX identities (executor.rs:310-311, :339-345; aggregate_kernel.rs:27-33)
+    ng, ok, oa, cap = ctx.group_by_i64(None, 0, aggs, 1)
+    res = g.typed_agg_results(oa.to_numpy(), cap, ng, aggs)
+    assert ng == 1 and [int(r[0]) if r.dtype != np.float64 else float(r[0]) for r in res] == [0, 0, 2**63 - 1, -2**63, 0.0]
+
+
+def test_group_by_fused_filter_c1a_shape(ctx):
+    # BASELINE config 1: filter v_i > 2^19 then GROUP BY k SUM/COUNT on a 1 Mi-row table
+    import gpu_olap_engine_b200 as g
+    n = 1 << 20
+    k = O.gen_uniform_i64(n, 1, 1000); vi = O.gen_uniform_i64(n, 11, 1 << 20); vf = O.gen_dyadic_f64(n, 12, 1 << 20)
+    mask = O.filter_mask_i64(vi, O.GT, literal=1 << 19)
+    check_group_by(ctx, k, [vi, vi, vf], [O.SUM, O.COUNT, O.SUM], 1000, terms_fn=lambda d: [g.Term(d[0], g.GT, 1 << 19)], mask=mask)
+    check_group_by(ctx, None, [vi, vi, vf], [O.SUM, O.COUNT, O.AVG], 1, terms_fn=lambda d: [g.Term(d[0], g.GT, 1 << 19)], mask=mask)
+
+
+def test_group_by_edge_keys_and_empty(ctx):
+    k = np.array([-2**63, 2**63 - 1, -2**63, 0, -1, 0, 2**63 - 1, -2**63], np.int64)
+    v = np.arange(8, dtype=np.int64) - 3
+    check_group_by(ctx, k, [v] * 5, ALL5, 4)
+    check_group_by(ctx, k, [v] * 5, ALL5, 100000)                            # forces the global-table regime
+    assert check_group_by(ctx, np.array([], np.int64), [np.array([], np.int64)], [O.SUM], 10) == 0
+
+
+def test_group_by_capacity_error(ctx):
+    import gpu_olap_engine_b200 as g
+    k = dev(ctx, np.arange(1000, dtype=np.int64))
+    with pytest.raises(g.OlapError) as ei:
+        ctx.group_by_i64(k, 1000, [(g.COUNT, None, g.I64)], 1000, out_capacity=10)
+    assert ei.value.status == 6
+
+
+# ------------------------------------------------------------------------------------------------- memory
+def test_pool_alloc_free_and_cap():
+    import gpu_olap_engine_b200 as g
+    with g.Context(0, max_gpu_memory=1 << 20) as c:   # EngineConfig.max_gpu_memory as the pool cap
+        a = c.alloc(1000, np.int64)
+        assert c.pool_stats()["used"] >= 8000
+        with pytest.raises(g.OlapError) as ei:
+            c.alloc(1 << 20, np.int64)
+        assert ei.value.status == 2
+        a.free()
+        assert c.pool_stats()["used"] == 0 and c.pool_stats()["high_water"] >= 8000
