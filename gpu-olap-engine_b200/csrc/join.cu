@@ -119,11 +119,20 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : 2) partition_kern
   __syncthreads();
   const uint64_t begin = blockIdx.x * a.chunk, end = min(a.n, begin + a.chunk);
 
+  // software pipeline: the next tile's keys are already in flight (registers) while this tile is ranked, staged and
+  // written, so the HBM read latency hides behind the shared-memory phases
+  uint64_t kn[2][4]; bool okn[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; j++) load_keys4(a, begin + (uint64_t)(j * kPartThreads + tid) * 4, end, kn[j], okn[j]);
   for (uint64_t tile = begin; tile < end; tile += kPartTile) {
-    // phase 1: load 8 rows, pick the partition from the high hash bits, rank inside the tile with one smem atomic
+    // phase 1: pick the partition from the high hash bits, rank inside the tile with one smem atomic per row
     uint64_t k[2][4]; bool ok[2][4]; uint32_t part[2][4], rank[2][4];
 #pragma unroll
-    for (int j = 0; j < 2; j++) load_keys4(a, tile + (uint64_t)(j * kPartThreads + tid) * 4, end, k[j], ok[j]);
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) { k[j][e] = kn[j][e]; ok[j][e] = okn[j][e]; }
+#pragma unroll
+    for (int j = 0; j < 2; j++) load_keys4(a, tile + kPartTile + (uint64_t)(j * kPartThreads + tid) * 4, end, kn[j], okn[j]);
 #pragma unroll
     for (int j = 0; j < 2; j++)
 #pragma unroll
@@ -202,7 +211,8 @@ static olap_status launch_partition(olap_ctx* ctx, PartArgs& a, unsigned grid, c
 }
 
 // histogram + scan + scatter of one relation.  hist must hold P * grid u32.
-static olap_status run_partition(olap_ctx* ctx, PartArgs& a, int npay, bool ids, uint32_t* part_begin, cudaStream_t s) {
+static olap_status run_partition(olap_ctx* ctx, PartArgs& a, int npay, bool ids, uint32_t* part_begin, cudaStream_t s,
+                                 const char* hist_mark = nullptr, const char* part_mark = nullptr) {
   PartPlan pl = plan_partition(ctx, a.n);
   a.chunk = pl.chunk;
   a.vec = aligned32(a.keys);
@@ -210,6 +220,7 @@ static olap_status run_partition(olap_ctx* ctx, PartArgs& a, int npay, bool ids,
   part_hist_kernel<<<pl.grid, kPartThreads, 0, s>>>(a);
   part_scan_kernel<<<1, 1024, 0, s>>>(a.hist, P * pl.grid, pl.grid, P, part_begin);
   count_launch(ctx, 2);
+  if (hist_mark) phase_mark(ctx, s, hist_mark);
   if (ids) {
     if (npay == 0) OLAP_TRY((launch_partition<0, true>(ctx, a, pl.grid, s)));
     else { set_error("ids + payload partitioning is not instantiated"); return OLAP_ERR_UNSUPPORTED; }
@@ -223,87 +234,206 @@ static olap_status run_partition(olap_ctx* ctx, PartArgs& a, int npay, bool ids,
     }
   }
   OLAP_CUDA(cudaGetLastError());
+  if (part_mark) phase_mark(ctx, s, part_mark);
   return OLAP_OK;
 }
 
 // ------------------------------------------------------------------------------------------- build / probe
-// 16-byte slot {key, build row, generation}; a slot is occupied iff generation == the current one.
+// The table is an array of 32-byte buckets = one L2 sector: {key0, key1, row0, row1, count, maxdisp}.
+//   build : ONE atomicAdd on the bucket's counter per visited bucket: 0/1 -> the slot is ours (plain stores follow),
+//           >= 2 -> full, try the next bucket.  A key that lands d > 0 buckets past its home bucket h records
+//           atomicMax(table[h].maxdisp, d).
+//   probe : reads the home bucket (one sector) and must look further only if maxdisp[h] > 0 -- i.e. only when a key
+//           with the SAME home was displaced (about 8 % of probes at load 0.5), no matter how long the linear-probing
+//           cluster around it is.  Those continuations go to a per-CTA queue and are processed in parallel phases
+//           (one dependent L2 round trip per phase for the whole tile).
+// Measured on the way here (scratch/micro2.cu, profiles/r01_*): a CAS-per-slot build of 512 Ki rows took 29 us even
+// with the table in L2 (every failed CAS is a dependent ~1 us round trip; the kernel waits for its longest chain);
+// recycling slots through a generation tag instead of clearing made every insert a read-modify-write of a DRAM-resident
+// line (20 G/s); "walk while the bucket is full / was passed" made each warp loop ~5 times per row group with 4 lanes
+// active (28 us per 2048-row tile of pure dependent latency).  The table is cleared right before its build: a pure
+// write allocates the lines in L2 without a DRAM read.
+// Home bucket = mulhi(hash << partition_bits, n_buckets): any table size (exactly 32 B per build row at load 0.5, no
+// power-of-two rounding), independent of the bits that chose the partition.
 constexpr int kBuildThreads = 256;
 constexpr int kProbeThreads = 256;
-constexpr int kProbeRows = 8;
-constexpr int kProbeTile = kProbeThreads * kProbeRows;   // 2048 probe rows per tile
-constexpr int kProbeStage = 4096;                        // staged pairs per tile (32 KB)
+constexpr int kProbeRows = 4;                            // rows per thread per sub-round (one 256-bit key load)
+constexpr int kProbeSub = 2;                             // sub-rounds per tile: the sync/atomic/flush chain is paid once per tile
+constexpr int kProbeTile = kProbeThreads * kProbeRows * kProbeSub;   // 2048 probe rows per tile
+constexpr int kProbeStage = 3072;                        // staged pairs per tile (24 KB)
+constexpr int kProbeQueue = 512;                         // continuation queue entries per phase buffer
 
+struct Bucket { uint64_t k0, k1; uint32_t r0, r1, cnt, maxdisp; };  // 32 bytes
+
+// table reads: 256-bit, no L1 allocation (no reuse inside an SM; the table lives in L2)
+__device__ __forceinline__ Bucket ld_bucket(const Bucket* p) {
+  uint64_t a, b, c, d;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  Bucket r;
+  r.k0 = a; r.k1 = b; r.r0 = (uint32_t)c; r.r1 = (uint32_t)(c >> 32); r.cnt = (uint32_t)d; r.maxdisp = (uint32_t)(d >> 32);
+  return r;
+}
+
+__device__ __forceinline__ uint64_t home_bucket(uint64_t key, int bits, uint64_t n_buckets) {
+  return __umul64hi(mix64(key) << bits, n_buckets);
+}
+
+// one row per thread: every insert's key load, atomic and stores are in flight together
 __global__ void __launch_bounds__(kBuildThreads) build_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
-                                                              uint64_t begin, uint64_t end, uint4* __restrict__ table, uint64_t mask,
-                                                              uint32_t gen) {
+                                                              uint64_t begin, uint64_t end, Bucket* __restrict__ table,
+                                                              uint64_t n_buckets, int bits) {
   const uint64_t stride = (uint64_t)gridDim.x * kBuildThreads;
   for (uint64_t row = begin + blockIdx.x * (uint64_t)kBuildThreads + threadIdx.x; row < end; row += stride) {
     const uint64_t key = ld_stream_u64(keys + row);
     const uint32_t id = ids ? ld_stream_u32(ids + row) : (uint32_t)row;
-    uint64_t s = mix64(key) & mask;
+    const uint64_t home = home_bucket(key, bits, n_buckets);
+    uint64_t b = home;
+    uint32_t d = 0;
     for (;;) {
-      // generations only grow, so atomicMax claims a stale slot and leaves a live one untouched in one L2 atomic
-      const uint32_t old = atomicMax(reinterpret_cast<uint32_t*>(table + s) + 3, gen);
-      if (old != gen) {
-        table[s] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), id, gen);
-        break;
-      }
-      s = (s + 1) & mask;
+      Bucket* bk = table + b;
+      const uint32_t slot = atomicAdd(&bk->cnt, 1u);
+      if (slot == 0) { bk->k0 = key; bk->r0 = id; break; }
+      if (slot == 1) { bk->k1 = key; bk->r1 = id; break; }
+      if (++b == n_buckets) b = 0;
+      d++;
     }
+    if (d) atomicMax(&table[home].maxdisp, d);
   }
 }
 
-__global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
-                                                              uint64_t begin, uint64_t end, const uint4* __restrict__ table, uint64_t mask,
-                                                              uint32_t gen, olap_pair* __restrict__ out, uint64_t max_matches,
-                                                              unsigned long long* __restrict__ count) {
-  __shared__ uint2 s_buf[kProbeStage];
-  __shared__ uint32_t s_n;
-  __shared__ unsigned long long s_base;
-  const int tid = threadIdx.x;
-  for (uint64_t tile = begin + blockIdx.x * (uint64_t)kProbeTile; tile < end; tile += (uint64_t)gridDim.x * kProbeTile) {
-    if (tid == 0) s_n = 0;
+struct ProbeShared {
+  uint2 stage[kProbeStage];
+  uint64_t q_key[2][kProbeQueue];
+  uint32_t q_pid[2][kProbeQueue], q_bkt[2][kProbeQueue], q_rem[2][kProbeQueue];
+  uint32_t q_n[2];
+  uint32_t n;
+  unsigned long long base;
+};
+
+__device__ __forceinline__ void stage_or_spill(uint2* stage, uint32_t idx, uint32_t brow, uint32_t pid, olap_pair* out, uint64_t max_matches,
+                                               unsigned long long* count) {
+  if (idx < kProbeStage) stage[idx] = make_uint2(brow, pid);
+  else {  // more matches than the stage holds (duplicate-heavy build side): reserve directly
+    const unsigned long long pos = atomicAdd(count, 1ULL);
+    if (out && pos < max_matches) out[pos] = olap_pair{brow, pid};
+  }
+}
+
+// one continuation step: look at bucket bk for key, emit hits (per-thread smem atomic: continuations are rare)
+__device__ __forceinline__ void probe_step(ProbeShared& sh, const Bucket* table, uint32_t bk, uint64_t key, uint32_t pid, olap_pair* out,
+                                           uint64_t max_matches, unsigned long long* count) {
+  const Bucket x = ld_bucket(table + bk);
+  if (x.cnt >= 1 && x.k0 == key) stage_or_spill(sh.stage, atomicAdd(&sh.n, 1u), x.r0, pid, out, max_matches, count);
+  if (x.cnt >= 2 && x.k1 == key) stage_or_spill(sh.stage, atomicAdd(&sh.n, 1u), x.r1, pid, out, max_matches, count);
+}
+
+// VEC: keys (and ids) may be read with 256/128-bit loads (32-byte aligned base; tiles start on multiples of 4 rows)
+template <bool VEC>
+__global__ void __launch_bounds__(kProbeThreads, 4) probe_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
+                                                                 uint64_t begin, uint64_t end, const Bucket* __restrict__ table,
+                                                                 uint64_t n_buckets, int bits, olap_pair* __restrict__ out,
+                                                                 uint64_t max_matches, unsigned long long* __restrict__ count) {
+  __shared__ ProbeShared sh;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned lt = (1u << lane) - 1;
+  const uint32_t nbk = (uint32_t)n_buckets;
+  const uint64_t first = begin & ~3ULL;  // tiles start 4-row aligned so vector loads stay aligned; rows < begin are masked
+  for (uint64_t tile = first + blockIdx.x * (uint64_t)kProbeTile; tile < end; tile += (uint64_t)gridDim.x * kProbeTile) {
+    if (tid == 0) { sh.n = 0; sh.q_n[0] = 0; sh.q_n[1] = 0; }
     __syncthreads();
-    uint64_t key[kProbeRows];
-    uint64_t slot[kProbeRows];
-    uint4 ent[kProbeRows];
+#pragma unroll 1
+    for (int sub = 0; sub < kProbeSub; sub++) {
+      const uint64_t row0 = tile + (uint64_t)(sub * kProbeThreads + tid) * kProbeRows;
+      uint64_t key[kProbeRows];
+      uint32_t pid[kProbeRows];
+      bool live[kProbeRows];
+      if (VEC && row0 >= begin && row0 + 3 < end) {
+        u64x4 v = ld_stream_u64x4(keys + row0);
+        key[0] = v.a; key[1] = v.b; key[2] = v.c; key[3] = v.d;
+        if (ids) { uint4 w = ld_stream_u32x4(ids + row0); pid[0] = w.x; pid[1] = w.y; pid[2] = w.z; pid[3] = w.w; }
+        else { pid[0] = (uint32_t)row0; pid[1] = (uint32_t)row0 + 1; pid[2] = (uint32_t)row0 + 2; pid[3] = (uint32_t)row0 + 3; }
+        live[0] = live[1] = live[2] = live[3] = true;
+      } else {
 #pragma unroll
-    for (int j = 0; j < kProbeRows; j++) {  // all first-slot loads of the tile are in flight before any is consumed
-      const uint64_t row = tile + (uint64_t)j * kProbeThreads + tid;
-      key[j] = row < end ? ld_stream_u64(keys + row) : 0;
-      slot[j] = mix64(key[j]) & mask;
-      ent[j] = row < end ? __ldg(table + slot[j]) : make_uint4(0, 0, 0, gen - 1);
-    }
+        for (int j = 0; j < kProbeRows; j++) {
+          const uint64_t row = row0 + j;
+          live[j] = row >= begin && row < end;
+          key[j] = live[j] ? ld_stream_u64(keys + row) : 0;
+          pid[j] = live[j] ? (ids ? ld_stream_u32(ids + row) : (uint32_t)row) : 0;
+        }
+      }
+      uint32_t b[kProbeRows];
+      Bucket e[kProbeRows];
 #pragma unroll
-    for (int j = 0; j < kProbeRows; j++) {
-      const uint64_t row = tile + (uint64_t)j * kProbeThreads + tid;
-      uint4 e = ent[j];
-      uint64_t s = slot[j];
-      uint32_t pid = 0xFFFFFFFFu;
-      while (e.w == gen) {
-        if (e.x == (uint32_t)key[j] && e.y == (uint32_t)(key[j] >> 32)) {
-          if (pid == 0xFFFFFFFFu) pid = ids ? ld_stream_u32(ids + row) : (uint32_t)row;
-          const uint32_t idx = atomicAdd(&s_n, 1u);
-          if (idx < kProbeStage) s_buf[idx] = make_uint2(e.z, pid);
-          else {  // more matches than the stage holds (duplicate-heavy build side): reserve directly
-            const unsigned long long pos = atomicAdd(count, 1ULL);
-            if (out && pos < max_matches) out[pos] = olap_pair{e.z, pid};
+      for (int j = 0; j < kProbeRows; j++) {  // all home-bucket loads are in flight before any is consumed
+        b[j] = (uint32_t)home_bucket(key[j], bits, n_buckets);
+        e[j].cnt = 0; e[j].maxdisp = 0;
+        if (live[j]) e[j] = ld_bucket(table + b[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kProbeRows; j++) {
+        const Bucket x = e[j];
+        // every lane is here (convergent): hits are ranked with two ballots and appended with ONE shared-memory atomic
+        // per warp -- a same-address ATOMS costs ~5 cycles, one per hit would dominate the tile
+        const bool h0 = x.cnt >= 1 && x.k0 == key[j], h1 = x.cnt >= 2 && x.k1 == key[j];
+        const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+        if (m0 | m1) {
+          const uint32_t n0 = __popc(m0);
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&sh.n, n0 + __popc(m1));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (h0) stage_or_spill(sh.stage, base + __popc(m0 & lt), x.r0, pid[j], out, max_matches, count);
+          if (h1) stage_or_spill(sh.stage, base + n0 + __popc(m1 & lt), x.r1, pid[j], out, max_matches, count);
+        }
+        // a key with this home bucket was displaced: queue the row for the continuation phases
+        const bool cont = x.maxdisp != 0;
+        const unsigned mc = __ballot_sync(0xffffffffu, cont);
+        if (mc) {
+          uint32_t qb = 0;
+          if (lane == 0) qb = atomicAdd(&sh.q_n[0], __popc(mc));
+          qb = __shfl_sync(0xffffffffu, qb, 0);
+          if (cont) {
+            const uint32_t qi = qb + __popc(mc & lt);
+            uint32_t nb1 = b[j] + 1;
+            if (nb1 == nbk) nb1 = 0;
+            if (qi < kProbeQueue) { sh.q_key[0][qi] = key[j]; sh.q_pid[0][qi] = pid[j]; sh.q_bkt[0][qi] = nb1; sh.q_rem[0][qi] = x.maxdisp; }
+            else {  // queue full (pathological skew): walk the chain right here
+              for (uint32_t r = x.maxdisp; r; r--) { probe_step(sh, table, nb1, key[j], pid[j], out, max_matches, count); if (++nb1 == nbk) nb1 = 0; }
+            }
           }
         }
-        s = (s + 1) & mask;
-        e = __ldg(table + s);
       }
     }
     __syncthreads();
-    const uint32_t n = min(s_n, (uint32_t)kProbeStage);
-    if (tid == 0 && n) s_base = atomicAdd(count, (unsigned long long)n);  // one global atomic per tile
+    // continuation phases: every queued row looks at its next bucket; rows with displacement left re-queue
+    for (int cur = 0;; cur ^= 1) {
+      const uint32_t qn = min(sh.q_n[cur], (uint32_t)kProbeQueue);
+      if (qn == 0) break;
+      for (uint32_t i = tid; i < qn; i += kProbeThreads) {
+        const uint64_t k = sh.q_key[cur][i];
+        const uint32_t p = sh.q_pid[cur][i], rem = sh.q_rem[cur][i] - 1;
+        uint32_t bk = sh.q_bkt[cur][i];
+        probe_step(sh, table, bk, k, p, out, max_matches, count);
+        if (rem) {
+          if (++bk == nbk) bk = 0;
+          const uint32_t qi = atomicAdd(&sh.q_n[cur ^ 1], 1u);
+          if (qi < kProbeQueue) { sh.q_key[cur ^ 1][qi] = k; sh.q_pid[cur ^ 1][qi] = p; sh.q_bkt[cur ^ 1][qi] = bk; sh.q_rem[cur ^ 1][qi] = rem; }
+          else for (uint32_t r = rem; r; r--) { probe_step(sh, table, bk, k, p, out, max_matches, count); if (++bk == nbk) bk = 0; }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) sh.q_n[cur] = 0;
+      __syncthreads();
+    }
+    __syncthreads();
+    const uint32_t n = min(sh.n, (uint32_t)kProbeStage);
+    if (tid == 0 && n) sh.base = atomicAdd(count, (unsigned long long)n);  // one global atomic per tile
     __syncthreads();
     if (out && n) {
-      const unsigned long long base = s_base;
+      const unsigned long long base = sh.base;
       for (uint32_t i = tid; i < n; i += kProbeThreads) {
         const unsigned long long pos = base + i;
-        if (pos < max_matches) st_stream_u64(out + pos, (uint64_t)s_buf[i].x | ((uint64_t)s_buf[i].y << 32));
+        if (pos < max_matches) st_stream_u64(out + pos, (uint64_t)sh.stage[i].x | ((uint64_t)sh.stage[i].y << 32));
       }
     }
     __syncthreads();
@@ -312,24 +442,12 @@ __global__ void __launch_bounds__(kProbeThreads) probe_kernel(const uint64_t* __
 
 static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 
-// table arena: grown on demand, zeroed once; slots are recycled through the generation tag
+// table arena: grown on demand, kept across calls; every table is cleared on its stream right before its build
 static olap_status ensure_arena(olap_ctx* ctx, uint64_t bytes) {
   if (ctx->table_arena_bytes >= bytes) return OLAP_OK;
   if (ctx->table_arena) { OLAP_CUDA(cudaDeviceSynchronize()); OLAP_CUDA(cudaFree(ctx->table_arena)); ctx->table_arena = nullptr; ctx->table_arena_bytes = 0; }
   OLAP_CUDA(cudaMalloc(&ctx->table_arena, bytes));
-  OLAP_CUDA(cudaMemset(ctx->table_arena, 0, bytes));
   ctx->table_arena_bytes = bytes;
-  ctx->table_generation = 0;
-  return OLAP_OK;
-}
-static olap_status next_generations(olap_ctx* ctx, uint32_t n, uint32_t* first) {
-  if ((uint64_t)ctx->table_generation + n >= 0xFFFFFFF0ULL) {
-    OLAP_CUDA(cudaDeviceSynchronize());
-    OLAP_CUDA(cudaMemset(ctx->table_arena, 0, ctx->table_arena_bytes));
-    ctx->table_generation = 0;
-  }
-  *first = ctx->table_generation + 1;
-  ctx->table_generation += n;
   return OLAP_OK;
 }
 
@@ -348,16 +466,18 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
 
 static olap_status join_broadcast(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, const uint64_t* pk, uint64_t np, olap_pair* out,
                                   uint64_t max_matches, unsigned long long* d_count, cudaStream_t s) {
-  const uint64_t cap = pow2_at_least(std::max<uint64_t>(2 * nb, 1024));
-  OLAP_TRY(ensure_arena(ctx, cap * 16));
-  uint32_t gen;
-  OLAP_TRY(next_generations(ctx, 1, &gen));
-  uint4* table = (uint4*)ctx->table_arena;
-  build_kernel<<<grid_rows(ctx, nb, kBuildThreads * 4, 8), kBuildThreads, 0, s>>>(bk, nullptr, 0, nb, table, cap - 1, gen);
+  const uint64_t nbk = std::max<uint64_t>(nb, 64);  // one 2-slot bucket per build row: load factor 0.5
+  OLAP_TRY(ensure_arena(ctx, nbk * 32));
+  Bucket* table = (Bucket*)ctx->table_arena;
+  OLAP_CUDA(cudaMemsetAsync(table, 0, nbk * 32, s));
+  build_kernel<<<grid_rows(ctx, nb, kBuildThreads, 16), kBuildThreads, 0, s>>>(bk, nullptr, 0, nb, table, nbk, 0);
   phase_mark(ctx, s, "build");
-  probe_kernel<<<grid_rows(ctx, np, kProbeTile, 4), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, table, cap - 1, gen, out, max_matches, d_count);
+  if (aligned32(pk))
+    probe_kernel<true><<<grid_rows(ctx, np, kProbeTile, 8), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, table, nbk, 0, out, max_matches, d_count);
+  else
+    probe_kernel<false><<<grid_rows(ctx, np, kProbeTile, 8), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, table, nbk, 0, out, max_matches, d_count);
   phase_mark(ctx, s, "probe");
-  count_launch(ctx, 2);
+  count_launch(ctx, 3);
   OLAP_CUDA(cudaGetLastError());
   return OLAP_OK;
 }
@@ -386,11 +506,9 @@ static olap_status join_radix(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, co
   memset(&a, 0, sizeof(a));
   a.bits = bits;
   a.keys = bk; a.n = nb; a.hist = hist_b; a.out_keys = pkb; a.out_ids = pib;
-  OLAP_TRY(run_partition(ctx, a, 0, true, beg, s));
-  phase_mark(ctx, s, "partition_build");
+  OLAP_TRY(run_partition(ctx, a, 0, true, beg, s, "hist_build", "partition_build"));
   a.keys = pk; a.n = np; a.hist = hist_p; a.out_keys = pkp; a.out_ids = pip;
-  OLAP_TRY(run_partition(ctx, a, 0, true, beg + P + 1, s));
-  phase_mark(ctx, s, "partition_probe");
+  OLAP_TRY(run_partition(ctx, a, 0, true, beg + P + 1, s, "hist_probe", "partition_probe"));
 
   std::vector<uint32_t> h(2 * (P + 1));
   OLAP_CUDA(cudaMemcpyAsync(h.data(), beg, h.size() * 4, cudaMemcpyDeviceToHost, s));
@@ -399,13 +517,13 @@ static olap_status join_radix(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, co
   const uint32_t* hp = h.data() + P + 1;
   uint64_t max_part = 0;
   for (uint32_t p = 0; p < P; p++) max_part = std::max<uint64_t>(max_part, hb[p + 1] - hb[p]);
-  const uint64_t cap = pow2_at_least(std::max<uint64_t>(2 * max_part, 1024));
+  const uint64_t nbk = std::max<uint64_t>(max_part, 64);  // buckets per table: exactly 32 B per build row of the largest partition
   int S = (int)std::min<uint64_t>(ctx->streams.size(), env_u64("OLAP_JOIN_STREAMS", 3));
+  const uint64_t dbg = env_u64("OLAP_JOIN_DEBUG", 0);  // timing decomposition only: 1 skips probes, 2 skips builds, 4 marks every kernel
+  if (dbg & 4) S = 1;
   if (S < 1) S = 1;
   if (S > 8) S = 8;
-  OLAP_TRY(ensure_arena(ctx, (uint64_t)S * cap * 16));
-  uint32_t gen0;
-  OLAP_TRY(next_generations(ctx, P, &gen0));
+  OLAP_TRY(ensure_arena(ctx, (uint64_t)S * nbk * 32));
 
   // fork: tables of different partitions are built and probed on S side streams so their ramps and tails overlap
   OLAP_CUDA(cudaEventRecord(ctx->fork_ev, s));
@@ -415,12 +533,20 @@ static olap_status join_radix(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, co
     const uint64_t b0 = hb[p], b1 = hb[p + 1], p0 = hp[p], p1 = hp[p + 1];
     if (b1 == b0 || p1 == p0) continue;  // inner join: an empty side yields nothing
     const int k = p % S;
-    cudaStream_t st = ctx->streams[k];
-    uint4* table = (uint4*)ctx->table_arena + (uint64_t)k * cap;
-    build_kernel<<<grid_rows(ctx, b1 - b0, kBuildThreads * 4, 8), kBuildThreads, 0, st>>>(pkb, pib, b0, b1, table, cap - 1, gen0 + p);
-    probe_kernel<<<grid_rows(ctx, p1 - p0, kProbeTile, 4), kProbeThreads, 0, st>>>(pkp, pip, p0, p1, table, cap - 1, gen0 + p, out, max_matches,
-                                                                                d_count);
-    launches += 2;
+    cudaStream_t st = (dbg & 4) ? s : ctx->streams[k];
+    Bucket* table = (Bucket*)ctx->table_arena + (uint64_t)k * nbk;
+    const uint64_t tb = std::max<uint64_t>(b1 - b0, 64);  // this partition's table: one bucket per build row
+    if (!(dbg & 2)) {
+      OLAP_CUDA(cudaMemsetAsync(table, 0, tb * 32, st));
+      if (dbg & 4) phase_mark(ctx, st, "p_clear");
+      build_kernel<<<grid_rows(ctx, b1 - b0, kBuildThreads, 16), kBuildThreads, 0, st>>>(pkb, pib, b0, b1, table, tb, bits);
+      if (dbg & 4) phase_mark(ctx, st, "p_build");
+    }
+    if (!(dbg & 1))
+      probe_kernel<true><<<grid_rows(ctx, p1 - p0, kProbeTile, 8), kProbeThreads, 0, st>>>(pkp, pip, p0, p1, table, tb, bits, out, max_matches,
+                                                                                        d_count);
+    if (dbg & 4) phase_mark(ctx, st, "p_probe");
+    launches += 3;
   }
   count_launch(ctx, launches);
   for (int k = 0; k < S; k++) {

@@ -54,9 +54,8 @@ def test_filter_conjunction_columns_f64_and_unaligned(ctx):
                  g.Term(df.ptr + 8 * off, g.LT, 600.25, type=g.F64)]
         cnt, mask, sel = ctx.filter(terms, n)
         aa, bb, ff = a[off:off + n], b[off:off + n], f[off:off + n]
-        exp = O.filter_mask_i64(aa, O.GT, literal=1 << 19)
-        O.lib().orc_mask_and(exp.ctypes.data, O.filter_mask_i64(aa, O.LE, rhs=bb).ctypes.data, n)
-        exp &= (ff < 600.25).astype(np.uint8)
+        # conjunction = AND of the term masks (SURVEY.md 8(c) completion rule)
+        exp = O.filter_mask_i64(aa, O.GT, literal=1 << 19) & O.filter_mask_i64(aa, O.LE, rhs=bb) & (ff < 600.25).astype(np.uint8)
         assert (mask.to_numpy() == exp).all() and cnt == exp.sum()
         assert (sel.to_numpy(cnt) == O.mask_to_indices(exp)).all()
 
