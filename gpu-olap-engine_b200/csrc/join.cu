@@ -24,7 +24,8 @@ namespace olap {
 constexpr int kPartThreads = 512;
 constexpr int kPartTile = 4096;          // rows staged per CTA iteration (8 per thread)
 constexpr int kMaxPartBits = 8;          // <= 256 partitions per pass
-constexpr int kMaxPay = 4;               // 8-byte payload columns carried along (group-by)
+constexpr int kMaxPay = 4;
+constexpr uint64_t kShuffleSalt = 0x5bd1e9955bd1e995ULL;  // multi-GPU destination hash = mix64(key ^ salt)               // 8-byte payload columns carried along (group-by)
 
 struct PartArgs {
   const uint64_t* keys;
@@ -32,6 +33,7 @@ struct PartArgs {
   const uint64_t* pay_in[kMaxPay];
   uint64_t n, chunk;                     // rows, rows per CTA (multiple of kPartTile)
   int bits;
+  uint64_t salt;                         // xor-ed into the key before hashing: the multi-GPU shuffle uses bits independent of the local join's
   uint32_t* hist;                        // [P][gridDim.x]: counts, then exclusive offsets after the scan
   uint64_t* out_keys;
   uint32_t* out_ids;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(kPartThreads) part_hist_kernel(PartArgs a) {
     uint64_t k[4]; bool ok[4];
     load_keys4(a, i, end, k, ok);
 #pragma unroll
-    for (int e = 0; e < 4; e++) if (ok[e]) atomicAdd(&s_h[mix64(k[e]) >> sh], 1u);
+    for (int e = 0; e < 4; e++) if (ok[e]) atomicAdd(&s_h[mix64(k[e] ^ a.salt) >> sh], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < P; i += kPartThreads) a.hist[(uint64_t)i * gridDim.x + blockIdx.x] = s_h[i];
@@ -137,7 +139,7 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : 2) partition_kern
     for (int j = 0; j < 2; j++)
 #pragma unroll
       for (int e = 0; e < 4; e++)
-        if (ok[j][e]) { part[j][e] = (uint32_t)(mix64(k[j][e]) >> sh); rank[j][e] = atomicAdd(&s_cnt[part[j][e]], 1u); }
+        if (ok[j][e]) { part[j][e] = (uint32_t)(mix64(k[j][e] ^ a.salt) >> sh); rank[j][e] = atomicAdd(&s_cnt[part[j][e]], 1u); }
     __syncthreads();
     // phase 2: exclusive scan of the tile histogram; advance this CTA's global cursors
     uint32_t c = 0, inc = 0;
@@ -615,8 +617,8 @@ olap_status olap_hash_join_i64(olap_ctx* ctx, const int64_t* build_keys, uint64_
   return OLAP_OK;
 }
 
-olap_status olap_radix_partition_i64(olap_ctx* ctx, const int64_t* keys, const uint32_t* row_ids, uint64_t n_rows, int32_t bits,
-                                     int64_t* out_keys, uint32_t* out_row_ids, uint32_t* out_part_begin, void* stream) {
+static olap_status partition_api(olap_ctx* ctx, const int64_t* keys, const uint32_t* row_ids, uint64_t n_rows, int32_t bits, uint64_t salt,
+                                 int64_t* out_keys, uint32_t* out_row_ids, uint32_t* out_part_begin, void* stream) {
   OLAP_REQUIRE(ctx, "ctx is NULL");
   OLAP_REQUIRE(bits >= 1 && bits <= kMaxPartBits, "bits must be in [1, 8]");
   OLAP_REQUIRE(n_rows < 0xFFFFFFFFULL, "row ids are u32");
@@ -631,9 +633,24 @@ olap_status olap_radix_partition_i64(olap_ctx* ctx, const int64_t* keys, const u
   OLAP_TRY(sc.get<uint32_t>((uint64_t)P * ctx->sm_count * 2, &hist));
   PartArgs a;
   memset(&a, 0, sizeof(a));
-  a.bits = bits; a.keys = (const uint64_t*)keys; a.ids_in = row_ids; a.n = n_rows; a.hist = hist;
+  a.bits = bits; a.salt = salt; a.keys = (const uint64_t*)keys; a.ids_in = row_ids; a.n = n_rows; a.hist = hist;
   a.out_keys = (uint64_t*)out_keys; a.out_ids = out_row_ids;
   return run_partition(ctx, a, 0, true, out_part_begin, s);
+}
+
+olap_status olap_radix_partition_i64(olap_ctx* ctx, const int64_t* keys, const uint32_t* row_ids, uint64_t n_rows, int32_t bits,
+                                     int64_t* out_keys, uint32_t* out_row_ids, uint32_t* out_part_begin, void* stream) {
+  return partition_api(ctx, keys, row_ids, n_rows, bits, 0, out_keys, out_row_ids, out_part_begin, stream);
+}
+
+olap_status olap_shuffle_partition_i64(olap_ctx* ctx, const int64_t* keys, const uint32_t* row_ids, uint64_t n_rows, int32_t bits,
+                                       int64_t* out_keys, uint32_t* out_row_ids, uint32_t* out_part_begin, void* stream) {
+  return partition_api(ctx, keys, row_ids, n_rows, bits, kShuffleSalt, out_keys, out_row_ids, out_part_begin, stream);
+}
+
+uint32_t olap_shuffle_dest_of(int64_t key, int32_t bits) {
+  if (bits <= 0) return 0;
+  return (uint32_t)(mix64((uint64_t)key ^ kShuffleSalt) >> (64 - bits));
 }
 
 }  // extern "C"

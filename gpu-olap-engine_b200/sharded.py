@@ -1,0 +1,307 @@
+"""Key-sharded hash join and group-by across the GPUs of one box: one process per GPU, torch.distributed (NCCL over
+NVLink 5 / NVSwitch) for the exchange, the sm_100a kernels behind the C ABI for everything else.
+
+The reference has no multi-GPU path ("No multi-GPU support yet", README.md:414); this follows SURVEY.md 8(e):
+  join      dest = top bits of mix64(key ^ salt)  ->  olap_shuffle_partition_i64 writes per-destination contiguous send
+            regions (no staging copy)  ->  count exchange  ->  all-to-all of (key, source row id)  ->  independent local
+            joins (identical to the 1-GPU path; the salt keeps the destination bits independent of the local radix bits)
+  group-by  local pre-aggregation (cuts the volume to <= G tuples per GPU)  ->  all-to-all of (key, partials) by the
+            same destination hash  ->  per-shard merge (SUM/COUNT add, MIN/MAX combine, AVG carried as (sum, count))
+Output stays sharded.  Row ids are (source rank, local row id): pairs index the receive buffers, whose per-source
+segments and shipped local ids give the global id (see global_pairs).
+
+The device operations are injected (``ops``) so that the exchange logic runs unchanged under gloo on CPU in tests/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .core import AVG, COUNT, F64, I64, JOIN_AUTO, MAX, MIN, SUM, AggSpec
+
+
+def _log2(world: int) -> int:
+    bits = int(math.log2(world))
+    if (1 << bits) != world:
+        raise ValueError("key sharding needs a power-of-two number of ranks")
+    return bits
+
+
+class DeviceOps:
+    """GPU implementation of the operations the sharded operators need: C-ABI calls on torch CUDA tensors."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.device = torch.device("cuda", ctx.device)
+
+    def _stream(self):
+        # torch's default stream is the legacy stream (handle 0); the C ABI reads NULL as "the context's stream 0",
+        # so pass cudaStreamLegacy (0x1) explicitly to stay ordered with torch's own work
+        return torch.cuda.current_stream(self.device).cuda_stream or 1
+
+    def empty(self, n, dtype):
+        return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
+
+    def shuffle_partition(self, keys, n, bits):
+        """(keys sorted by destination rank, their local row ids, begin offsets[2^bits + 1])."""
+        out_k = self.empty(n, torch.int64); out_i = self.empty(n, torch.int32)
+        begin = self.empty((1 << bits) + 1, torch.int32)
+        if bits == 0:
+            out_k.copy_(keys[:n]); out_i.copy_(torch.arange(n, dtype=torch.int32, device=self.device))
+            return out_k, out_i, [0, n]
+        _lib.check(self.lib.olap_shuffle_partition_i64(self.ctx.handle, keys.data_ptr(), None, n, bits, out_k.data_ptr(), out_i.data_ptr(),
+                                                       begin.data_ptr(), self._stream()))
+        return out_k, out_i, begin.tolist()
+
+    def hash_join(self, build_keys, nb, probe_keys, npb, max_matches, strategy=JOIN_AUTO):
+        pairs = self.empty(2 * max(max_matches, 1), torch.int32)
+        cnt = C.c_uint64()
+        st = self.lib.olap_hash_join_i64(self.ctx.handle, build_keys.data_ptr() if nb else None, nb, probe_keys.data_ptr() if npb else None, npb,
+                                         pairs.data_ptr(), max_matches, None, C.byref(cnt), strategy, self._stream())
+        _lib.check(st)
+        return cnt.value, pairs
+
+    def group_by(self, keys, n, cols, funcs, types, hint):
+        """Returns (n_groups, keys[G], [col[G] as int64 bit patterns])."""
+        na = len(funcs)
+        cap = max(int(hint), 1)
+        if keys is not None and n == 0:   # grouped aggregation of nothing: no groups (a NULL key pointer would mean "global")
+            return 0, self.empty(0, torch.int64), [self.empty(0, torch.int64) for _ in range(na)]
+        kp = None if keys is None else keys.data_ptr()
+        while True:
+            ok = self.empty(cap, torch.int64); oa = self.empty(max(na, 1) * cap, torch.int64)
+            specs = (AggSpec * max(na, 1))(*[AggSpec(c.data_ptr() if c is not None and n else None, f, t) for c, f, t in zip(cols, funcs, types)])
+            g = C.c_uint64()
+            st = self.lib.olap_group_by_i64(self.ctx.handle, kp, specs, na, n, hint,
+                                            None, 0, ok.data_ptr(), oa.data_ptr(), cap, None, C.byref(g), self._stream())
+            if st == _lib.ERR_CAPACITY:
+                cap = int(g.value); continue
+            _lib.check(st)
+            return g.value, ok[:g.value], [oa[i * cap:i * cap + g.value] for i in range(na)]
+
+
+class ShardedExchange:
+    """all-to-all of variable-size per-destination segments (the only collective on the path)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.bits = _log2(self.world)
+        self.bytes_sent = 0
+
+    def exchange_counts(self, send_counts):
+        if self.world == 1:
+            return list(send_counts)
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        s = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        r = torch.empty_like(s)
+        dist.all_to_all_single(r, s, group=self.group)
+        return r.tolist()
+
+    def all_to_all(self, tensor, send_counts, recv_counts):
+        if self.world == 1:
+            return tensor
+        out = torch.empty(sum(recv_counts), dtype=tensor.dtype, device=tensor.device)
+        dist.all_to_all_single(out, tensor, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=self.group)
+        self.bytes_sent += (sum(send_counts) - send_counts[self.rank]) * tensor.element_size()
+        return out
+
+
+class ShardedJoin:
+    """GpuHashJoin across ranks.  join() returns a dict describing this rank's shard of the result."""
+
+    def __init__(self, ops, group=None):
+        self.ops = ops
+        self.x = ShardedExchange(group)
+
+    def shuffle(self, keys, n):
+        pk, pid, begin = self.ops.shuffle_partition(keys, n, self.x.bits)
+        send = [begin[p + 1] - begin[p] for p in range(self.x.world)]
+        recv = self.x.exchange_counts(send)
+        rk = self.x.all_to_all(pk, send, recv)
+        ri = self.x.all_to_all(pid, send, recv)
+        return rk, ri, recv
+
+    def join(self, build_keys, n_build, probe_keys, n_probe, max_matches=None, strategy=JOIN_AUTO):
+        bk, bi, brecv = self.shuffle(build_keys, n_build)   # build side first: tables can be built while probes arrive
+        pk, pi, precv = self.shuffle(probe_keys, n_probe)
+        nb, npb = int(bk.numel()), int(pk.numel())
+        mm = max_matches if max_matches is not None else max(npb, 1)
+        count, pairs = self.ops.hash_join(bk, nb, pk, npb, mm, strategy)
+        return {"count": count, "pairs": pairs, "build_ids": bi, "build_recv": brecv, "probe_ids": pi, "probe_recv": precv,
+                "n_build_local": nb, "n_probe_local": npb}
+
+    @staticmethod
+    def global_pairs(res, build_rank_offsets, probe_rank_offsets):
+        """Translate (receive-buffer positions) into global (left_row, right_row) ids; int64 tensor [count, 2]."""
+        k = int(res["count"])
+        pairs = res["pairs"][:2 * k].view(-1, 2).to(torch.int64) & 0xFFFFFFFF
+
+        def to_global(pos, ids, recv, offs):
+            bounds = torch.tensor(np.cumsum([0] + list(recv)), device=pos.device)
+            src = torch.bucketize(pos.contiguous(), bounds[1:], right=True)
+            return torch.tensor(list(offs), device=pos.device, dtype=torch.int64)[src] + (ids.to(torch.int64) & 0xFFFFFFFF)[pos]
+
+        left = to_global(pairs[:, 0], res["build_ids"], res["build_recv"], build_rank_offsets)
+        right = to_global(pairs[:, 1], res["probe_ids"], res["probe_recv"], probe_rank_offsets)
+        return torch.stack([left, right], 1)
+
+
+class ShardedGroupBy:
+    """GpuAggregate across ranks: local partial aggregates, key-sharded exchange of the partials, per-shard merge."""
+
+    def __init__(self, ops, group=None):
+        self.ops = ops
+        self.x = ShardedExchange(group)
+
+    def group_by(self, keys, n, cols, funcs, types, n_groups_hint):
+        # 1. local pre-aggregation.  Partials are deduplicated: AVG(x) and SUM(x) share one sum, every COUNT/AVG shares the
+        #    one row count -- so the merge needs at most as many accumulators as the local pass
+        pf, pc, pt, index = [], [], [], {}
+
+        def partial(f, c, t):
+            key = ("count",) if f == COUNT else (f, id(c), t)
+            if key not in index:
+                index[key] = len(pf)
+                pf.append(f); pc.append(c); pt.append(I64 if f == COUNT else t)
+            return index[key]
+
+        plan = []
+        for c, f, t in zip(cols, funcs, types):
+            plan.append((partial(SUM, c, t), partial(COUNT, c, t)) if f == AVG else (partial(f, c, t), None))
+        g, gk, parts = self.ops.group_by(keys, n, pc, pf, pt, n_groups_hint)
+        # 2. route every partial row to the rank that owns its key
+        pk, pid, begin = self.ops.shuffle_partition(gk, g, self.x.bits)
+        send = [begin[p + 1] - begin[p] for p in range(self.x.world)]
+        recv = self.x.exchange_counts(send)
+        order = pid.to(torch.int64) & 0xFFFFFFFF
+        rk = self.x.all_to_all(pk, send, recv)
+        rparts = [self.x.all_to_all(p.index_select(0, order).contiguous(), send, recv) for p in parts]
+        # 3. merge: SUM/COUNT add, MIN/MAX combine
+        mf = [SUM if f in (SUM, COUNT) else f for f in pf]
+        m, mk, merged = self.ops.group_by(rk, int(rk.numel()), rparts, mf, pt, max(n_groups_hint, 1))
+        # 4. finalise
+        out = []
+        for (f, t), (i, ic) in zip(zip(funcs, types), plan):
+            if f == AVG:
+                s = merged[i].view(torch.float64) if t == F64 else merged[i].to(torch.float64)
+                cnt = merged[ic].to(torch.float64)
+                out.append(torch.where(cnt > 0, s / cnt, torch.zeros_like(s)))
+            else:
+                out.append(merged[i].view(torch.float64) if (t == F64 and f != COUNT) else merged[i])
+        return m, mk, out
+
+
+# ------------------------------------------------------------------------------------------------- bench (N > 1)
+def bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, ClockSampler):
+    """bench.py's N > 1 leg: weak scaling, per-GPU 2^log2_build unique-key build x 2^log2_probe FK probe over the GLOBAL
+    key domain; rows are contiguous-sharded (not pre-partitioned by key).  value = rows of all ranks / max-over-ranks time."""
+    ops = DeviceOps(ctx)
+    sj = ShardedJoin(ops)
+    # one stream for everything: torch's copies and NCCL collectives run on the context's stream 0, like the kernels
+    torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 0), device=ops.device))
+    nb, npb = 1 << args.log2_build, 1 << args.log2_probe
+    gnb = nb * world
+    dev = ops.device
+    build = ops.empty(nb, torch.int64); probe = ops.empty(npb, torch.int64)
+    ctx.generate(nb, 1, 3, gnb, row0=rank * nb, out=build.data_ptr())        # slice of a permutation of [0, world * 2^27)
+    ctx.generate(npb, 0, 33, gnb, row0=rank * npb, out=probe.data_ptr())     # uniform FK over the global build domain
+    ctx.synchronize()
+
+    def step():
+        return sj.join(build, nb, probe, npb, max_matches=int(npb * 1.25) + 4096)
+
+    for _ in range(args.warmup):
+        res = step()
+    total = torch.tensor([res["count"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(total)
+    assert int(total.item()) == npb * world, f"global join count {int(total.item())} != {npb * world}"
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sj.x.bytes_sent = 0
+    launches0 = ctx.launch_count()
+    dist.barrier(); torch.cuda.synchronize()
+    ev0.record()
+    t_shuffle = 0.0
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        bk, bi, brecv = sj.shuffle(build, nb)
+        pk, pi, precv = sj.shuffle(probe, npb)
+        e1.record()
+        cnt, pairs = ops.hash_join(bk, int(bk.numel()), pk, int(pk.numel()), int(npb * 1.25) + 4096)
+        torch.cuda.synchronize()
+        t_shuffle += e0.elapsed_time(e1)
+    ev1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1), t_shuffle], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms[0].item() / args.steps
+    shuffle_ms = ms[1].item() / args.steps
+    launches = ctx.launch_count() - launches0
+    phases = ctx.last_phase_times()
+    rows = (nb + npb) * world
+    sent = sj.x.bytes_sent / args.steps
+
+    # e2e: host (pinned) key columns -> H2D -> sharded join -> D2H of this rank's pairs
+    hb = torch.empty(nb, dtype=torch.int64).pin_memory(); hp = torch.empty(npb, dtype=torch.int64).pin_memory()
+    hb.copy_(build); hp.copy_(probe)
+    hout = torch.empty(2 * (int(npb * 1.25) + 4096), dtype=torch.int32).pin_memory()
+    db2, dp2 = torch.empty_like(build), torch.empty_like(probe)
+
+    def e2e_step():
+        db2.copy_(hb, non_blocking=True); dp2.copy_(hp, non_blocking=True)
+        r = sj.join(db2, nb, dp2, npb, max_matches=int(npb * 1.25) + 4096)
+        hout[:2 * r["count"]].copy_(r["pairs"][:2 * r["count"]], non_blocking=True)
+        torch.cuda.synchronize()
+        return r["count"]
+
+    e2e_step()
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 2))
+    out_rows = 0
+    for _ in range(n_e2e):
+        out_rows = e2e_step()
+    dist.barrier()
+    e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        part_ms = phases.get("partition_probe")
+        part_rows = res["n_probe_local"]
+        achieved = 20.0 * part_rows / (part_ms * 1e-3) / 1e9 if part_ms else None
+        line = {
+            "metric": "join rows/sec (|build|+|probe|)/time", "value": rows / (ms_step * 1e-3), "unit": "rows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"{world}-GPU key-sharded radix hash join, per GPU 2^{args.log2_build} unique-key build x 2^{args.log2_probe} FK probe "
+                                   f"(global 2^{args.log2_build}*{world} x 2^{args.log2_probe}*{world}), int64 keys, uniform, rows contiguous-sharded",
+                       "exchange": "NCCL all_to_all_single of (key i64, source row id u32), both sides", "l2": "inputs larger than L2",
+                       "parallelism": f"key-radix shards x{world}"},
+            "clocks": clocks,
+            "e2e": {"value": rows / (e2e.item() * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": (nb + npb) * 8 * world,
+                    "d2h_bytes_per_step": int(out_rows) * 8 * world, "ms_per_step": e2e.item(), "steps": n_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "partition_kernel<0,true> (probe side, local join)", "achieved": achieved, "peak": peak,
+                         "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None},
+            "nvlink": {"shuffle_ms_per_step": shuffle_ms, "bytes_out_per_rank_per_step": sent,
+                       "achieved_gbs_per_direction": sent / (shuffle_ms * 1e-3) / 1e9 if shuffle_ms else None, "peak_nominal_gbs": 900.0,
+                       "peak_measured_gbs": 770.0, "note": "shuffle phase includes the partition kernels that fill the send regions"},
+            "phases_ms": phases,
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

@@ -154,6 +154,15 @@ OLAP_API olap_status olap_radix_partition_i64(olap_ctx* ctx, const int64_t* keys
 /* the partition a key lands in (host helper for tests) */
 OLAP_API uint32_t olap_partition_of(int64_t key, int32_t bits);
 
+/* Multi-GPU key sharding (no reference analogue: README.md:414 "No multi-GPU support yet").  Same kernel as
+ * olap_radix_partition_i64 but the destination (one of 2^bits ranks) comes from mix64(key ^ salt), independent of
+ * the bits the local join partitions on.  Partition p is the contiguous send region for rank p, so the output feeds
+ * an NCCL all-to-all (torch.distributed.all_to_all_single) with no staging copy.                                 */
+OLAP_API olap_status olap_shuffle_partition_i64(olap_ctx* ctx, const int64_t* keys, const uint32_t* row_ids, uint64_t n_rows,
+                                                int32_t bits, int64_t* out_keys, uint32_t* out_row_ids, uint32_t* out_part_begin,
+                                                void* stream);
+OLAP_API uint32_t olap_shuffle_dest_of(int64_t key, int32_t bits);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Aggregation.  Replaces AggregateParams/AggregateSpec/AggregateKernel::aggregate
  * (gpu-kernel-compiler/src/aggregate_kernel.rs:37-125) and hash_aggregate_kernel (join_kernels.cuh:216-240).

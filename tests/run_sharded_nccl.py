@@ -1,0 +1,63 @@
+"""torchrun entry (one process per GPU, NCCL): parity of the key-sharded join and group-by against the oracle.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tests/run_sharded_nccl.py
+Used by tests/test_gpu_sharded.py when at least two GPUs are visible, and directly under `gpurun --gpus N`."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gpu_olap_engine_b200 as g  # noqa: E402
+import oracle as O  # noqa: E402
+from gpu_olap_engine_b200 import sharded  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = g.Context(local, 0, 8)
+    ops = sharded.DeviceOps(ctx)
+    torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 0), device=ops.device))
+    dev = ops.device
+    for nb, npb, dom in [(200000, 900000, 150000), (1 << 21, 1 << 22, 1 << 22), (1000, 0, 10)]:
+        gb = O.gen_uniform_i64(nb * world, 11, dom); gp = O.gen_uniform_i64(npb * world, 12, dom)
+        sj = sharded.ShardedJoin(ops)
+        res = sj.join(torch.from_numpy(gb[rank * nb:(rank + 1) * nb].copy()).to(dev), nb,
+                      torch.from_numpy(gp[rank * npb:(rank + 1) * npb].copy()).to(dev), npb, max_matches=max(4 * npb, 16))
+        pairs = sharded.ShardedJoin.global_pairs(res, [r * nb for r in range(world)], [r * npb for r in range(world)]).cpu().numpy()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, pairs)
+        if rank == 0:
+            allp = np.concatenate(gathered)
+            ec, ep = O.hash_join_i64(gb, gp, threads=4)
+            assert len(allp) == ec, (len(allp), ec)
+            assert (O.sort_pairs(allp.astype(np.uint32)) == O.sort_pairs(ep)).all()
+            print(f"sharded join ok: world={world} {nb}x{npb} per rank, {ec} pairs")
+    n = 500000
+    for G in (300, 200000):
+        k = O.gen_uniform_i64(n * world, 4, G); v = O.gen_uniform_i64(n * world, 5, 1 << 20); f = O.gen_dyadic_f64(n * world, 6, 1 << 20)
+        sl = slice(rank * n, (rank + 1) * n)
+        funcs = [O.SUM, O.COUNT, O.MIN, O.MAX, O.AVG, O.SUM, O.AVG]
+        cols = [torch.from_numpy(v[sl].copy()).to(dev)] * 5 + [torch.from_numpy(f[sl].copy().view(np.int64)).to(dev)] * 2
+        sg = sharded.ShardedGroupBy(ops)
+        m, mk, out = sg.group_by(torch.from_numpy(k[sl].copy()).to(dev), n, cols, funcs, [0] * 5 + [1] * 2, G)
+        shard = (mk.cpu().numpy(), [o.cpu().numpy() for o in out])
+        gs = [None] * world
+        dist.all_gather_object(gs, shard)
+        if rank == 0:
+            keys = np.concatenate([s[0] for s in gs]); order = np.argsort(keys)
+            ek, eres = O.group_by_i64(k, [v] * 5 + [f] * 2, funcs)
+            assert len(np.unique(keys)) == len(keys) and (keys[order] == ek).all()
+            for i, exp in enumerate(eres):
+                got = np.concatenate([s[1][i] for s in gs])[order]
+                assert (got == exp).all(), i
+            print(f"sharded group-by ok: world={world} G={G}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
