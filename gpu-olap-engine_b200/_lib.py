@@ -62,6 +62,23 @@ SIGNATURES = {
     "olap_group_by_i64": (i32, [vp, vp, C.POINTER(AggSpec), i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_agg_identity": (i64, [i32]),
     "olap_compute_launch_params": (None, [u64, C.POINTER(u32), C.POINTER(u32)]),
+    "olap_expr_column": (vp, [u64, C.c_char_p]),
+    "olap_expr_literal": (vp, [C.c_char_p]),
+    "olap_expr_binary": (vp, [vp, C.c_char_p, vp]),
+    "olap_expr_free": (None, [vp]),
+    "olap_plan_table_scan": (vp, [C.c_char_p, vp, C.POINTER(C.c_int64), i32]),
+    "olap_plan_filter": (vp, [vp, vp]),
+    "olap_plan_projection": (vp, [vp, pvp, i32]),
+    "olap_plan_hash_join": (vp, [vp, vp, pvp, i32, pvp, i32, i32]),
+    "olap_plan_aggregate": (vp, [vp, pvp, i32, C.POINTER(i32), pvp, i32]),
+    "olap_plan_free": (None, [vp]),
+    "olap_register_batch": (i32, [vp, C.c_char_p, vp, vp]),
+    "olap_drop_table": (i32, [vp, C.c_char_p]),
+    "olap_execute": (i32, [vp, vp, pvp]),
+    "olap_result_num_batches": (i32, [vp]),
+    "olap_result_num_rows": (i64, [vp, i32]),
+    "olap_result_export": (i32, [vp, i32, vp, vp]),
+    "olap_result_free": (None, [vp]),
     "olap_generate": (i32, [vp, vp, u64, i32, u64, u64, u64, vp]),
     "olap_set_profiling": (i32, [vp, i32]),
     "olap_last_phase_times": (i32, [vp, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_float)), C.POINTER(i32)]),

@@ -57,6 +57,9 @@ struct olap_ctx {
   uint64_t table_arena_bytes = 0;
   uint32_t table_generation = 0;
   cudaEvent_t fork_ev = nullptr, join_ev[8] = {};
+  // operator layer state (in-memory catalog of device-resident tables), owned by operators.cu
+  void* op_state = nullptr;
+  void (*op_state_free)(void*) = nullptr;
 
   cudaStream_t stream_of(void* s) const { return s ? (cudaStream_t)s : streams[0]; }
 };

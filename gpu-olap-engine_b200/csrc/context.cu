@@ -183,6 +183,7 @@ olap_status olap_ctx_destroy(olap_ctx* ctx) {
   if (!ctx) return OLAP_OK;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  if (ctx->op_state && ctx->op_state_free) { ctx->op_state_free(ctx->op_state); ctx->op_state = nullptr; }  // frees its pool buffers first
   for (auto& m : ctx->marks) cudaEventDestroy(m.second);
   if (ctx->table_arena) cudaFree(ctx->table_arena);
   for (auto& kv : ctx->live) cudaFree(kv.first);

@@ -187,6 +187,71 @@ OLAP_API int64_t olap_agg_identity(int32_t func);
 /* compute_launch_params (filter_kernel.rs:75-79, aggregate_kernel.rs:127-131), without the u32 truncation bug */
 OLAP_API void olap_compute_launch_params(uint64_t n_rows, uint32_t* grid, uint32_t* block);
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Operator API: the drop-in boundary proper.  Mirrors PhysicalPlan / PhysicalExpr / AggregateExpr
+ * (gpu-olap-core/src/physical_plan.rs:11-84) and executor::execute (gpu-olap-core/src/executor.rs:15-24) over
+ * the Arrow C Data Interface -- the same ArrowArray / ArrowSchema structs arrow-rs's `arrow::ffi` and pyarrow
+ * exchange, so the Rust side is a mechanical wrapper.  Builders take ownership of their
+ * children; olap_plan_free / olap_expr_free release a whole tree.
+ * ------------------------------------------------------------------------------------------------------- */
+#ifndef ARROW_C_DATA_INTERFACE
+#define ARROW_C_DATA_INTERFACE
+struct ArrowSchema {
+  const char* format; const char* name; const char* metadata; int64_t flags; int64_t n_children;
+  struct ArrowSchema** children; struct ArrowSchema* dictionary;
+  void (*release)(struct ArrowSchema*); void* private_data;
+};
+struct ArrowArray {
+  int64_t length; int64_t null_count; int64_t offset; int64_t n_buffers; int64_t n_children;
+  const void** buffers; struct ArrowArray** children; struct ArrowArray* dictionary;
+  void (*release)(struct ArrowArray*); void* private_data;
+};
+#endif
+
+typedef struct olap_expr olap_expr;
+typedef struct olap_plan olap_plan;
+typedef struct olap_result olap_result;
+
+/* JoinType, gpu-olap-core/src/logical_plan.rs:52-58; only Inner executes (README.md:410-411) */
+enum { OLAP_JOIN_INNER = 0, OLAP_JOIN_LEFT = 1, OLAP_JOIN_RIGHT = 2, OLAP_JOIN_FULL = 3 };
+
+/* PhysicalExpr::{Column{index,name}, Literal{value}, BinaryExpr{left,op,right}} (physical_plan.rs:66-75).  Columns
+ * resolve by name first, then by index (executor.rs:381-387); literals parse as i64, else f64 (:390-401).       */
+OLAP_API olap_expr* olap_expr_column(uint64_t index, const char* name);
+OLAP_API olap_expr* olap_expr_literal(const char* value);
+OLAP_API olap_expr* olap_expr_binary(olap_expr* left, const char* op, olap_expr* right);
+OLAP_API void olap_expr_free(olap_expr* e);
+
+/* PhysicalPlan::GpuTableScan{table_name, schema, projection} (physical_plan.rs:13-17).  Rows come from the batches
+ * registered under table_name (the in-memory cache of catalog.rs:83-87); with none registered the scan yields one
+ * EMPTY batch typed from `schema` exactly as execute_table_scan does (executor.rs:110-155).  schema may be NULL when
+ * the table is registered.  projection: column indices or NULL.                                               */
+OLAP_API olap_plan* olap_plan_table_scan(const char* table_name, const struct ArrowSchema* schema, const int64_t* projection,
+                                         int32_t n_projection);
+OLAP_API olap_plan* olap_plan_filter(olap_plan* input, olap_expr* predicate);                         /* GpuFilter     :20-23 */
+OLAP_API olap_plan* olap_plan_projection(olap_plan* input, olap_expr* const* exprs, int32_t n_exprs); /* GpuProjection :26-29 */
+OLAP_API olap_plan* olap_plan_hash_join(olap_plan* left, olap_plan* right, olap_expr* const* left_keys, int32_t n_left_keys,
+                                        olap_expr* const* right_keys, int32_t n_right_keys, int32_t join_type); /* GpuHashJoin :32-39 */
+/* GpuAggregate{input, group_by, aggr_exprs} (:52-57); aggr_exprs[i] = AggregateExpr::<func>{input} (:77-84) */
+OLAP_API olap_plan* olap_plan_aggregate(olap_plan* input, olap_expr* const* group_by, int32_t n_group_by, const int32_t* agg_funcs,
+                                        olap_expr* const* agg_inputs, int32_t n_aggs);
+OLAP_API void olap_plan_free(olap_plan* p);
+
+/* Catalog::get_table_data analogue: import one RecordBatch (struct-typed ArrowArray) into device memory and append
+ * it to table_name.  Numeric columns are widened to 8 bytes ON DEVICE, Utf8 becomes FNV-1a-64 as i64, nulls become 0
+ * (arrow-interop/src/record_batch_convert.rs:35-130).  The array is released after the copy.                   */
+OLAP_API olap_status olap_register_batch(olap_ctx* ctx, const char* table_name, struct ArrowArray* batch, struct ArrowSchema* schema);
+OLAP_API olap_status olap_drop_table(olap_ctx* ctx, const char* table_name);
+
+/* executor::execute(plan, config) -> Vec<RecordBatch> (executor.rs:15-24).  Results are exported as Arrow C Data
+ * (host memory owned by the exported array; its release callback frees it).                                    */
+OLAP_API olap_status olap_execute(olap_ctx* ctx, const olap_plan* plan, olap_result** out);
+OLAP_API int32_t olap_result_num_batches(const olap_result* r);
+OLAP_API int64_t olap_result_num_rows(const olap_result* r, int32_t batch);
+OLAP_API olap_status olap_result_export(olap_result* r, int32_t batch, struct ArrowArray* out_array, struct ArrowSchema* out_schema);
+OLAP_API void olap_result_free(olap_result* r);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Synthetic data on the device (counter-based splitmix64(seed, row); any shard can generate
  * its slice).  kind: 0 uniform i64 in [0, domain); 1 permutation of [0, domain) evaluated at row0 + i;

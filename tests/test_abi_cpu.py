@@ -1,0 +1,79 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/olap_b200.h declares (no
+compute calls without a GPU), host-only entry points answer, and the reference's boundary constants hold."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "olap_b200.h")).read()
+    return sorted(set(re.findall(r"OLAP_API[^;(]*?\b(olap_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    import gpu_olap_engine_b200 as g
+    lib = ctypes.CDLL(g.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 45
+    for s in syms:
+        getattr(lib, s)                       # AttributeError if the header declares something the library lacks
+    assert set(syms) == set(g._lib.SIGNATURES), set(syms) ^ set(g._lib.SIGNATURES)
+
+
+def test_reference_boundary_constants():
+    from gpu_olap_engine_b200.kernels import AggFunc, CmpOp, FilterKernel, JoinKernel, JoinStrategy, compute_launch_params
+    # join_kernel.rs:85-87
+    assert JoinKernel.choose_strategy(500_000) == JoinStrategy.BroadcastHashJoin
+    assert JoinKernel.choose_strategy(5_000_000) == JoinStrategy.RadixHashJoin
+    assert JoinKernel.choose_strategy(1_000_000) == JoinStrategy.BroadcastHashJoin and JoinKernel.choose_strategy(1_000_001) == JoinStrategy.RadixHashJoin
+    # aggregate_kernel.rs:139-143
+    assert (AggFunc.Sum.identity_value(), AggFunc.Min.identity_value(), AggFunc.Max.identity_value()) == (0, 2**63 - 1, -2**63)
+    assert AggFunc.Count.identity_value() == 0 and AggFunc.Avg.identity_value() == 0
+    # filter_kernel.rs:87-95
+    assert compute_launch_params(1024) == (4, 256) and FilterKernel.compute_launch_params(1) == (1, 256)
+    assert compute_launch_params(2**33)[0] == 2**33 // 256      # no `n_rows as u32` truncation (Appendix B #8)
+    assert [int(c) for c in CmpOp] == [0, 1, 2, 3, 4, 5]        # codegen.rs:10
+
+
+def test_engine_config_defaults():
+    import gpu_olap_engine_b200 as g
+    c = g.EngineConfig()                                         # lib.rs:33-43
+    assert (c.max_gpu_memory, c.num_streams, c.use_unified_memory, c.batch_size, c.enable_cache) == (8 << 30, 8, True, 1 << 20, True)
+
+
+def test_host_side_hash_helpers_and_plan_builders():
+    import gpu_olap_engine_b200 as g
+    L = g.load()
+    parts = [L.olap_partition_of(k, 8) for k in range(10000)]
+    assert min(parts) >= 0 and max(parts) <= 255 and len(set(parts)) == 256
+    dest = [L.olap_shuffle_dest_of(k, 3) for k in range(10000)]
+    assert set(dest) == set(range(8))
+    agree = sum(1 for k in range(10000) if L.olap_shuffle_dest_of(k, 3) == L.olap_partition_of(k, 3))
+    assert 800 < agree < 1700                                    # destination bits are independent of the local radix bits
+    e = L.olap_expr_binary(L.olap_expr_column(0, b"a"), b">", L.olap_expr_literal(b"10"))
+    p = L.olap_plan_filter(L.olap_plan_table_scan(b"t", None, None, -1), e)
+    assert p
+    L.olap_plan_free(p)
+    assert not L.olap_plan_filter(None, None)
+
+
+def test_context_creation_fails_loudly_without_gpu():
+    import torch
+    import gpu_olap_engine_b200 as g
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(g.OlapError):
+        g.Context(0)
+
+
+def test_oracle_is_not_imported_by_the_product():
+    pkg = os.path.join(ROOT, "gpu-olap-engine_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f

@@ -1,0 +1,170 @@
+"""Operator-level parity: PhysicalPlan trees built the way a reference user builds them, executed through the C-ABI
+operator layer (olap_execute) on the GPU and compared with the oracle's restatement of executor.rs."""
+import numpy as np
+import pyarrow as pa
+import pytest
+
+import oracle as O
+from oracle import executor as OX
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ex(ctx):
+    import gpu_olap_engine_b200 as g
+    return g.GpuExecutor(g.EngineConfig(), ctx=ctx)
+
+
+def col(name, index=0):
+    import gpu_olap_engine_b200 as g
+    return g.Column(index, name)     # the planner always sets index 0 and resolves by name (physical_plan.rs:199)
+
+
+def lit(v):
+    import gpu_olap_engine_b200 as g
+    return g.Literal(str(v))
+
+
+def run_both(ex, plan, tables, sort_by=None, exact=True):
+    for name, rbs in tables.items():
+        ex.drop_table(name)
+        if rbs:
+            ex.register_table(name, rbs)
+    got = ex.execute(plan)
+    exp = OX.execute(plan, tables)
+    assert len(got) == len(exp)
+    for g_rb, (names, cols, n) in zip(got, exp):
+        assert g_rb.num_rows == n and g_rb.schema.names == names
+        gcols = [g_rb.column(i).to_numpy(zero_copy_only=False) for i in range(g_rb.num_columns)]
+        if sort_by is not None and n:
+            keys = [names.index(s) for s in sort_by]
+            go = np.lexsort([gcols[k] for k in reversed(keys)]); eo = np.lexsort([cols[k] for k in reversed(keys)])
+            gcols = [c[go] for c in gcols]; cols = [c[eo] for c in cols]
+        for name, gc, ec in zip(names, gcols, cols):
+            assert gc.dtype == ec.dtype, name
+            assert (gc == ec).all() if exact else np.allclose(gc, ec, rtol=1e-12, atol=0), name
+    return got
+
+
+def make_sales(n, seed, batches=3):
+    k = O.gen_uniform_i64(n, seed, 1000); vi = O.gen_uniform_i64(n, seed + 1, 1 << 20); vf = O.gen_dyadic_f64(n, seed + 2, 1 << 20)
+    q = O.gen_uniform_i64(n, seed + 3, 50).astype(np.int32)
+    tbl = pa.table({"k": k, "v_i": vi, "v_f": vf, "qty": q})
+    edges = np.linspace(0, n, batches + 1).astype(int)
+    return [tbl.slice(a, b - a).combine_chunks().to_batches()[0] for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+
+def test_reference_filter_unit_vector(ex):
+    # gpu-olap-core/src/executor.rs:553-570
+    import gpu_olap_engine_b200 as g
+    tables = {"t": [pa.record_batch({"a": pa.array([5, 15, 25], pa.int64())})]}
+    plan = g.GpuFilter(g.GpuTableScan("t"), g.BinaryExpr(col("a"), ">", lit(10)))
+    got = run_both(ex, plan, tables)
+    assert got[0].column(0).to_pylist() == [15, 25]
+
+
+@pytest.mark.parametrize("op", ["=", "==", "!=", "<>", ">", ">=", "<", "<=", "~"])
+def test_filter_ops_scan_and_drop_empty(ex, op):
+    import gpu_olap_engine_b200 as g
+    tables = {"sales": make_sales(30000, 1)}
+    run_both(ex, g.GpuFilter(g.GpuTableScan("sales"), g.BinaryExpr(col("qty"), op, lit(7))), tables)
+    # literal on the left, column vs column, non-Int64 comparison falls through to "pass all" (executor.rs:471-472)
+    run_both(ex, g.GpuFilter(g.GpuTableScan("sales"), g.BinaryExpr(lit(500), op, col("k"))), tables)
+    run_both(ex, g.GpuFilter(g.GpuTableScan("sales"), g.BinaryExpr(col("k"), op, col("qty"))), tables)
+    run_both(ex, g.GpuFilter(g.GpuTableScan("sales"), g.BinaryExpr(col("k"), op, col("v_f"))), tables)
+
+
+def test_filter_conjunction_and_f64_extension(ex):
+    import gpu_olap_engine_b200 as g
+    tables = {"sales": make_sales(50000, 2)}
+    pred = g.BinaryExpr(g.BinaryExpr(col("v_i"), ">", lit(1 << 19)), "AND", g.BinaryExpr(g.BinaryExpr(col("k"), "<", lit(700)), "AND",
+                                                                                         g.BinaryExpr(col("v_f"), "<=", lit("512.25"))))
+    run_both(ex, g.GpuFilter(g.GpuTableScan("sales"), pred), tables)
+
+
+def test_projection_names_literals_and_arithmetic(ex):
+    import gpu_olap_engine_b200 as g
+    tables = {"sales": make_sales(20000, 3)}
+    exprs = [col("k"), lit(42), g.BinaryExpr(col("v_i"), "+", col("k")), g.BinaryExpr(g.BinaryExpr(col("v_i"), "*", lit(3)), "-", col("qty")),
+             g.BinaryExpr(col("v_i"), "/", g.BinaryExpr(col("k"), "-", lit(500))), g.BinaryExpr(col("k"), "%", lit(3)),
+             g.BinaryExpr(col("v_f"), "*", lit("0.5"))]
+    got = run_both(ex, g.GpuProjection(g.GpuTableScan("sales", projection=[0, 1, 2, 3]), exprs), tables)
+    assert got[0].schema.names[:3] == ["k", "lit(42)", "(v_i + k)"]
+
+
+def test_empty_scan_uses_plan_schema(ex):
+    # execute_table_scan (executor.rs:110-155): no data -> one empty batch; float fields Float64, everything else Int64
+    import gpu_olap_engine_b200 as g
+    schema = pa.schema([("a", pa.int32()), ("b", pa.float32()), ("c", pa.string())])
+    got = run_both(ex, g.GpuTableScan("nothing_here", schema=schema, projection=[1, 0]), {"nothing_here": []})
+    assert got[0].num_rows == 0 and got[0].schema.types == [pa.float64(), pa.int64()]
+
+
+def test_global_aggregate_is_the_reference_execution(ex):
+    import gpu_olap_engine_b200 as g
+    tables = {"sales": make_sales(100000, 4)}
+    aggs = [g.Sum(col("v_i")), g.Count(col("v_i")), g.Min(col("v_i")), g.Max(col("v_i")), g.Avg(col("v_i")), g.Sum(col("v_f")), g.Avg(col("qty")),
+            g.Sum(g.BinaryExpr(col("v_i"), "*", col("qty")))]
+    got = run_both(ex, g.GpuAggregate(g.GpuTableScan("sales"), [], aggs), tables)
+    assert all(t == pa.float64() for t in got[0].schema.types) and got[0].num_rows == 1   # executor.rs:347: everything Float64
+    # filter that removes every row, then aggregate: SUM 0, COUNT 0, AVG 0, MIN f64::MAX, MAX f64::MIN (executor.rs:310-345)
+    plan = g.GpuAggregate(g.GpuFilter(g.GpuTableScan("sales"), g.BinaryExpr(col("k"), "<", lit(-1))), [], aggs[:5])
+    got = run_both(ex, plan, tables)
+    assert got[0].to_pydict() == {"SUM(v_i)": [0.0], "COUNT(v_i)": [0.0], "MIN(v_i)": [np.finfo(np.float64).max],
+                                  "MAX(v_i)": [-np.finfo(np.float64).max], "AVG(v_i)": [0.0]}
+
+
+def test_filter_group_by_c1a_shape(ex):
+    # examples/rust_usage.rs shape (BASELINE config 1): WHERE v_i > 2^19 GROUP BY k  SUM / COUNT / MIN / MAX / AVG
+    import gpu_olap_engine_b200 as g
+    tables = {"sales": make_sales(1 << 20, 5, batches=4)}
+    plan = g.GpuAggregate(g.GpuFilter(g.GpuTableScan("sales"), g.BinaryExpr(col("v_i"), ">", lit(1 << 19))), [col("k")],
+                          [g.Sum(col("v_i")), g.Count(col("v_i")), g.Min(col("v_i")), g.Max(col("v_f")), g.Avg(col("v_f")), g.Sum(col("v_f"))])
+    got = run_both(ex, plan, tables, sort_by=["k"])
+    assert got[0].num_rows == 1000
+
+
+def test_hash_join_c1b_shape_materialised(ex):
+    # BASELINE config 1: 100 K build rows (left) joined with 1 M probe rows; output = left columns then right columns
+    import gpu_olap_engine_b200 as g
+    nb, npb = 100000, 1000000
+    left = pa.table({"id": O.gen_perm_i64(nb, 2, nb), "name_hash": O.gen_uniform_i64(nb, 8, 1 << 40), "w": O.gen_dyadic_f64(nb, 9, 1 << 10)})
+    right = pa.table({"cust": O.gen_uniform_i64(npb, 22, nb), "amount": O.gen_uniform_i64(npb, 23, 10000)})
+    tables = {"customers": left.to_batches(max_chunksize=40000), "orders": right.to_batches(max_chunksize=300000)}
+    plan = g.GpuHashJoin(g.GpuTableScan("customers"), g.GpuTableScan("orders"), [col("id")], [col("cust")], g.JoinType.Inner)
+    got = run_both(ex, plan, tables, sort_by=["cust", "amount", "id"])
+    assert got[0].num_rows == npb and got[0].schema.names == ["id", "name_hash", "w", "cust", "amount"]
+    # join feeding an aggregate (join -> group by), duplicates on the build side, one side empty
+    dup = pa.table({"id": O.gen_uniform_i64(5000, 3, 800), "x": O.gen_uniform_i64(5000, 4, 100)})
+    tables2 = {"customers": dup.to_batches(), "orders": right.slice(0, 50000).to_batches()}
+    plan2 = g.GpuAggregate(g.GpuHashJoin(g.GpuTableScan("customers"), g.GpuTableScan("orders"), [col("id")], [col("cust")]), [col("id")],
+                           [g.Count(col("amount")), g.Sum(g.BinaryExpr(col("amount"), "*", col("x")))])
+    run_both(ex, plan2, tables2, sort_by=["id"])
+    empty = g.GpuFilter(g.GpuTableScan("orders"), g.BinaryExpr(col("cust"), "<", lit(0)))
+    assert ex.execute(g.GpuHashJoin(g.GpuTableScan("customers"), empty, [col("id")], [col("cust")])) == []   # executor.rs:231-233
+
+
+def test_arrow_import_layout_rules(ex):
+    # record_batch_convert.rs:35-130: widening, u64 reinterpretation, nulls -> 0, Utf8 -> FNV-1a
+    import gpu_olap_engine_b200 as g
+    rb = pa.record_batch({"i8": pa.array([1, None, -3], pa.int8()), "u64": pa.array([2**64 - 1, 5, None], pa.uint64()),
+                          "f32": pa.array([1.5, None, -2.25], pa.float32()), "s": pa.array(["a", None, "foobar"])})
+    got = run_both(ex, g.GpuTableScan("mixed"), {"mixed": [rb]})
+    assert got[0].column("i8").to_pylist() == [1, 0, -3] and got[0].column("u64").to_pylist() == [-1, 5, 0]
+    assert got[0].column("s").to_pylist()[2] == np.uint64(0x85944171f73967e8).astype(np.int64)
+    sl = pa.record_batch({"a": pa.array(range(100), pa.int16())}).slice(10, 50)     # non-zero Arrow offset
+    run_both(ex, g.GpuTableScan("sliced"), {"sliced": [sl]})
+
+
+def test_operator_errors(ex):
+    import gpu_olap_engine_b200 as g
+    ex.drop_table("sales"); ex.register_table("sales", make_sales(1000, 6))
+    with pytest.raises(g.OlapError, match="not found"):
+        ex.execute(g.GpuProjection(g.GpuTableScan("sales"), [g.Column(99, "nope")]))
+    with pytest.raises(g.OlapError, match="Cannot parse literal"):
+        ex.execute(g.GpuProjection(g.GpuTableScan("sales"), [lit("abc")]))
+    with pytest.raises(g.OlapError, match="INNER"):
+        ex.execute(g.GpuHashJoin(g.GpuTableScan("sales"), g.GpuTableScan("sales"), [col("k")], [col("k")], g.JoinType.Left))
+    with pytest.raises(g.OlapError, match="not registered"):
+        ex.execute(g.GpuTableScan("missing"))
