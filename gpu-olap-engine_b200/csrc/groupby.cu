@@ -4,42 +4,65 @@
 // (kernels/join_kernels.cuh:216-240: direct addressing, SUM only, one global atomic per row).
 //
 // Regimes (chosen from n_groups_hint; a wrong hint costs speed, never correctness):
-//   no key      per-thread register accumulators -> warp shuffle -> one global atomic per CTA per cell
-//   shared      per-CTA open-addressing table in shared memory, replicated R times for tiny cardinalities so
-//               that smem-atomic contention stays low; rows whose key does not fit fall through to the global
-//               table; tables are merged into the global table at the end
-//   global      global open-addressing table (L2-resident up to ~1M groups), native 64-bit L2 atomics,
-//               read-before-atomic for MIN/MAX
-//   partitioned rows are radix-partitioned by key hash (join.cu's partitioner) so that every partition's groups
-//               fit the shared regime -- see group_by_partitioned below
+//   no key       per-thread register accumulators -> warp shuffle -> one global atomic per CTA per cell
+//   shared       per-CTA open-addressing table in shared memory, replicated R times for tiny cardinalities so that
+//                same-address smem-atomic contention stays low; rows whose key does not fit spill to the global table;
+//                tables are merged into the global table at the end
+//   partitioned  rows (key + distinct value columns, filter applied) are radix-partitioned by key hash with join.cu's
+//                write-combining partitioner, so that every partition's groups fit a shared-memory table (one CTA per
+//                partition, results written straight to the output) or, for very high cardinalities, an L2-resident
+//                global table reused partition after partition
+//   global       one global open-addressing table (native 64-bit L2 atomics, read-before-atomic MIN/MAX): the
+//                universal fallback (also the spill target of the other regimes)
 // Roofline: HBM; algorithmic bytes per row = 8 B key + 8 B per distinct value column (+ 8 B per predicate column).
 #include "common.cuh"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace olap {
 
 constexpr int kMaxCells = 8;
+constexpr int kMaxVcols = 6;
 constexpr uint64_t kEmptyKey = 0x8000000000000000ULL;  // INT64_MIN is the empty marker; the real key lives in slot `cap`
 
 enum CellOp : int8_t { ADD_I64 = 0, ADD_F64 = 1, MIN_I64 = 2, MAX_I64 = 3, MIN_F64 = 4, MAX_F64 = 5 };
+
+struct OutSpec {
+  int n_aggs;
+  int8_t func[16];
+  int8_t type[16];
+  int8_t cell[16];  // cell index feeding this aggregate (-1: count only)
+};
 
 struct GbParams {
   const uint64_t* keys;  // NULL: single global group
   uint64_t n;
   TermPack terms;
+  int n_vcols;                             // distinct value columns, each loaded once per row
+  const uint64_t* vcol[kMaxVcols];
   int n_cells;
-  const uint64_t* cell_col[kMaxCells];
   int8_t cell_op[kMaxCells];
+  int8_t cell_vcol[kMaxCells];
   // global table: SoA, cap + 1 entries each (the extra one holds key == INT64_MIN)
   uint64_t* g_keys;
   unsigned long long* g_count;
   uint64_t* g_cells;  // cell c at g_cells + c * (g_cap + 1)
   uint64_t g_cap;     // power of two
   uint32_t* g_overflow;
-  // shared regime
+  bool vec;           // keys and value columns are 32-byte aligned: 256-bit loads
+  // shared-memory tables
   uint32_t s_slots;   // power of two, per copy
   uint32_t s_copies;  // power of two
+  // partitioned input (keys / vcol point at the partitioned copies)
+  const uint32_t* part_begin;
+  uint32_t n_parts;
+  // direct output (partitioned regime)
+  OutSpec out;
+  int64_t* out_keys;
+  uint64_t* out_aggs;
+  uint64_t out_cap;
+  unsigned long long* out_n;
 };
 
 // order-preserving f64 <-> i64 (involution); lets MIN/MAX of doubles use integer atomics
@@ -86,7 +109,6 @@ __device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) {
   return v;
 }
 
-// atomic update of a global cell
 __device__ __forceinline__ void cell_atomic_global(int op, uint64_t* cell, uint64_t v) {
   switch (op) {
     case ADD_I64: atomicAdd((unsigned long long*)cell, (unsigned long long)v); break;
@@ -98,9 +120,18 @@ __device__ __forceinline__ void cell_atomic_global(int op, uint64_t* cell, uint6
       if ((long long)v > (long long)ld_cg_u64(cell)) atomicMax((long long*)cell, (long long)v);
   }
 }
+// Shared memory has no native 64-bit atomic add (ptxas emits an ATOMS.CAST.SPIN.64 loop that collapses under contention):
+// an i64 sum is kept as two 32-bit halves updated with native ATOMS.ADD, the carry detected from the returned low word.
 __device__ __forceinline__ void cell_atomic_shared(int op, uint64_t* cell, uint64_t v) {
   switch (op) {
-    case ADD_I64: atomicAdd((unsigned long long*)cell, (unsigned long long)v); break;
+    case ADD_I64: {
+      uint32_t* w = reinterpret_cast<uint32_t*>(cell);
+      const uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+      const uint32_t old = atomicAdd(w, lo);
+      const uint32_t carry = (uint32_t)(old + lo) < lo;
+      if (hi + carry) atomicAdd(w + 1, hi + carry);
+      break;
+    }
     case ADD_F64: atomicAdd((double*)cell, __longlong_as_double((long long)v)); break;
     case MIN_I64: case MIN_F64:
       if ((long long)v < *(volatile long long*)cell) atomicMin((long long*)cell, (long long)v);
@@ -110,56 +141,138 @@ __device__ __forceinline__ void cell_atomic_shared(int op, uint64_t* cell, uint6
   }
 }
 
-// find-or-insert in the global table; returns the slot, or ~0 when the table is full (overflow flag raised)
-__device__ __forceinline__ uint64_t global_slot(const GbParams& p, uint64_t key) {
-  if (key == kEmptyKey) return p.g_cap;
-  const uint64_t mask = p.g_cap - 1;
-  uint64_t s = mix64(key) & mask;
-  for (uint64_t probes = 0; probes <= mask; probes++) {
-    uint64_t k = ld_cg_u64(p.g_keys + s);
-    if (k == key) return s;
-    if (k == kEmptyKey) {
-      uint64_t old = atomicCAS((unsigned long long*)(p.g_keys + s), (unsigned long long)kEmptyKey, (unsigned long long)key);
-      if (old == kEmptyKey || old == key) return s;
-    }
-    s = (s + 1) & mask;
-  }
-  atomicExch(p.g_overflow, 1u);
-  return ~0ULL;
+// static-index pick from a small register array (a dynamic index would push the array to local memory)
+template <int NV>
+__device__ __forceinline__ uint64_t pick(const uint64_t (&v)[NV], int i) {
+  uint64_t r = v[0];
+#pragma unroll
+  for (int k = 1; k < NV; k++) r = (i == k) ? v[k] : r;
+  return r;
 }
 
-__device__ __forceinline__ void global_update_row(const GbParams& p, uint64_t key, const uint64_t* vals, const bool* valid) {
-  uint64_t s = global_slot(p, key);
+// find-or-insert in the global table; returns the slot, or ~0 when the table is full (overflow flag raised).
+// Warp-uniform loop: EVERY lane of the warp calls this (active = false for lanes without a row) and iterates until no
+// lane is pending, so the warp is converged again when it returns.  A per-lane `for (...) break` loop left the warps
+// split for the rest of the kernel (ncu: 2.8 active threads per instruction, 11x the instructions).
+__device__ __forceinline__ uint64_t global_slot(const GbParams& p, uint64_t key, bool active) {
+  const uint64_t mask = p.g_cap - 1;
+  uint64_t s = mix64(key) & mask, slot = ~0ULL, probes = 0;
+  bool pending = active;
+  if (pending && key == kEmptyKey) { slot = p.g_cap; pending = false; }
+  while (__any_sync(0xffffffffu, pending)) {
+    if (pending) {
+      const uint64_t k = ld_cg_u64(p.g_keys + s);
+      if (k == key) { slot = s; pending = false; }
+      else {
+        if (k == kEmptyKey) {
+          const uint64_t old = atomicCAS((unsigned long long*)(p.g_keys + s), (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (old == kEmptyKey || old == key) { slot = s; pending = false; }
+        }
+        if (pending) {
+          s = (s + 1) & mask;
+          if (++probes > mask) { atomicExch(p.g_overflow, 1u); pending = false; }
+        }
+      }
+    }
+  }
+  return slot;
+}
+
+template <int NV>
+__device__ __forceinline__ void global_update_row(const GbParams& p, uint64_t key, const uint64_t (&v)[NV], bool active) {
+  const uint64_t s = global_slot(p, key, active);
   if (s == ~0ULL) return;
   atomicAdd(p.g_count + s, 1ULL);
+#pragma unroll
+  for (int c = 0; c < kMaxCells; c++)
+    if (c < p.n_cells) {
+      bool valid;
+      const uint64_t x = cell_encode(p.cell_op[c], pick<NV>(v, p.cell_vcol[c]), valid);
+      if (valid) cell_atomic_global(p.cell_op[c], p.g_cells + (uint64_t)c * (p.g_cap + 1) + s, x);
+    }
+}
+
+// finalise one group into the output (COUNT, AVG = sum / count, f64 MIN/MAX decoding); slot layout aggregate_kernel.rs:98
+__device__ __forceinline__ void emit_group(const OutSpec& o, int64_t* out_keys, uint64_t* out_aggs, uint64_t out_cap, uint64_t g, int64_t key,
+                                           unsigned long long cnt, const uint64_t (&cells)[kMaxCells]) {
+  out_keys[g] = key;
 #pragma unroll 1
-  for (int c = 0; c < p.n_cells; c++)
-    if (valid[c]) cell_atomic_global(p.cell_op[c], p.g_cells + (uint64_t)c * (p.g_cap + 1) + s, vals[c]);
+  for (int a = 0; a < o.n_aggs; a++) {
+    uint64_t cell = 0;
+#pragma unroll
+    for (int c = 0; c < kMaxCells; c++) cell = (o.cell[a] == c) ? cells[c] : cell;
+    uint64_t r;
+    if (o.func[a] == OLAP_COUNT) r = cnt;
+    else if (o.func[a] == OLAP_AVG) {
+      const double s = o.type[a] == OLAP_F64 ? __longlong_as_double((long long)cell) : (double)(long long)cell;
+      r = (uint64_t)__double_as_longlong(cnt ? s / (double)cnt : 0.0);
+    } else if ((o.func[a] == OLAP_MIN || o.func[a] == OLAP_MAX) && o.type[a] == OLAP_F64) r = (uint64_t)f64_ord(cell);
+    else r = cell;
+    out_aggs[(uint64_t)a * out_cap + g] = r;
+  }
 }
 
 constexpr int kGbThreads = 512;
-constexpr int kGbRows = 4;  // rows per thread per iteration (independent loads in flight)
+constexpr int kGbRows = 4;  // rows per thread per iteration: all of their loads are in flight together
+
+// loads the keys and the distinct value columns of this thread's kGbRows CONSECUTIVE rows (row0 is a multiple of 4, so
+// one 256-bit evict-first load per column when the columns are 32-byte aligned), masks rows outside [begin, end), applies
+// the filter
+template <int NV, bool KEYED>
+__device__ __forceinline__ void load_rows(const GbParams& p, uint64_t row0, uint64_t begin, uint64_t end, uint64_t (&key)[kGbRows],
+                                          uint64_t (&v)[kGbRows][NV], bool (&pass)[kGbRows]) {
+  if (p.vec && row0 >= begin && row0 + 3 < end) {
+    if (KEYED) { const u64x4 k = ld_stream_u64x4(p.keys + row0); key[0] = k.a; key[1] = k.b; key[2] = k.c; key[3] = k.d; }
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      if (q < p.n_vcols) { const u64x4 x = ld_stream_u64x4(p.vcol[q] + row0); v[0][q] = x.a; v[1][q] = x.b; v[2][q] = x.c; v[3][q] = x.d; }
+      else { v[0][q] = v[1][q] = v[2][q] = v[3][q] = 0; }
+    }
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++) { pass[j] = true; if (!KEYED) key[j] = 0; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++) {
+      const uint64_t row = row0 + j;
+      pass[j] = row >= begin && row < end;
+      key[j] = (KEYED && pass[j]) ? ld_stream_u64(p.keys + row) : 0;
+#pragma unroll
+      for (int q = 0; q < NV; q++) v[j][q] = (pass[j] && q < p.n_vcols) ? ld_stream_u64(p.vcol[q] + row) : 0;
+    }
+  }
+  if (p.terms.n) {
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++)
+      if (pass[j]) pass[j] = eval_terms_row(p.terms, row0 + j);
+  }
+}
 
 // ------------------------------------------------------------------------------------------- no-key regime
+template <int NV>
 __global__ void __launch_bounds__(kGbThreads) gb_nokey_kernel(GbParams p) {
   uint64_t acc[kMaxCells];
   unsigned long long cnt = 0;
 #pragma unroll
   for (int c = 0; c < kMaxCells; c++) acc[c] = c < p.n_cells ? cell_identity(p.cell_op[c]) : 0;
-  const uint64_t stride = (uint64_t)gridDim.x * kGbThreads;
-  for (uint64_t row = blockIdx.x * (uint64_t)kGbThreads + threadIdx.x; row < p.n; row += stride) {
-    if (p.terms.n && !eval_terms_row(p.terms, row)) continue;
-    cnt++;
+  const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
+  for (uint64_t base = blockIdx.x * tile; base < p.n; base += (uint64_t)gridDim.x * tile) {
+    uint64_t key[kGbRows], v[kGbRows][NV];
+    bool pass[kGbRows];
+    load_rows<NV, false>(p, base + (uint64_t)threadIdx.x * kGbRows, 0, p.n, key, v, pass);
 #pragma unroll
-    for (int c = 0; c < kMaxCells; c++) {
-      if (c < p.n_cells) {
-        bool valid;
-        uint64_t v = cell_encode(p.cell_op[c], ld_stream_u64(p.cell_col[c] + row), valid);
-        if (valid) acc[c] = cell_combine(p.cell_op[c], acc[c], v);
-      }
+    for (int j = 0; j < kGbRows; j++) {
+      if (!pass[j]) continue;
+      cnt++;
+#pragma unroll
+      for (int c = 0; c < kMaxCells; c++)
+        if (c < p.n_cells) {
+          bool valid;
+          const uint64_t x = cell_encode(p.cell_op[c], pick<NV>(v[j], p.cell_vcol[c]), valid);
+          if (valid) acc[c] = cell_combine(p.cell_op[c], acc[c], x);
+        }
     }
   }
-  // warp reduce, then one atomic per warp (f64 sums: the order varies run to run; see DESIGN.md on f64 parity)
+  // warp reduce, then one atomic per CTA (f64 sums: the order varies run to run; see DESIGN.md on f64 parity)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -171,7 +284,8 @@ __global__ void __launch_bounds__(kGbThreads) gb_nokey_kernel(GbParams p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) {
     s_acc[warp][kMaxCells] = cnt;
-    for (int c = 0; c < p.n_cells; c++) s_acc[warp][c] = acc[c];
+#pragma unroll
+    for (int c = 0; c < kMaxCells; c++) s_acc[warp][c] = acc[c];
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -187,103 +301,155 @@ __global__ void __launch_bounds__(kGbThreads) gb_nokey_kernel(GbParams p) {
 }
 
 // ------------------------------------------------------------------------------------------- global regime
-__global__ void __launch_bounds__(kGbThreads) gb_global_kernel(GbParams p) {
+// begin/end: row range (whole input, or one partition of the partitioned copies)
+template <int NV>
+__global__ void __launch_bounds__(kGbThreads) gb_global_kernel(GbParams p, uint64_t begin, uint64_t end) {
   const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
-  for (uint64_t base = blockIdx.x * tile; base < p.n; base += (uint64_t)gridDim.x * tile) {
-    uint64_t key[kGbRows];
+  for (uint64_t base = (begin & ~3ULL) + blockIdx.x * tile; base < end; base += (uint64_t)gridDim.x * tile) {
+    uint64_t key[kGbRows], v[kGbRows][NV];
     bool pass[kGbRows];
+    load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, begin, end, key, v, pass);
 #pragma unroll
-    for (int j = 0; j < kGbRows; j++) {
-      uint64_t row = base + (uint64_t)j * kGbThreads + threadIdx.x;
-      pass[j] = row < p.n;
-      key[j] = pass[j] ? ld_stream_u64(p.keys + row) : 0;
-    }
-#pragma unroll
-    for (int j = 0; j < kGbRows; j++) {
-      uint64_t row = base + (uint64_t)j * kGbThreads + threadIdx.x;
-      if (pass[j] && p.terms.n) pass[j] = eval_terms_row(p.terms, row);
-      if (!pass[j]) continue;
-      uint64_t vals[kMaxCells];
-      bool valid[kMaxCells];
-#pragma unroll
-      for (int c = 0; c < kMaxCells; c++)
-        if (c < p.n_cells) vals[c] = cell_encode(p.cell_op[c], ld_stream_u64(p.cell_col[c] + row), valid[c]);
-      global_update_row(p, key[j], vals, valid);
-    }
+    for (int j = 0; j < kGbRows; j++) global_update_row<NV>(p, key[j], v[j], pass[j]);
   }
 }
 
-// ------------------------------------------------------------------------------------------- shared regime
-// Dynamic smem layout per copy: keys[s_slots + 1] | count[s_slots + 1] (u32) | cells[n_cells][s_slots + 1]
-__global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t slots1 = p.s_slots + 1, total = slots1 * p.s_copies;
-  uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* s_cells = s_keys + total;                                        // [c][copy][slot]
-  uint32_t* s_count = reinterpret_cast<uint32_t*>(s_cells + (uint64_t)p.n_cells * total);
-  for (uint32_t i = threadIdx.x; i < total; i += kGbThreads) {
-    s_keys[i] = kEmptyKey;
-    s_count[i] = 0;
-    for (int c = 0; c < p.n_cells; c++) s_cells[(uint64_t)c * total + i] = cell_identity(p.cell_op[c]);
+// ------------------------------------------------------------------------------------------- shared-memory tables
+// Dynamic smem layout: keys[total] | cells[n_cells][total] | count[total] (u32), total = (s_slots + 1) * s_copies
+struct SmemTable {
+  uint64_t* keys; uint64_t* cells; uint32_t* count; uint32_t slots1, total;
+};
+__device__ __forceinline__ SmemTable smem_table(const GbParams& p, unsigned char* raw) {
+  SmemTable t;
+  t.slots1 = p.s_slots + 1; t.total = t.slots1 * p.s_copies;
+  t.keys = reinterpret_cast<uint64_t*>(raw);
+  t.cells = t.keys + t.total;
+  t.count = reinterpret_cast<uint32_t*>(t.cells + (uint64_t)p.n_cells * t.total);
+  return t;
+}
+__device__ __forceinline__ void smem_table_clear(const GbParams& p, const SmemTable& t) {
+  for (uint32_t i = threadIdx.x; i < t.total; i += kGbThreads) {
+    t.keys[i] = kEmptyKey;
+    t.count[i] = 0;
+    for (int c = 0; c < p.n_cells; c++) t.cells[(uint64_t)c * t.total + i] = cell_identity(p.cell_op[c]);
   }
-  __syncthreads();
-  const uint32_t copy_base = (threadIdx.x & (p.s_copies - 1)) * slots1;
-  const uint32_t smask = p.s_slots - 1;
-  // leave a quarter of each copy free so that probe sequences stay short
-  const uint32_t max_probe = p.s_slots;
+}
 
-  const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
-  for (uint64_t base = blockIdx.x * tile; base < p.n; base += (uint64_t)gridDim.x * tile) {
-    uint64_t key[kGbRows];
-    bool pass[kGbRows];
-#pragma unroll
-    for (int j = 0; j < kGbRows; j++) {
-      uint64_t row = base + (uint64_t)j * kGbThreads + threadIdx.x;
-      pass[j] = row < p.n;
-      key[j] = pass[j] ? ld_stream_u64(p.keys + row) : 0;
-    }
-#pragma unroll
-    for (int j = 0; j < kGbRows; j++) {
-      uint64_t row = base + (uint64_t)j * kGbThreads + threadIdx.x;
-      if (pass[j] && p.terms.n) pass[j] = eval_terms_row(p.terms, row);
-      if (!pass[j]) continue;
-      uint64_t vals[kMaxCells];
-      bool valid[kMaxCells];
-#pragma unroll
-      for (int c = 0; c < kMaxCells; c++)
-        if (c < p.n_cells) vals[c] = cell_encode(p.cell_op[c], ld_stream_u64(p.cell_col[c] + row), valid[c]);
-      // find-or-insert in this thread's copy
-      uint32_t slot = 0xFFFFFFFFu;
-      if (key[j] == kEmptyKey) slot = copy_base + p.s_slots;
+// aggregate one row per lane into the lane's copy (warp-uniform: every lane calls it, active = false without a row);
+// rows whose key finds no room fall through to the global table
+template <int NV>
+__device__ __forceinline__ void smem_update_row(const GbParams& p, const SmemTable& t, uint32_t copy_base, uint64_t key, const uint64_t (&v)[NV],
+                                                bool active) {
+  const uint32_t smask = p.s_slots - 1;
+  uint32_t s = (uint32_t)(mix64(key) >> 40) & smask, slot = 0xFFFFFFFFu, probes = 0;
+  bool pending = active;
+  if (pending && key == kEmptyKey) { slot = copy_base + p.s_slots; pending = false; }
+  while (__any_sync(0xffffffffu, pending)) {
+    if (pending) {
+      const uint64_t k = *(volatile uint64_t*)(t.keys + copy_base + s);
+      if (k == key) { slot = copy_base + s; pending = false; }
       else {
-        uint32_t s = (uint32_t)(mix64(key[j]) >> 32) & smask;
-        for (uint32_t probes = 0; probes < max_probe; probes++) {
-          uint64_t k = *(volatile uint64_t*)(s_keys + copy_base + s);
-          if (k == key[j]) { slot = copy_base + s; break; }
-          if (k == kEmptyKey) {
-            uint64_t old = atomicCAS((unsigned long long*)(s_keys + copy_base + s), (unsigned long long)kEmptyKey, (unsigned long long)key[j]);
-            if (old == kEmptyKey || old == key[j]) { slot = copy_base + s; break; }
-          }
+        if (k == kEmptyKey) {
+          const uint64_t old = atomicCAS((unsigned long long*)(t.keys + copy_base + s), (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (old == kEmptyKey || old == key) { slot = copy_base + s; pending = false; }
+        }
+        if (pending) {
           s = (s + 1) & smask;
+          if (++probes >= p.s_slots) pending = false;  // copy is full: spill
         }
       }
-      if (slot == 0xFFFFFFFFu) { global_update_row(p, key[j], vals, valid); continue; }  // copy is full: spill to the global table
-      atomicAdd(s_count + slot, 1u);
-#pragma unroll 1
-      for (int c = 0; c < p.n_cells; c++)
-        if (valid[c]) cell_atomic_shared(p.cell_op[c], s_cells + (uint64_t)c * total + slot, vals[c]);
+    }
+  }
+  const bool spill = active && slot == 0xFFFFFFFFu;
+  if (__any_sync(0xffffffffu, spill)) global_update_row<NV>(p, key, v, spill);
+  if (!active || spill) return;
+  atomicAdd(t.count + slot, 1u);
+#pragma unroll
+  for (int c = 0; c < kMaxCells; c++)
+    if (c < p.n_cells) {
+      bool valid;
+      const uint64_t x = cell_encode(p.cell_op[c], pick<NV>(v, p.cell_vcol[c]), valid);
+      if (valid) cell_atomic_shared(p.cell_op[c], t.cells + (uint64_t)c * t.total + slot, x);
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const SmemTable t = smem_table(p, smem_raw);
+  smem_table_clear(p, t);
+  __syncthreads();
+  const uint32_t copy_base = (threadIdx.x & (p.s_copies - 1)) * t.slots1;
+  const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
+  for (uint64_t base = blockIdx.x * tile; base < p.n; base += (uint64_t)gridDim.x * tile) {
+    uint64_t key[kGbRows], v[kGbRows][NV];
+    bool pass[kGbRows];
+    load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, 0, p.n, key, v, pass);
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++) {
+      smem_update_row<NV>(p, t, copy_base, key[j], v[j], pass[j]);
+      __syncwarp();
     }
   }
   __syncthreads();
-  // merge every copy into the global table
-  for (uint32_t i = threadIdx.x; i < total; i += kGbThreads) {
-    const uint32_t cnt = s_count[i];
-    if (!cnt) continue;
-    const uint64_t key = (i % slots1 == p.s_slots) ? kEmptyKey : s_keys[i];
-    uint64_t s = global_slot(p, key);
-    if (s == ~0ULL) continue;
+  // merge every copy into the global table (warp-uniform trip count: global_slot is a convergent call)
+  for (uint32_t i0 = 0; i0 < t.total; i0 += kGbThreads) {
+    const uint32_t i = i0 + threadIdx.x;
+    const uint32_t cnt = i < t.total ? t.count[i] : 0;
+    const uint64_t key = (cnt && i % t.slots1 != p.s_slots) ? t.keys[i] : kEmptyKey;
+    const uint64_t s = global_slot(p, key, cnt != 0);
+    if (!cnt || s == ~0ULL) continue;
     atomicAdd(p.g_count + s, (unsigned long long)cnt);
-    for (int c = 0; c < p.n_cells; c++) cell_atomic_global(p.cell_op[c], p.g_cells + (uint64_t)c * (p.g_cap + 1) + s, s_cells[(uint64_t)c * total + i]);
+    for (int c = 0; c < p.n_cells; c++) cell_atomic_global(p.cell_op[c], p.g_cells + (uint64_t)c * (p.g_cap + 1) + s, t.cells[(uint64_t)c * t.total + i]);
+  }
+}
+
+// one CTA per partition (grid-stride over partitions): every partition's groups are disjoint from all others', so the
+// table goes straight to the output; rows that do not fit the table spill to the global table (extracted afterwards)
+template <int NV>
+__global__ void __launch_bounds__(kGbThreads) gb_part_smem_kernel(GbParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_groups;
+  const SmemTable t = smem_table(p, smem_raw);
+  const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
+  for (uint32_t part = blockIdx.x; part < p.n_parts; part += gridDim.x) {
+    smem_table_clear(p, t);
+    if (threadIdx.x == 0) s_groups = 0;
+    __syncthreads();
+    const uint64_t begin = p.part_begin[part], end = p.part_begin[part + 1];
+    for (uint64_t base = begin & ~3ULL; base < end; base += tile) {
+      uint64_t key[kGbRows], v[kGbRows][NV];
+      bool pass[kGbRows];
+      load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, begin, end, key, v, pass);
+#pragma unroll
+      for (int j = 0; j < kGbRows; j++) {
+        smem_update_row<NV>(p, t, 0, key[j], v[j], pass[j]);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // count the groups, reserve a dense output range with one global atomic, write them out
+    uint32_t mine = 0;
+    for (uint32_t i = threadIdx.x; i < t.total; i += kGbThreads) mine += t.count[i] != 0;
+    uint32_t my_off = 0;
+    if (mine) my_off = atomicAdd(&s_groups, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_groups) s_base = atomicAdd(p.out_n, (unsigned long long)s_groups);
+    __syncthreads();
+    uint64_t g = s_base + my_off;
+    for (uint32_t i = threadIdx.x; i < t.total; i += kGbThreads) {
+      const uint32_t cnt = t.count[i];
+      if (!cnt) continue;
+      if (g < p.out_cap) {
+        uint64_t cells[kMaxCells];
+#pragma unroll
+        for (int c = 0; c < kMaxCells; c++) cells[c] = c < p.n_cells ? t.cells[(uint64_t)c * t.total + i] : 0;
+        emit_group(p.out, p.out_keys, p.out_aggs, p.out_cap, g, i == p.s_slots ? INT64_MIN : (int64_t)t.keys[i], cnt, cells);
+      }
+      g++;
+    }
+    __syncthreads();
   }
 }
 
@@ -297,49 +463,33 @@ __global__ void __launch_bounds__(256) gb_init_kernel(GbParams p) {
   }
 }
 
-struct OutSpec {
-  int n_aggs;
-  int8_t func[16];
-  int8_t type[16];
-  int8_t cell[16];  // cell index feeding this aggregate (-1: count only)
-};
-
-__global__ void __launch_bounds__(256) gb_extract_kernel(GbParams p, OutSpec o, bool emit_empty_global, int64_t* __restrict__ out_keys,
-                                                         uint64_t* __restrict__ out_aggs, uint64_t out_cap,
-                                                         unsigned long long* __restrict__ out_n) {
+__global__ void __launch_bounds__(256) gb_extract_kernel(GbParams p, bool emit_empty_global) {
   const uint64_t n = p.g_cap + 1, stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x; i0 < n; i0 += stride) {
     const uint64_t i = i0 + threadIdx.x;
-    unsigned long long cnt = i < n ? p.g_count[i] : 0;
-    bool occ = cnt != 0 || (emit_empty_global && i == 0);
-    unsigned m = __ballot_sync(0xffffffffu, occ);
+    const unsigned long long cnt = i < n ? p.g_count[i] : 0;
+    const bool occ = cnt != 0 || (emit_empty_global && i == 0);
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
     if (!m) continue;
     const int lane = threadIdx.x & 31;
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(out_n, (unsigned long long)__popc(m));
+    if (lane == 0) base = atomicAdd(p.out_n, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (!occ) continue;
     const uint64_t g = base + __popc(m & ((1u << lane) - 1));
-    if (g >= out_cap) continue;
-    out_keys[g] = p.keys ? (i == p.g_cap ? INT64_MIN : (int64_t)p.g_keys[i]) : 0;
-    for (int a = 0; a < o.n_aggs; a++) {
-      uint64_t r;
-      const uint64_t cell = o.cell[a] >= 0 ? p.g_cells[(uint64_t)o.cell[a] * n + i] : 0;
-      if (o.func[a] == OLAP_COUNT) r = cnt;
-      else if (o.func[a] == OLAP_AVG) {
-        double s = o.type[a] == OLAP_F64 ? __longlong_as_double((long long)cell) : (double)(long long)cell;
-        r = (uint64_t)__double_as_longlong(cnt ? s / (double)cnt : 0.0);
-      } else if ((o.func[a] == OLAP_MIN || o.func[a] == OLAP_MAX) && o.type[a] == OLAP_F64) r = (uint64_t)f64_ord(cell);
-      else r = cell;
-      out_aggs[(uint64_t)a * out_cap + g] = r;
-    }
+    if (g >= p.out_cap) continue;
+    uint64_t cells[kMaxCells];
+#pragma unroll
+    for (int c = 0; c < kMaxCells; c++) cells[c] = c < p.n_cells ? p.g_cells[(uint64_t)c * n + i] : 0;
+    emit_group(p.out, p.out_keys, p.out_aggs, p.out_cap, g, p.keys ? (i == p.g_cap ? INT64_MIN : (int64_t)p.g_keys[i]) : 0, cnt, cells);
   }
 }
 
 // ------------------------------------------------------------------------------------------- host driver
-static olap_status build_cells(const olap_agg_spec* specs, int n_aggs, GbParams* p, OutSpec* o) {
+static olap_status build_cells(const olap_agg_spec* specs, int n_aggs, GbParams* p) {
   OLAP_REQUIRE(n_aggs >= 0 && n_aggs <= 16, "n_aggs must be in [0, 16]");
-  p->n_cells = 0;
+  OutSpec* o = &p->out;
+  p->n_cells = 0; p->n_vcols = 0;
   o->n_aggs = n_aggs;
   for (int a = 0; a < n_aggs; a++) {
     const int f = specs[a].func, t = specs[a].value_type;
@@ -348,16 +498,22 @@ static olap_status build_cells(const olap_agg_spec* specs, int n_aggs, GbParams*
     o->func[a] = (int8_t)f; o->type[a] = (int8_t)t; o->cell[a] = -1;
     if (f == OLAP_COUNT) continue;
     OLAP_REQUIRE(specs[a].values, "aggregate value column is NULL");
-    int8_t op = (f == OLAP_SUM || f == OLAP_AVG) ? (t == OLAP_F64 ? ADD_F64 : ADD_I64)
-                : f == OLAP_MIN ? (t == OLAP_F64 ? MIN_F64 : MIN_I64) : (t == OLAP_F64 ? MAX_F64 : MAX_I64);
+    int vc = -1;
+    for (int q = 0; q < p->n_vcols; q++) if (p->vcol[q] == (const uint64_t*)specs[a].values) vc = q;
+    if (vc < 0) {
+      OLAP_REQUIRE(p->n_vcols < kMaxVcols, "more than 6 distinct value columns in one aggregation");
+      vc = p->n_vcols++;
+      p->vcol[vc] = (const uint64_t*)specs[a].values;
+    }
+    const int8_t op = (f == OLAP_SUM || f == OLAP_AVG) ? (t == OLAP_F64 ? ADD_F64 : ADD_I64)
+                      : f == OLAP_MIN ? (t == OLAP_F64 ? MIN_F64 : MIN_I64) : (t == OLAP_F64 ? MAX_F64 : MAX_I64);
     int found = -1;
-    for (int c = 0; c < p->n_cells; c++)
-      if (p->cell_op[c] == op && p->cell_col[c] == (const uint64_t*)specs[a].values) found = c;
+    for (int c = 0; c < p->n_cells; c++) if (p->cell_op[c] == op && p->cell_vcol[c] == vc) found = c;
     if (found < 0) {
       OLAP_REQUIRE(p->n_cells < kMaxCells, "more than 8 distinct (function, column) accumulators");
       found = p->n_cells++;
       p->cell_op[found] = op;
-      p->cell_col[found] = (const uint64_t*)specs[a].values;
+      p->cell_vcol[found] = (int8_t)vc;
     }
     o->cell[a] = (int8_t)found;
   }
@@ -365,10 +521,80 @@ static olap_status build_cells(const olap_agg_spec* specs, int n_aggs, GbParams*
 }
 
 static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+static unsigned capped_grid(uint64_t want, uint64_t cap) { return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want)); }
 
-// defined in join.cu: partitioned group-by support
-olap_status group_by_partitioned(olap_ctx* ctx, GbParams& p, const OutSpec& o, uint64_t n_groups_hint, int64_t* out_keys,
-                                 uint64_t* out_aggs, uint64_t out_cap, unsigned long long* d_n, cudaStream_t s, bool* handled);
+#define GB_DISPATCH_NV(nv, ...)                                 \
+  switch (nv) {                                                 \
+    case 0: case 1: { constexpr int NV = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; } break;       \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; } break;       \
+    case 4: { constexpr int NV = 4; __VA_ARGS__; } break;       \
+    case 5: { constexpr int NV = 5; __VA_ARGS__; } break;       \
+    default: { constexpr int NV = 6; __VA_ARGS__; } break;      \
+  }
+
+// join.cu: radix-partition (key, value columns) with the fused filter; returns the partition boundaries on the device
+olap_status group_by_partition_rows(olap_ctx* ctx, const uint64_t* keys, uint64_t n, const TermPack& terms, int n_vcols,
+                                    const uint64_t* const* vcols, int bits, uint64_t* out_keys, uint64_t* const* out_vcols,
+                                    uint32_t* part_begin, cudaStream_t s);
+
+// shared-memory budget per CTA for group tables
+static uint64_t slot_bytes(const GbParams& p) { return 8 + 4 + 8ULL * p.n_cells; }
+
+static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups_hint, Scratch& sc, cudaStream_t s) {
+  const int bits = 8;
+  const uint32_t P = 1u << bits;
+  uint64_t* pk = nullptr;
+  uint64_t* pv[kMaxVcols] = {};
+  uint32_t* begin = nullptr;
+  OLAP_TRY(sc.get<uint64_t>(p.n, &pk));
+  for (int q = 0; q < p.n_vcols; q++) OLAP_TRY(sc.get<uint64_t>(p.n, &pv[q]));
+  OLAP_TRY(sc.get<uint32_t>(P + 1, &begin));
+  OLAP_TRY(group_by_partition_rows(ctx, p.keys, p.n, p.terms, p.n_vcols, p.vcol, bits, pk, pv, begin, s));
+  phase_mark(ctx, s, "partition");
+  GbParams q = p;  // aggregate the partitioned copies; the filter has been applied by the partition pass
+  q.keys = pk;
+  for (int i = 0; i < p.n_vcols; i++) q.vcol[i] = pv[i];
+  q.terms.n = 0;
+  q.vec = true;  // pool allocations are 256-byte aligned
+  q.part_begin = begin; q.n_parts = P;
+  const uint64_t per_part = (n_groups_hint + P - 1) / P;
+  uint64_t need = pow2_at_least((per_part * 3 + 1) / 2);  // <= 67 % load even if the partitions are a little uneven
+  if (need < 64) need = 64;
+  const uint64_t bytes = (need + 1) * slot_bytes(p) + 16;
+  if (bytes <= 200 * 1024) {
+    q.s_slots = (uint32_t)need; q.s_copies = 1;
+    const unsigned per_sm = bytes <= 100 * 1024 ? 2 : 1;
+    GB_DISPATCH_NV(p.n_vcols, {
+      OLAP_CUDA(cudaFuncSetAttribute(gb_part_smem_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      gb_part_smem_kernel<NV><<<capped_grid(P, (uint64_t)ctx->sm_count * per_sm), kGbThreads, bytes, s>>>(q);
+    });
+    count_launch(ctx);
+  } else {
+    // very high cardinality: every partition aggregates into an L2-resident slice-sized global table, reused in turn
+    std::vector<uint32_t> h(P + 1);
+    OLAP_CUDA(cudaMemcpyAsync(h.data(), begin, (P + 1) * 4, cudaMemcpyDeviceToHost, s));
+    OLAP_CUDA(cudaStreamSynchronize(s));
+    GbParams t = q;
+    t.g_cap = pow2_at_least(std::max<uint64_t>(2 * per_part + per_part / 2, 1024));
+    const uint64_t n1 = t.g_cap + 1;
+    OLAP_TRY(sc.get<uint64_t>(n1, &t.g_keys));
+    OLAP_TRY(sc.get<unsigned long long>(n1, &t.g_count));
+    OLAP_TRY(sc.get<uint64_t>(n1 * std::max(p.n_cells, 1), &t.g_cells));
+    const unsigned tgrid = capped_grid((n1 + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
+    for (uint32_t part = 0; part < P; part++) {
+      const uint64_t b0 = h[part], b1 = h[part + 1];
+      if (b1 == b0) continue;
+      gb_init_kernel<<<tgrid, 256, 0, s>>>(t);
+      GB_DISPATCH_NV(p.n_vcols, (gb_global_kernel<NV><<<capped_grid((b1 - b0 + tile - 1) / tile, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(t, b0, b1)));
+      gb_extract_kernel<<<tgrid, 256, 0, s>>>(t, false);
+      count_launch(ctx, 3);
+    }
+  }
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
 
 }  // namespace olap
 
@@ -381,18 +607,19 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
   OLAP_REQUIRE(ctx, "ctx is NULL");
   OLAP_REQUIRE(n_aggs == 0 || specs, "specs is NULL");
   OLAP_REQUIRE(out_capacity == 0 || (out_keys && (n_aggs == 0 || out_aggs)), "output pointer is NULL");
+  OLAP_REQUIRE(n_rows < 0xFFFFFFFFULL || !keys, "grouped aggregation partitions with u32 offsets: n_rows must be < 2^32 - 1");
   std::lock_guard<std::mutex> g(ctx->mu);
   OLAP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream_of(stream);
 
   GbParams p;
   memset(&p, 0, sizeof(p));
-  OutSpec o;
-  memset(&o, 0, sizeof(o));
-  OLAP_TRY(build_cells(specs, n_aggs, &p, &o));
+  OLAP_TRY(build_cells(specs, n_aggs, &p));
   OLAP_TRY(pack_terms(terms, n_terms, &p.terms));
   p.keys = (const uint64_t*)keys;
   p.n = n_rows;
+  p.vec = (((uintptr_t)keys) & 31) == 0;
+  for (int q = 0; q < p.n_vcols; q++) p.vec = p.vec && (((uintptr_t)p.vcol[q]) & 31) == 0;
   if (!keys) n_groups_hint = 1;
   if (n_groups_hint < 1) n_groups_hint = 1;
 
@@ -401,64 +628,58 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
   uint32_t* d_overflow = nullptr;
   OLAP_TRY(sc.get<unsigned long long>(1, &d_n));
   OLAP_TRY(sc.get<uint32_t>(1, &d_overflow));
+  p.out_keys = out_keys; p.out_aggs = (uint64_t*)out_aggs; p.out_cap = out_capacity; p.out_n = d_n;
+  p.g_overflow = d_overflow;
   phase_begin(ctx, s);
 
+  const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
+  const uint64_t tiles = (n_rows + tile - 1) / tile;
   uint64_t n_groups = 0;
   for (int attempt = 0;; attempt++) {
     Scratch tsc(ctx, s);
-    p.g_cap = keys ? pow2_at_least(2 * n_groups_hint < 1024 ? 1024 : 2 * n_groups_hint) : 1;
+    // regime
+    const uint64_t sbytes = slot_bytes(p), budget = 96 * 1024;  // shared regime: two CTAs per SM
+    uint64_t need = pow2_at_least((n_groups_hint * 4 + 2) / 3);
+    if (need < 16) need = 16;
+    const bool shared = keys && attempt == 0 && (need + 1) * sbytes + 16 <= budget;
+    const bool partitioned = keys && attempt == 0 && !shared && n_rows >= (1u << 20) && p.n_vcols <= 4;  // the partitioner carries <= 4 payload columns
+    // global table: the spill target of the shared/partitioned regimes (small), or the whole table
+    uint64_t gh = (shared || partitioned) ? std::min<uint64_t>(n_groups_hint, 4096) : n_groups_hint;
+    p.g_cap = keys ? pow2_at_least(std::max<uint64_t>(2 * gh, 1024)) : 1;
     const uint64_t n1 = p.g_cap + 1;
     OLAP_TRY(tsc.get<uint64_t>(n1, &p.g_keys));
     OLAP_TRY(tsc.get<unsigned long long>(n1, &p.g_count));
     OLAP_TRY(tsc.get<uint64_t>(n1 * (p.n_cells ? p.n_cells : 1), &p.g_cells));
-    p.g_overflow = d_overflow;
     OLAP_CUDA(cudaMemsetAsync(d_n, 0, 8, s));
     OLAP_CUDA(cudaMemsetAsync(d_overflow, 0, 4, s));
-    const unsigned init_grid = (unsigned)(((n1 + 255) / 256) < (uint64_t)ctx->sm_count * 8 ? ((n1 + 255) / 256) : (uint64_t)ctx->sm_count * 8);
-    gb_init_kernel<<<init_grid, 256, 0, s>>>(p);
+    const unsigned tgrid = capped_grid((n1 + 255) / 256, (uint64_t)ctx->sm_count * 8);
+    gb_init_kernel<<<tgrid, 256, 0, s>>>(p);
     count_launch(ctx);
     phase_mark(ctx, s, "init");
-
-    bool handled = false;
     if (n_rows > 0) {
-      const uint64_t tiles = (n_rows + (uint64_t)kGbThreads * kGbRows - 1) / ((uint64_t)kGbThreads * kGbRows);
       if (!keys) {
-        unsigned grid = (unsigned)(tiles < (uint64_t)ctx->sm_count * 4 ? tiles : (uint64_t)ctx->sm_count * 4);
-        gb_nokey_kernel<<<grid, kGbThreads, 0, s>>>(p);
+        GB_DISPATCH_NV(p.n_vcols, (gb_nokey_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p)));
         count_launch(ctx);
-        handled = true;
+      } else if (shared) {
+        uint64_t copies = 1;
+        while (copies < 64 && (need + 1) * sbytes * copies * 2 + 16 <= budget) copies <<= 1;
+        p.s_slots = (uint32_t)need; p.s_copies = (uint32_t)copies;
+        const size_t smem = (size_t)((need + 1) * copies * sbytes + 16);
+        GB_DISPATCH_NV(p.n_vcols, {
+          OLAP_CUDA(cudaFuncSetAttribute(gb_shared_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          gb_shared_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 2), kGbThreads, smem, s>>>(p);
+        });
+        count_launch(ctx);
+      } else if (partitioned) {
+        OLAP_TRY(run_partitioned(ctx, p, n_groups_hint, tsc, s));
       } else {
-        // shared regime if a table with <= 75 % load fits the per-CTA budget
-        const uint64_t slot_bytes = 8 + 4 + 8ULL * p.n_cells;
-        const uint64_t budget = 96 * 1024;  // two CTAs per SM
-        uint64_t need = pow2_at_least((n_groups_hint * 4 + 2) / 3);
-        if (need < 16) need = 16;
-        if ((need + 1) * slot_bytes <= budget && attempt == 0) {
-          uint64_t copies = 1;
-          while (copies < 32 && (need + 1) * slot_bytes * copies * 2 <= budget) copies <<= 1;
-          p.s_slots = (uint32_t)need;
-          p.s_copies = (uint32_t)copies;
-          const size_t smem = (size_t)((need + 1) * copies * slot_bytes + 16);
-          OLAP_CUDA(cudaFuncSetAttribute(gb_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          unsigned grid = (unsigned)(tiles < (uint64_t)ctx->sm_count * 2 ? tiles : (uint64_t)ctx->sm_count * 2);
-          gb_shared_kernel<<<grid, kGbThreads, smem, s>>>(p);
-          count_launch(ctx);
-          handled = true;
-        } else if (attempt == 0) {
-          OLAP_TRY(group_by_partitioned(ctx, p, o, n_groups_hint, out_keys, (uint64_t*)out_aggs, out_capacity, d_n, s, &handled));
-        }
-        if (!handled) {
-          unsigned grid = (unsigned)(tiles < (uint64_t)ctx->sm_count * 4 ? tiles : (uint64_t)ctx->sm_count * 4);
-          gb_global_kernel<<<grid, kGbThreads, 0, s>>>(p);
-          count_launch(ctx);
-        }
+        GB_DISPATCH_NV(p.n_vcols, (gb_global_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p, 0, n_rows)));
+        count_launch(ctx);
       }
       OLAP_CUDA(cudaGetLastError());
     }
     phase_mark(ctx, s, "aggregate");
-    const uint64_t n1b = p.g_cap + 1;
-    const unsigned ex_grid = (unsigned)(((n1b + 255) / 256) < (uint64_t)ctx->sm_count * 8 ? ((n1b + 255) / 256) : (uint64_t)ctx->sm_count * 8);
-    gb_extract_kernel<<<ex_grid, 256, 0, s>>>(p, o, /*emit_empty_global=*/keys == nullptr, out_keys, (uint64_t*)out_aggs, out_capacity, d_n);
+    gb_extract_kernel<<<tgrid, 256, 0, s>>>(p, /*emit_empty_global=*/keys == nullptr);
     count_launch(ctx);
     OLAP_CUDA(cudaGetLastError());
     phase_mark(ctx, s, "extract");
@@ -467,8 +688,9 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
     OLAP_CUDA(cudaMemcpyAsync(&n_groups, d_n, 8, cudaMemcpyDeviceToHost, s));
     OLAP_CUDA(cudaStreamSynchronize(s));
     if (!h_overflow) break;
-    // the caller's hint was too small for the global table: grow and redo (correctness never depends on the hint)
-    n_groups_hint = n_groups_hint * 8 > n_rows ? (n_rows ? n_rows : 1) : n_groups_hint * 8;
+    // the caller's hint was too small for the spill/global table: redo everything on one big global table
+    n_groups_hint = std::max<uint64_t>(n_groups_hint * 8, 1u << 16);
+    if (n_groups_hint > n_rows) n_groups_hint = n_rows ? n_rows : 1;
     OLAP_REQUIRE(attempt < 24, "group-by table kept overflowing");
   }
   phase_end(ctx, s);

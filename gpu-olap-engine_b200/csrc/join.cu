@@ -560,13 +560,19 @@ static olap_status join_radix(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, co
   return OLAP_OK;
 }
 
-// Partitioned group-by hook (groupby.cu); filled in by a later milestone.
-struct GbParams;
-struct OutSpec;
-olap_status group_by_partitioned(olap_ctx*, GbParams&, const OutSpec&, uint64_t, int64_t*, uint64_t*, uint64_t, unsigned long long*,
-                                 cudaStream_t, bool* handled) {
-  *handled = false;
-  return OLAP_OK;
+// Partition pass of the partitioned group-by (groupby.cu): (key, up to 4 value columns) with the filter fused in.
+olap_status group_by_partition_rows(olap_ctx* ctx, const uint64_t* keys, uint64_t n, const TermPack& terms, int n_vcols,
+                                    const uint64_t* const* vcols, int bits, uint64_t* out_keys, uint64_t* const* out_vcols,
+                                    uint32_t* part_begin, cudaStream_t s) {
+  if (n_vcols > kMaxPay) { set_error("partitioned group-by carries at most %d value columns", kMaxPay); return OLAP_ERR_UNSUPPORTED; }
+  Scratch sc(ctx, s);
+  uint32_t* hist = nullptr;
+  OLAP_TRY(sc.get<uint32_t>((uint64_t)(1u << bits) * ctx->sm_count * 2, &hist));
+  PartArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bits = bits; a.keys = keys; a.n = n; a.hist = hist; a.out_keys = out_keys; a.terms = terms;
+  for (int q = 0; q < n_vcols; q++) { a.pay_in[q] = vcols[q]; a.pay_out[q] = out_vcols[q]; }
+  return run_partition(ctx, a, n_vcols, false, part_begin, s);
 }
 
 }  // namespace olap

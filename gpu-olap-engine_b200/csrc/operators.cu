@@ -357,8 +357,12 @@ static olap_status exec_aggregate(olap_ctx* ctx, const olap_plan* p, Batches* ou
   const int na = (int)p->agg_in.size();
   std::vector<Value> vals(na);
   std::vector<olap_agg_spec> specs(na);
+  std::map<std::string, int> seen;  // identical input expressions are evaluated once (SUM(x), AVG(x), MIN(x) share one column)
   for (int a = 0; a < na; a++) {
-    if (!in.empty()) OLAP_TRY(eval_over_batches(ctx, p->agg_in[a], in, n, &vals[a]));
+    const std::string ename = expr_name(p->agg_in[a]);
+    auto it = seen.find(ename);
+    if (it != seen.end()) vals[a] = vals[it->second];
+    else if (!in.empty()) { OLAP_TRY(eval_over_batches(ctx, p->agg_in[a], in, n, &vals[a])); seen[ename] = a; }
     else { vals[a].type = OLAP_I64; OLAP_TRY(new_buf(ctx, 16, &vals[a].buf)); }
     specs[a].values = vals[a].data(); specs[a].func = p->agg_funcs[a]; specs[a].value_type = vals[a].type;
   }

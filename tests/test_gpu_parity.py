@@ -192,7 +192,8 @@ def check_group_by(ctx, keys, cols, funcs, hint, terms_fn=None, mask=None, rtol=
     import gpu_olap_engine_b200 as g
     n = len(cols[0]) if cols else len(keys)
     dk = None if keys is None else dev(ctx, keys)
-    dcols = [dev(ctx, c) for c in cols]
+    uploaded = {}
+    dcols = [uploaded.setdefault(id(c), dev(ctx, c)) if id(c) not in uploaded else uploaded[id(c)] for c in cols]   # one device column per distinct input
     aggs = [(f, d, g.F64 if c.dtype == np.float64 else g.I64) for f, d, c in zip(funcs, dcols, cols)]
     terms = terms_fn(dcols) if terms_fn else None
     ng, ok, oa, cap = ctx.group_by_i64(dk, n, aggs, hint, out_capacity=max(hint, 1 << 16), terms=terms)
