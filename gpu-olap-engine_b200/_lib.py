@@ -57,7 +57,7 @@ SIGNATURES = {
     "olap_choose_join_strategy": (i32, [u64]),
     "olap_radix_partition_i64": (i32, [vp, vp, vp, u64, i32, vp, vp, vp, vp]),
     "olap_partition_of": (u32, [i64, i32]),
-    "olap_shuffle_partition_i64": (i32, [vp, vp, vp, u64, i32, vp, vp, vp, vp]),
+    "olap_shuffle_partition_i64": (i32, [vp, vp, vp, u64, i32, vp, vp, vp, vp, vp]),
     "olap_shuffle_dest_of": (u32, [i64, i32]),
     "olap_group_by_i64": (i32, [vp, vp, C.POINTER(AggSpec), i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_agg_identity": (i64, [i32]),

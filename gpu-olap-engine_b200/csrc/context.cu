@@ -368,7 +368,8 @@ int32_t olap_choose_join_strategy(uint64_t n_build) { return n_build <= 1000000U
 
 uint32_t olap_partition_of(int64_t key, int32_t bits) {
   if (bits <= 0) return 0;
-  return (uint32_t)(mix64((uint64_t)key) >> (64 - bits));
+  const uint64_t k = (uint64_t)key;  // must match part_hash(key, 0) in join.cu
+  return (uint32_t)(((k ^ (k >> 29)) * 0x9E3779B97F4A7C15ULL) >> (64 - bits));
 }
 
 }  // extern "C"

@@ -248,29 +248,72 @@ __device__ __forceinline__ void load_rows(const GbParams& p, uint64_t row0, uint
 }
 
 // ------------------------------------------------------------------------------------------- no-key regime
+// Branch-free row body: every value column keeps all six accumulators (i64 / f64 sum, min, max) in registers -- ~25
+// instructions per row and column -- and the requested (op, column) cells are picked once at the end.  (A per-row
+// runtime dispatch over the cell list cost ~100 instructions per row and left the kernel issue-bound at 26 % of HBM.)
+template <int NV>
+struct AllAcc {
+  uint64_t add_i[NV]; double add_f[NV]; long long min_i[NV], max_i[NV], min_f[NV], max_f[NV];
+};
+
 template <int NV>
 __global__ void __launch_bounds__(kGbThreads) gb_nokey_kernel(GbParams p) {
-  uint64_t acc[kMaxCells];
+  AllAcc<NV> a;
+#pragma unroll
+  for (int q = 0; q < NV; q++) {
+    a.add_i[q] = 0; a.add_f[q] = 0.0;
+    a.min_i[q] = INT64_MAX; a.max_i[q] = INT64_MIN;
+    a.min_f[q] = (long long)cell_identity(MIN_F64); a.max_f[q] = (long long)cell_identity(MAX_F64);
+  }
   unsigned long long cnt = 0;
-#pragma unroll
-  for (int c = 0; c < kMaxCells; c++) acc[c] = c < p.n_cells ? cell_identity(p.cell_op[c]) : 0;
+  constexpr int U = NV <= 2 ? 2 : 1;  // independent 256-bit loads per column in flight per thread
   const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
-  for (uint64_t base = blockIdx.x * tile; base < p.n; base += (uint64_t)gridDim.x * tile) {
-    uint64_t key[kGbRows], v[kGbRows][NV];
-    bool pass[kGbRows];
-    load_rows<NV, false>(p, base + (uint64_t)threadIdx.x * kGbRows, 0, p.n, key, v, pass);
+  for (uint64_t base = blockIdx.x * tile * U; base < p.n; base += (uint64_t)gridDim.x * tile * U) {
+    uint64_t key[U][kGbRows], v[U][kGbRows][NV];
+    bool pass[U][kGbRows];
 #pragma unroll
-    for (int j = 0; j < kGbRows; j++) {
-      if (!pass[j]) continue;
-      cnt++;
+    for (int u = 0; u < U; u++) load_rows<NV, false>(p, base + u * tile + (uint64_t)threadIdx.x * kGbRows, 0, p.n, key[u], v[u], pass[u]);
 #pragma unroll
-      for (int c = 0; c < kMaxCells; c++)
-        if (c < p.n_cells) {
-          bool valid;
-          const uint64_t x = cell_encode(p.cell_op[c], pick<NV>(v[j], p.cell_vcol[c]), valid);
-          if (valid) acc[c] = cell_combine(p.cell_op[c], acc[c], x);
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < kGbRows; j++) {
+        const bool ok = pass[u][j];
+        cnt += ok;
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+          const uint64_t x = v[u][j][q];
+          const double d = __longlong_as_double((long long)x);
+          const long long o = f64_ord(x);
+          const bool fok = ok && d == d;  // NaN never wins a MIN / MAX (executor.rs:319-324 compares with < and >)
+          a.add_i[q] += ok ? x : 0;
+          a.add_f[q] += ok ? d : 0.0;
+          a.min_i[q] = ok ? min(a.min_i[q], (long long)x) : a.min_i[q];
+          a.max_i[q] = ok ? max(a.max_i[q], (long long)x) : a.max_i[q];
+          a.min_f[q] = fok ? min(a.min_f[q], o) : a.min_f[q];
+          a.max_f[q] = fok ? max(a.max_f[q], o) : a.max_f[q];
+        }
+      }
+  }
+  // pick the requested cells
+  uint64_t acc[kMaxCells];
+#pragma unroll
+  for (int c = 0; c < kMaxCells; c++) {
+    uint64_t r = 0;
+    if (c < p.n_cells) {
+#pragma unroll
+      for (int q = 0; q < NV; q++)
+        if (p.cell_vcol[c] == q) {
+          switch (p.cell_op[c]) {
+            case ADD_I64: r = a.add_i[q]; break;
+            case ADD_F64: r = (uint64_t)__double_as_longlong(a.add_f[q]); break;
+            case MIN_I64: r = (uint64_t)a.min_i[q]; break;
+            case MAX_I64: r = (uint64_t)a.max_i[q]; break;
+            case MIN_F64: r = (uint64_t)a.min_f[q]; break;
+            default: r = (uint64_t)a.max_f[q];
+          }
         }
     }
+    acc[c] = r;
   }
   // warp reduce, then one atomic per CTA (f64 sums: the order varies run to run; see DESIGN.md on f64 parity)
 #pragma unroll
@@ -658,7 +701,7 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
     phase_mark(ctx, s, "init");
     if (n_rows > 0) {
       if (!keys) {
-        GB_DISPATCH_NV(p.n_vcols, (gb_nokey_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p)));
+        GB_DISPATCH_NV(p.n_vcols, (gb_nokey_kernel<NV><<<capped_grid((tiles + 1) / 2, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p)));
         count_launch(ctx);
       } else if (shared) {
         uint64_t copies = 1;

@@ -51,19 +51,36 @@ class DeviceOps:
     def empty(self, n, dtype):
         return torch.empty(max(int(n), 0), dtype=dtype, device=self.device)
 
-    def shuffle_partition(self, keys, n, bits):
-        """(keys sorted by destination rank, their local row ids, begin offsets[2^bits + 1])."""
-        out_k = self.empty(n, torch.int64); out_i = self.empty(n, torch.int32)
-        begin = self.empty((1 << bits) + 1, torch.int32)
+    def buffer(self, name, n, dtype):
+        """Cached scratch tensor: multi-GB send/receive buffers are reused across calls instead of re-allocated."""
+        cache = self.__dict__.setdefault("_buffers", {})
+        t = cache.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(int(n * 1.05) + 1024, 1), dtype=dtype, device=self.device)
+            cache[name] = t
+        return t[:n]
+
+    def shuffle_partition_async(self, keys, n, bits, tag=""):
+        """Partition rows by destination rank: (keys, local row ids, meta) where meta = begin[2^bits + 1] ++ count[2^bits]
+        is still on the device.  Region p = [begin[p], begin[p] + count[p]) starts on a multiple of 16 rows."""
+        P = 1 << bits
+        out_k = self.buffer("send_k" + tag, n + 16 * P, torch.int64); out_i = self.buffer("send_i" + tag, n + 16 * P, torch.int32)
+        meta = self.empty(2 * P + 1, torch.int32)
         if bits == 0:
-            out_k.copy_(keys[:n]); out_i.copy_(torch.arange(n, dtype=torch.int32, device=self.device))
-            return out_k, out_i, [0, n]
+            out_k[:n].copy_(keys[:n]); out_i[:n].copy_(torch.arange(n, dtype=torch.int32, device=self.device))
+            meta.copy_(torch.tensor([0, n, n], dtype=torch.int32))
+            return out_k, out_i, meta
         _lib.check(self.lib.olap_shuffle_partition_i64(self.ctx.handle, keys.data_ptr(), None, n, bits, out_k.data_ptr(), out_i.data_ptr(),
-                                                       begin.data_ptr(), self._stream()))
-        return out_k, out_i, begin.tolist()
+                                                       meta.data_ptr(), meta.data_ptr() + 4 * (P + 1), self._stream()))
+        return out_k, out_i, meta
+
+    def shuffle_partition(self, keys, n, bits, tag=""):
+        out_k, out_i, meta = self.shuffle_partition_async(keys, n, bits, tag)
+        m = meta.tolist(); P = 1 << bits
+        return out_k, out_i, m[:P + 1], m[P + 1:]
 
     def hash_join(self, build_keys, nb, probe_keys, npb, max_matches, strategy=JOIN_AUTO):
-        pairs = self.empty(2 * max(max_matches, 1), torch.int32)
+        pairs = self.buffer("pairs", 2 * max(max_matches, 1), torch.int32)
         cnt = C.c_uint64()
         st = self.lib.olap_hash_join_i64(self.ctx.handle, build_keys.data_ptr() if nb else None, nb, probe_keys.data_ptr() if npb else None, npb,
                                          pairs.data_ptr(), max_matches, None, C.byref(cnt), strategy, self._stream())
@@ -89,6 +106,16 @@ class DeviceOps:
             return g.value, ok[:g.value], [oa[i * cap:i * cap + g.value] for i in range(na)]
 
 
+class _Growable:
+    """Lazily sized view of a cached buffer: out_bufs[i][:total] allocates / reuses capacity once total is known."""
+
+    def __init__(self, buf, name, dtype):
+        self.buf, self.name, self.dtype = buf, name, dtype
+
+    def __getitem__(self, sl):
+        return self.buf(self.name, sl.stop, self.dtype)
+
+
 class ShardedExchange:
     """all-to-all of variable-size per-destination segments (the only collective on the path)."""
 
@@ -98,23 +125,58 @@ class ShardedExchange:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bits = _log2(self.world)
         self.bytes_sent = 0
+        self.nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
 
     def exchange_counts(self, send_counts):
         if self.world == 1:
             return list(send_counts)
-        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
-        s = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+        s = torch.tensor(send_counts, dtype=torch.int64, device="cuda" if self.nccl else "cpu")
         r = torch.empty_like(s)
         dist.all_to_all_single(r, s, group=self.group)
         return r.tolist()
 
-    def all_to_all(self, tensor, send_counts, recv_counts):
+    def all_to_all(self, tensor, send_counts, recv_counts, out=None):
+        """Contiguous variable-size all-to-all (small payloads: partial aggregates)."""
         if self.world == 1:
             return tensor
-        out = torch.empty(sum(recv_counts), dtype=tensor.dtype, device=tensor.device)
+        if out is None:
+            out = torch.empty(sum(recv_counts), dtype=tensor.dtype, device=tensor.device)
         dist.all_to_all_single(out, tensor, output_split_sizes=list(recv_counts), input_split_sizes=list(send_counts), group=self.group)
         self.bytes_sent += (sum(send_counts) - send_counts[self.rank]) * tensor.element_size()
         return out
+
+    def exchange_regions(self, cols, begin, count, out_bufs=None):
+        """Ship region p = cols[i][begin[p] : begin[p] + count[p]] to rank p, for every column in cols.
+
+        The bulk goes as multiple-of-4-row segments from 16-row-aligned starts into 4-row-aligned receive offsets: both
+        ends of every NCCL peer copy are 16-byte aligned (425 GB/s instead of ~170 GB/s measured on B200 / NVLink 5).
+        The <= 3 leftover rows per peer follow in one tiny all-to-all.  Returns ([received columns], segments) with
+        segments = [(source rank, rows)] in buffer order."""
+        W = self.world
+        if W == 1:
+            return [c[begin[0]:begin[0] + count[0]] for c in cols], [(0, count[0])]
+        recv = self.exchange_counts(count)
+        c4 = [c & ~3 for c in count]; r4 = [c & ~3 for c in recv]
+        cl = [c - d for c, d in zip(count, c4)]; rl = [c - d for c, d in zip(recv, r4)]
+        total = sum(recv)
+        outs = []
+        for i, col in enumerate(cols):
+            out = out_bufs[i][:total] if out_bufs else torch.empty(total, dtype=col.dtype, device=col.device)
+            ins = [col[begin[p]:begin[p] + c4[p]] for p in range(W)]
+            off, views = 0, []
+            for sidx in range(W):
+                views.append(out[off:off + r4[sidx]]); off += r4[sidx]
+            if self.nccl:
+                dist.all_to_all(views, ins, group=self.group)
+            else:  # gloo has no list all_to_all: same data movement through the contiguous form
+                tmp = torch.empty(sum(r4), dtype=col.dtype, device=col.device)
+                dist.all_to_all_single(tmp, torch.cat(ins), output_split_sizes=r4, input_split_sizes=c4, group=self.group)
+                out[:sum(r4)].copy_(tmp)
+            left = torch.cat([col[begin[p] + c4[p]:begin[p] + count[p]] for p in range(W)])
+            dist.all_to_all_single(out[off:total], left, output_split_sizes=rl, input_split_sizes=cl, group=self.group)
+            self.bytes_sent += (sum(count) - count[self.rank]) * col.element_size()
+            outs.append(out)
+        return outs, [(sidx, r4[sidx]) for sidx in range(W)] + [(sidx, rl[sidx]) for sidx in range(W)]
 
 
 class ShardedJoin:
@@ -123,22 +185,46 @@ class ShardedJoin:
     def __init__(self, ops, group=None):
         self.ops = ops
         self.x = ShardedExchange(group)
+        self._comm = None   # side stream for the exchange, so it overlaps the next partition kernel
 
-    def shuffle(self, keys, n):
-        pk, pid, begin = self.ops.shuffle_partition(keys, n, self.x.bits)
-        send = [begin[p + 1] - begin[p] for p in range(self.x.world)]
-        recv = self.x.exchange_counts(send)
-        rk = self.x.all_to_all(pk, send, recv)
-        ri = self.x.all_to_all(pid, send, recv)
-        return rk, ri, recv
+    def _exchange(self, pk, pid, begin, count, tag):
+        buf = getattr(self.ops, "buffer", None)
+        bufs = None
+        if buf and self.x.world > 1:   # cached receive buffers, sized once the counts are known
+            bufs = [_Growable(buf, "recv_k" + tag, pk.dtype), _Growable(buf, "recv_i" + tag, pid.dtype)]
+        (rk, ri), segs = self.x.exchange_regions([pk, pid], begin, count, bufs)
+        return rk, ri, segs
+
+    def shuffle(self, keys, n, tag=""):
+        pk, pid, begin, count = self.ops.shuffle_partition(keys, n, self.x.bits, tag)
+        return self._exchange(pk, pid, begin, count, tag)
+
+    def shuffle_both(self, build_keys, n_build, probe_keys, n_probe):
+        """Both sides; on CUDA the build-side exchange runs on a side stream while the probe side is being partitioned."""
+        if not (build_keys.is_cuda and self.x.world > 1 and hasattr(self.ops, "shuffle_partition_async")):
+            return self.shuffle(build_keys, n_build, "_b"), self.shuffle(probe_keys, n_probe, "_p")
+        P = self.x.world
+        main = torch.cuda.current_stream()
+        if self._comm is None:
+            self._comm = torch.cuda.Stream()
+        bk_s, bi_s, bbegin, bcount = self.ops.shuffle_partition(build_keys, n_build, self.x.bits, "_b")   # host waits for the build partition
+        done_b = torch.cuda.Event(); done_b.record(main)
+        pk_s, pi_s, pmeta = self.ops.shuffle_partition_async(probe_keys, n_probe, self.x.bits, "_p")      # queued, not awaited
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(done_b)
+            b = self._exchange(bk_s, bi_s, bbegin, bcount, "_b")
+            ev = torch.cuda.Event(); ev.record(self._comm)
+        m = pmeta.tolist()                              # host waits for the probe partition; the build exchange ran meanwhile
+        main.wait_event(ev)
+        p = self._exchange(pk_s, pi_s, m[:P + 1], m[P + 1:], "_p")
+        return b, p
 
     def join(self, build_keys, n_build, probe_keys, n_probe, max_matches=None, strategy=JOIN_AUTO):
-        bk, bi, brecv = self.shuffle(build_keys, n_build)   # build side first: tables can be built while probes arrive
-        pk, pi, precv = self.shuffle(probe_keys, n_probe)
+        (bk, bi, bsegs), (pk, pi, psegs) = self.shuffle_both(build_keys, n_build, probe_keys, n_probe)
         nb, npb = int(bk.numel()), int(pk.numel())
         mm = max_matches if max_matches is not None else max(npb, 1)
         count, pairs = self.ops.hash_join(bk, nb, pk, npb, mm, strategy)
-        return {"count": count, "pairs": pairs, "build_ids": bi, "build_recv": brecv, "probe_ids": pi, "probe_recv": precv,
+        return {"count": count, "pairs": pairs, "build_ids": bi, "build_recv": bsegs, "probe_ids": pi, "probe_recv": psegs,
                 "n_build_local": nb, "n_probe_local": npb}
 
     @staticmethod
@@ -147,10 +233,11 @@ class ShardedJoin:
         k = int(res["count"])
         pairs = res["pairs"][:2 * k].view(-1, 2).to(torch.int64) & 0xFFFFFFFF
 
-        def to_global(pos, ids, recv, offs):
-            bounds = torch.tensor(np.cumsum([0] + list(recv)), device=pos.device)
-            src = torch.bucketize(pos.contiguous(), bounds[1:], right=True)
-            return torch.tensor(list(offs), device=pos.device, dtype=torch.int64)[src] + (ids.to(torch.int64) & 0xFFFFFFFF)[pos]
+        def to_global(pos, ids, segs, offs):
+            bounds = torch.tensor(np.cumsum([0] + [c for _, c in segs]), device=pos.device)
+            seg = torch.bucketize(pos.contiguous(), bounds[1:], right=True)
+            seg_off = torch.tensor([offs[src] for src, _ in segs], device=pos.device, dtype=torch.int64)
+            return seg_off[seg] + (ids.to(torch.int64) & 0xFFFFFFFF)[pos]
 
         left = to_global(pairs[:, 0], res["build_ids"], res["build_recv"], build_rank_offsets)
         right = to_global(pairs[:, 1], res["probe_ids"], res["probe_recv"], probe_rank_offsets)
@@ -181,11 +268,12 @@ class ShardedGroupBy:
             plan.append((partial(SUM, c, t), partial(COUNT, c, t)) if f == AVG else (partial(f, c, t), None))
         g, gk, parts = self.ops.group_by(keys, n, pc, pf, pt, n_groups_hint)
         # 2. route every partial row to the rank that owns its key
-        pk, pid, begin = self.ops.shuffle_partition(gk, g, self.x.bits)
-        send = [begin[p + 1] - begin[p] for p in range(self.x.world)]
+        pk, pid, begin, send = self.ops.shuffle_partition(gk, g, self.x.bits, "_g")
         recv = self.x.exchange_counts(send)
-        order = pid.to(torch.int64) & 0xFFFFFFFF
-        rk = self.x.all_to_all(pk, send, recv)
+        # partials are tiny: compact the (16-row aligned) regions and use the plain contiguous all-to-all
+        sel = torch.cat([torch.arange(begin[p], begin[p] + send[p], device=pk.device) for p in range(self.x.world)])
+        order = pid.to(torch.int64)[sel] & 0xFFFFFFFF
+        rk = self.x.all_to_all(pk[sel].contiguous(), send, recv)
         rparts = [self.x.all_to_all(p.index_select(0, order).contiguous(), send, recv) for p in parts]
         # 3. merge: SUM/COUNT add, MIN/MAX combine
         mf = [SUM if f in (SUM, COUNT) else f for f in pf]
@@ -236,8 +324,7 @@ def bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, Cloc
     for _ in range(args.steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        bk, bi, brecv = sj.shuffle(build, nb)
-        pk, pi, precv = sj.shuffle(probe, npb)
+        (bk, bi, _bs), (pk, pi, _ps) = sj.shuffle_both(build, nb, probe, npb)
         e1.record()
         cnt, pairs = ops.hash_join(bk, int(bk.numel()), pk, int(pk.numel()), int(npb * 1.25) + 4096)
         torch.cuda.synchronize()

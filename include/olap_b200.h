@@ -157,10 +157,12 @@ OLAP_API uint32_t olap_partition_of(int64_t key, int32_t bits);
 /* Multi-GPU key sharding (no reference analogue: README.md:414 "No multi-GPU support yet").  Same kernel as
  * olap_radix_partition_i64 but the destination (one of 2^bits ranks) comes from mix64(key ^ salt), independent of
  * the bits the local join partitions on.  Partition p is the contiguous send region for rank p, so the output feeds
- * an NCCL all-to-all (torch.distributed.all_to_all_single) with no staging copy.                                 */
+ * an NCCL all-to-all with no staging copy.  out_part_count (dptr, 2^bits u32, nullable): when given, every region
+ * starts on a multiple of 16 rows (NCCL peer copies need 16-byte aligned segments to run at full NVLink speed), the
+ * row count of region p is out_part_count[p], and the output arrays must hold n_rows + 16 * 2^bits rows.          */
 OLAP_API olap_status olap_shuffle_partition_i64(olap_ctx* ctx, const int64_t* keys, const uint32_t* row_ids, uint64_t n_rows,
                                                 int32_t bits, int64_t* out_keys, uint32_t* out_row_ids, uint32_t* out_part_begin,
-                                                void* stream);
+                                                uint32_t* out_part_count, void* stream);
 OLAP_API uint32_t olap_shuffle_dest_of(int64_t key, int32_t bits);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -23,12 +23,20 @@ class HostOps:
     def empty(self, n, dtype):
         return torch.empty(max(int(n), 0), dtype=dtype)
 
-    def shuffle_partition(self, keys, n, bits):
+    def shuffle_partition(self, keys, n, bits, tag=""):
+        """Same contract as DeviceOps.shuffle_partition: regions start on multiples of 16 rows, (begin, count) per rank."""
         k = keys[:n].numpy()
         dest = np.array([self.lib.olap_shuffle_dest_of(int(x), bits) for x in k], np.int64) if bits else np.zeros(n, np.int64)
-        order = np.argsort(dest, kind="stable")
-        begin = np.concatenate([[0], np.cumsum(np.bincount(dest, minlength=1 << bits))]).tolist()
-        return torch.from_numpy(k[order].copy()), torch.from_numpy(order.astype(np.int32)), begin
+        P = 1 << bits
+        count = np.bincount(dest, minlength=P).tolist()
+        begin, end = [], 0
+        for c in count:
+            b = (end + 15) // 16 * 16; begin.append(b); end = b + c
+        ok = np.zeros(n + 16 * P, np.int64); oi = np.zeros(n + 16 * P, np.int32)
+        for p in range(P):
+            rows = np.nonzero(dest == p)[0]
+            ok[begin[p]:begin[p] + count[p]] = k[rows]; oi[begin[p]:begin[p] + count[p]] = rows
+        return torch.from_numpy(ok), torch.from_numpy(oi), begin + [end], count
 
     def hash_join(self, bk, nb, pk, npb, max_matches, strategy=-1):
         cnt, pairs = O.hash_join_i64(bk[:nb].numpy(), pk[:npb].numpy(), max_matches=max_matches)
