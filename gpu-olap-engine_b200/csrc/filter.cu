@@ -8,9 +8,11 @@
 
 namespace olap {
 
-constexpr int kFilterThreads = 256;
-constexpr int kFilterPairs = 4;                                   // 128-bit loads (2 rows) per thread per tile
-constexpr int kFilterTile = kFilterThreads * kFilterPairs * 2;    // 2048 rows per tile
+constexpr int kFilterThreads = 512;
+constexpr int kFilterQuads = 2;                                   // 256-bit loads (4 consecutive rows) per thread per tile
+constexpr int kFilterTile = kFilterThreads * kFilterQuads * 4;    // 4096 rows per tile
+constexpr int kScanQuads = 2;
+constexpr int kScanTile = kFilterThreads * kScanQuads * 4;        // look-back kernel: 4096-row tiles, selected row ids staged in smem
 constexpr int kMaxCompactCols = 8;
 
 struct CompactCols {
@@ -18,6 +20,116 @@ struct CompactCols {
   uint64_t* out[kMaxCompactCols];
   int n;
 };
+
+// The comparison operator is dispatched once per 4 (or 8) rows, not per row: the switch sits outside the row loop.
+template <class T, int N>
+__device__ __forceinline__ void and_cmp(int op, const T (&l)[N], const T (&r)[N], bool (&f)[N]) {
+  switch (op) {
+    case OLAP_EQ:
+#pragma unroll
+      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] == r[i];
+      break;
+    case OLAP_NE:
+#pragma unroll
+      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] != r[i];
+      break;
+    case OLAP_LT:
+#pragma unroll
+      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] < r[i];
+      break;
+    case OLAP_LE:
+#pragma unroll
+      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] <= r[i];
+      break;
+    case OLAP_GT:
+#pragma unroll
+      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] > r[i];
+      break;
+    case OLAP_GE:
+#pragma unroll
+      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] >= r[i];
+      break;
+    default:  // executor.rs:464: an unknown operator matches no row
+#pragma unroll
+      for (int i = 0; i < N; i++) f[i] = false;
+  }
+}
+
+// evaluates the conjunction on the 4 consecutive rows starting at row0 (a multiple of 4); rows >= n never pass
+template <bool VEC>
+__device__ __forceinline__ void eval_quad(const TermPack& terms, uint64_t row0, uint64_t n, bool (&f)[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; e++) f[e] = row0 + e < n;
+#pragma unroll 1
+  for (int k = 0; k < terms.n; k++) {
+    uint64_t l[4], r[4];
+    if (VEC && row0 + 3 < n) {
+      const u64x4 a = ld_stream_u64x4(terms.lhs[k] + row0);
+      l[0] = a.a; l[1] = a.b; l[2] = a.c; l[3] = a.d;
+      if (terms.rhs[k]) { const u64x4 b = ld_stream_u64x4(terms.rhs[k] + row0); r[0] = b.a; r[1] = b.b; r[2] = b.c; r[3] = b.d; }
+      else { r[0] = r[1] = r[2] = r[3] = (uint64_t)terms.lit[k]; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const bool in = row0 + e < n;
+        l[e] = in ? ld_stream_u64(terms.lhs[k] + row0 + e) : 0;
+        r[e] = (in && terms.rhs[k]) ? ld_stream_u64(terms.rhs[k] + row0 + e) : (uint64_t)terms.lit[k];
+      }
+    }
+    if (terms.type[k] == OLAP_F64) {
+      double dl[4], dr[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) { dl[e] = __longlong_as_double((long long)l[e]); dr[e] = __longlong_as_double((long long)r[e]); }
+      and_cmp<double, 4>(terms.op[k], dl, dr, f);
+    } else {
+      long long il[4], ir[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) { il[e] = (long long)l[e]; ir[e] = (long long)r[e]; }
+      and_cmp<long long, 4>(terms.op[k], il, ir, f);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_mask4(uint8_t* out_mask, uint64_t row0, uint64_t n, const bool (&f)[4]) {
+  if (row0 + 3 < n && ((uintptr_t)(out_mask + row0) & 3) == 0)
+    *reinterpret_cast<uint32_t*>(out_mask + row0) = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);
+  else {
+#pragma unroll
+    for (int e = 0; e < 4; e++) if (row0 + e < n) out_mask[row0 + e] = f[e];
+  }
+}
+
+// Mask and/or count only (the FilterParams contract, filter_kernel.rs:17-28): a pure streaming kernel -- no ranking,
+// no inter-tile dependency; one global atomic per CTA for the count.
+template <bool VEC>
+__global__ void __launch_bounds__(kFilterThreads) filter_mask_kernel(TermPack terms, uint64_t n, uint8_t* __restrict__ out_mask,
+                                                                     unsigned long long* __restrict__ out_count) {
+  unsigned cnt = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * kFilterTile;
+  for (uint64_t base = blockIdx.x * (uint64_t)kFilterTile; base < n; base += stride) {
+    bool f[kFilterQuads][4];
+#pragma unroll
+    for (int q = 0; q < kFilterQuads; q++) eval_quad<VEC>(terms, base + (uint64_t)(q * kFilterThreads + threadIdx.x) * 4, n, f[q]);
+#pragma unroll
+    for (int q = 0; q < kFilterQuads; q++) {
+      const uint64_t row0 = base + (uint64_t)(q * kFilterThreads + threadIdx.x) * 4;
+      if (out_mask && row0 < n) store_mask4(out_mask, row0, n, f[q]);
+      cnt += (unsigned)f[q][0] + f[q][1] + f[q][2] + f[q][3];
+    }
+  }
+  if (out_count) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    __shared__ unsigned s_c[kFilterThreads / 32];
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+      for (int w = 0; w < kFilterThreads / 32; w++) t += s_c[w];
+      if (t) atomicAdd(out_count, t);
+    }
+  }
+}
 
 // tile descriptor for the look-back: [63:62] status (0 = not ready, 1 = tile aggregate, 2 = inclusive prefix)
 constexpr uint64_t kStAgg = 1ULL << 62, kStPrefix = 2ULL << 62, kStMask = (1ULL << 62) - 1;
@@ -58,15 +170,19 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t* status, uint64_
   return excl;
 }
 
-// work[0] = tile ticket, work[1..] = tile descriptors.  VEC: all predicate columns are 16-byte aligned.
+// Selection vector and/or fused compaction of up to 8 columns, row order preserved: single pass with a decoupled
+// look-back over 16384-row tiles.  work[0] = tile ticket, work[1..] = tile descriptors.
 template <bool VEC>
 __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(TermPack terms, uint64_t n, uint64_t n_tiles,
                                                                      uint8_t* __restrict__ out_mask, uint32_t* __restrict__ out_sel,
                                                                      CompactCols cc, uint64_t* __restrict__ out_count,
                                                                      uint64_t* __restrict__ work) {
+  constexpr int W = kFilterThreads / 32;
   __shared__ uint64_t s_tile;
-  __shared__ uint32_t s_warp[kFilterPairs][kFilterThreads / 32];
+  __shared__ uint32_t s_warp[kScanQuads * W];
   __shared__ uint64_t s_excl;
+  __shared__ uint32_t s_total;
+  __shared__ uint32_t s_sel[kScanTile];  // the tile's passing row ids, compacted: written out with fully coalesced stores
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint64_t* status = work + 1;
 
@@ -75,80 +191,67 @@ __global__ void __launch_bounds__(kFilterThreads) filter_scan_kernel(TermPack te
     __syncthreads();
     const uint64_t tile = s_tile;
     if (tile >= n_tiles) return;
-    const uint64_t tile_base = tile * (uint64_t)kFilterTile;
+    const uint64_t tile_base = tile * (uint64_t)kScanTile;
 
-    bool f[kFilterPairs][2];
+    bool f[kScanQuads][4];
+    uint32_t rank[kScanQuads];
 #pragma unroll
-    for (int j = 0; j < kFilterPairs; j++) { f[j][0] = true; f[j][1] = true; }
-#pragma unroll 1
-    for (int k = 0; k < terms.n; k++) {
-      uint64_t l[kFilterPairs][2], r[kFilterPairs][2];
+    for (int q = 0; q < kScanQuads; q++) eval_quad<VEC>(terms, tile_base + (uint64_t)(q * kFilterThreads + tid) * 4, n, f[q]);
 #pragma unroll
-      for (int j = 0; j < kFilterPairs; j++) {
-        const uint64_t row = tile_base + (uint64_t)(j * kFilterThreads + tid) * 2;
-        l[j][0] = l[j][1] = 0; r[j][0] = r[j][1] = (uint64_t)terms.lit[k];
-        if (VEC && row + 1 < n) {
-          ulonglong2 v = ld_stream_u64x2(terms.lhs[k] + row);
-          l[j][0] = v.x; l[j][1] = v.y;
-          if (terms.rhs[k]) { ulonglong2 w = ld_stream_u64x2(terms.rhs[k] + row); r[j][0] = w.x; r[j][1] = w.y; }
-        } else {
-          if (row < n) { l[j][0] = ld_stream_u64(terms.lhs[k] + row); if (terms.rhs[k]) r[j][0] = ld_stream_u64(terms.rhs[k] + row); }
-          if (row + 1 < n) { l[j][1] = ld_stream_u64(terms.lhs[k] + row + 1); if (terms.rhs[k]) r[j][1] = ld_stream_u64(terms.rhs[k] + row + 1); }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kFilterPairs; j++) {
-        f[j][0] = f[j][0] && eval_term(terms, k, l[j][0], r[j][0]);
-        f[j][1] = f[j][1] && eval_term(terms, k, l[j][1], r[j][1]);
-      }
-    }
-    // rows past the end never pass; write the mask
-    uint32_t rank[kFilterPairs];
-#pragma unroll
-    for (int j = 0; j < kFilterPairs; j++) {
-      const uint64_t row = tile_base + (uint64_t)(j * kFilterThreads + tid) * 2;
-      f[j][0] = f[j][0] && row < n;
-      f[j][1] = f[j][1] && row + 1 < n;
-      if (out_mask) {
-        if (row + 1 < n) *reinterpret_cast<uchar2*>(out_mask + row) = make_uchar2(f[j][0], f[j][1]);
-        else if (row < n) out_mask[row] = f[j][0];
-      }
-      const unsigned b0 = __ballot_sync(0xffffffffu, f[j][0]), b1 = __ballot_sync(0xffffffffu, f[j][1]);
-      const unsigned lt = (1u << lane) - 1;
-      rank[j] = __popc(b0 & lt) + __popc(b1 & lt);  // passing rows of earlier lanes (both elements precede)
-      if (lane == 0) s_warp[j][warp] = __popc(b0) + __popc(b1);
-    }
-    __syncthreads();
-    if (warp == 0) {  // scan the 32 (pair, warp) totals in row order, then look back across tiles
-      constexpr int W = kFilterThreads / 32;
-      uint32_t c = lane < kFilterPairs * W ? s_warp[lane / W][lane % W] : 0;
+    for (int q = 0; q < kScanQuads; q++) {
+      const uint64_t row0 = tile_base + (uint64_t)(q * kFilterThreads + tid) * 4;
+      if (out_mask && row0 < n) store_mask4(out_mask, row0, n, f[q]);
+      // rows of a quad are consecutive, lanes follow each other: an inclusive warp scan of the per-thread counts ranks them
+      const uint32_t c = (uint32_t)f[q][0] + f[q][1] + f[q][2] + f[q][3];
       uint32_t inc = c;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      rank[q] = inc - c;
+      if (lane == 31) s_warp[q * W + warp] = inc;
+    }
+    __syncthreads();
+    if (warp == 0) {  // scan the (quad, warp) totals in row order (4 per lane), then look back across tiles
+      constexpr int PER = kScanQuads * W / 32;
+      uint32_t v[PER], sum = 0;
+#pragma unroll
+      for (int i = 0; i < PER; i++) { v[i] = s_warp[lane * PER + i]; sum += v[i]; }
+      uint32_t inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
       const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-      if (lane < kFilterPairs * W) s_warp[lane / W][lane % W] = inc - c;
+      uint32_t run = inc - sum;
+#pragma unroll
+      for (int i = 0; i < PER; i++) { s_warp[lane * PER + i] = run; run += v[i]; }
+      if (lane == 0) s_total = total;
+    }
+    __syncthreads();
+    if (warp == 0) {  // warp 0 walks back over the earlier tiles while the other warps stage this tile's row ids
+      const uint32_t total = s_total;
       const uint64_t excl = lookback_exclusive(status, tile, total, lane);
       if (lane == 0) {
         s_excl = excl;
         if (tile == n_tiles - 1 && out_count) *out_count = excl + total;
       }
     }
+#pragma unroll
+    for (int q = 0; q < kScanQuads; q++) {
+      const uint32_t row0 = (uint32_t)(q * kFilterThreads + tid) * 4;
+      uint32_t pos = s_warp[q * W + warp] + rank[q];
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (f[q][e]) s_sel[pos++] = row0 + e;
+    }
     __syncthreads();
-    if (out_sel || cc.n) {
+    {
+      // a warp scattering ~16 four-byte ids over 8 half-filled sectors made this kernel L2-write-transaction bound
+      // (5.7 ms at 2^30 rows); from shared memory every store instruction fills whole sectors
       const uint64_t excl = s_excl;
-#pragma unroll
-      for (int j = 0; j < kFilterPairs; j++) {
-        const uint64_t row = tile_base + (uint64_t)(j * kFilterThreads + tid) * 2;
-        uint64_t dst = excl + s_warp[j][warp] + rank[j];
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          if (f[j][e]) {
-            if (out_sel) out_sel[dst] = (uint32_t)(row + e);
+      const uint32_t total = s_total;
+      for (uint32_t i = tid; i < total; i += kFilterThreads) {
+        const uint64_t row = tile_base + s_sel[i];
+        if (out_sel) out_sel[excl + i] = (uint32_t)row;
 #pragma unroll 1
-            for (int c = 0; c < cc.n; c++) cc.out[c][dst] = ld_stream_u64(cc.in[c] + row + e);
-            dst++;
-          }
-        }
+        for (int c = 0; c < cc.n; c++) cc.out[c][excl + i] = ld_stream_u64(cc.in[c] + row);
       }
     }
     __syncthreads();  // s_tile / s_warp reused by the next tile
@@ -208,6 +311,7 @@ __global__ void __launch_bounds__(256) project_kernel(const uint64_t* __restrict
 }
 
 static inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+static inline bool aligned32(const void* p) { return (((uintptr_t)p) & 31) == 0; }
 
 static olap_status run_filter(olap_ctx* ctx, const olap_filter_term* terms, int32_t n_terms, uint64_t n, uint8_t* out_mask,
                               uint32_t* out_sel, const CompactCols& cc, uint64_t* out_count, uint64_t* host_count, cudaStream_t s) {
@@ -221,14 +325,22 @@ static olap_status run_filter(olap_ctx* ctx, const olap_filter_term* terms, int3
     if (dcount) OLAP_CUDA(cudaMemsetAsync(dcount, 0, 8, s));
   } else {
     const uint64_t n_tiles = (n + kFilterTile - 1) / kFilterTile;
-    uint64_t* work = nullptr;
-    OLAP_TRY(sc.get<uint64_t>(n_tiles + 1, &work));
-    OLAP_CUDA(cudaMemsetAsync(work, 0, (n_tiles + 1) * 8, s));
     bool vec = true;
-    for (int k = 0; k < tp.n; k++) vec = vec && aligned16(tp.lhs[k]) && (!tp.rhs[k] || aligned16(tp.rhs[k]));
-    unsigned grid = (unsigned)(n_tiles < (uint64_t)ctx->sm_count * 8 ? n_tiles : (uint64_t)ctx->sm_count * 8);
-    if (vec) filter_scan_kernel<true><<<grid, kFilterThreads, 0, s>>>(tp, n, n_tiles, out_mask, out_sel, cc, dcount, work);
-    else filter_scan_kernel<false><<<grid, kFilterThreads, 0, s>>>(tp, n, n_tiles, out_mask, out_sel, cc, dcount, work);
+    for (int k = 0; k < tp.n; k++) vec = vec && aligned32(tp.lhs[k]) && (!tp.rhs[k] || aligned32(tp.rhs[k]));
+    if (!out_sel && cc.n == 0) {  // mask / count only: streaming kernel, no inter-tile dependency
+      if (dcount) OLAP_CUDA(cudaMemsetAsync(dcount, 0, 8, s));
+      unsigned grid = (unsigned)(n_tiles < (uint64_t)ctx->sm_count * 4 ? n_tiles : (uint64_t)ctx->sm_count * 4);
+      if (vec) filter_mask_kernel<true><<<grid, kFilterThreads, 0, s>>>(tp, n, out_mask, (unsigned long long*)dcount);
+      else filter_mask_kernel<false><<<grid, kFilterThreads, 0, s>>>(tp, n, out_mask, (unsigned long long*)dcount);
+    } else {
+      const uint64_t s_tiles = (n + kScanTile - 1) / kScanTile;
+      uint64_t* work = nullptr;
+      OLAP_TRY(sc.get<uint64_t>(s_tiles + 1, &work));
+      OLAP_CUDA(cudaMemsetAsync(work, 0, (s_tiles + 1) * 8, s));
+      unsigned grid = (unsigned)(s_tiles < (uint64_t)ctx->sm_count * 3 ? s_tiles : (uint64_t)ctx->sm_count * 3);
+      if (vec) filter_scan_kernel<true><<<grid, kFilterThreads, 0, s>>>(tp, n, s_tiles, out_mask, out_sel, cc, dcount, work);
+      else filter_scan_kernel<false><<<grid, kFilterThreads, 0, s>>>(tp, n, s_tiles, out_mask, out_sel, cc, dcount, work);
+    }
     count_launch(ctx);
     OLAP_CUDA(cudaGetLastError());
   }

@@ -168,3 +168,44 @@ def test_operator_errors(ex):
         ex.execute(g.GpuHashJoin(g.GpuTableScan("sales"), g.GpuTableScan("sales"), [col("k")], [col("k")], g.JoinType.Left))
     with pytest.raises(g.OlapError, match="not registered"):
         ex.execute(g.GpuTableScan("missing"))
+
+
+def make_lineitem(n, seed):
+    """Synthetic lineitem columns of SURVEY.md 8(d) C4 (values are cents / hundredths so f64 products stay exact enough)."""
+    u = lambda s, d: O.gen_uniform_i64(n, seed + s, d)
+    qty = (u(1, 50) + 1).astype(np.float64)
+    price = np.round(qty * (900.0 + u(2, 120001) / 100.0) * 100.0) / 100.0
+    return pa.table({"l_shipdate": u(0, 2526) + 8036, "l_quantity": qty, "l_extendedprice": price, "l_discount": u(3, 11) / 100.0,
+                     "l_tax": u(4, 9) / 100.0, "l_returnflag": u(5, 3), "l_linestatus": u(6, 2)})
+
+
+def test_tpch_q6_shape(ex):
+    # BASELINE config 4 (Q6): shipdate in [1994-01-01, 1995-01-01) AND discount in [0.05, 0.07] AND quantity < 24;
+    # SUM(extendedprice * discount).  Float64 predicates / arithmetic are this core's extension (SURVEY 8(f) rank 3).
+    import gpu_olap_engine_b200 as g
+    t = make_lineitem(400000, 50)
+    tables = {"lineitem": t.to_batches(max_chunksize=150000)}
+    AND = lambda a, b: g.BinaryExpr(a, "AND", b)
+    pred = AND(AND(g.BinaryExpr(col("l_shipdate"), ">=", lit(8766)), g.BinaryExpr(col("l_shipdate"), "<", lit(9131))),
+               AND(AND(g.BinaryExpr(col("l_discount"), ">=", lit("0.05")), g.BinaryExpr(col("l_discount"), "<=", lit("0.07"))),
+                   g.BinaryExpr(col("l_quantity"), "<", lit("24.0"))))
+    plan = g.GpuAggregate(g.GpuFilter(g.GpuTableScan("lineitem"), pred), [], [g.Sum(g.BinaryExpr(col("l_extendedprice"), "*", col("l_discount"))),
+                                                                           g.Count(col("l_quantity"))])
+    got = run_both(ex, plan, tables, exact=False)      # f64 SUM over random data: <= 1e-12 relative (order differs)
+    assert got[0].column(1)[0].as_py() > 1000
+
+
+def test_tpch_q1_shape(ex):
+    # BASELINE config 4 (Q1): shipdate <= 1998-09-02, GROUP BY returnflag * 2 + linestatus, 8 aggregates
+    import gpu_olap_engine_b200 as g
+    t = make_lineitem(300000, 60)
+    tables = {"lineitem": t.to_batches(max_chunksize=100000)}
+    one = lit("1.0")
+    disc_price = g.BinaryExpr(col("l_extendedprice"), "*", g.BinaryExpr(one, "-", col("l_discount")))
+    charge = g.BinaryExpr(disc_price, "*", g.BinaryExpr(one, "+", col("l_tax")))
+    key = g.BinaryExpr(g.BinaryExpr(col("l_returnflag"), "*", lit(2)), "+", col("l_linestatus"))
+    aggs = [g.Sum(col("l_quantity")), g.Sum(col("l_extendedprice")), g.Sum(disc_price), g.Sum(charge), g.Avg(col("l_quantity")),
+            g.Avg(col("l_extendedprice")), g.Avg(col("l_discount")), g.Count(col("l_quantity"))]
+    plan = g.GpuAggregate(g.GpuFilter(g.GpuTableScan("lineitem"), g.BinaryExpr(col("l_shipdate"), "<=", lit(10471))), [key], aggs)
+    got = run_both(ex, plan, tables, sort_by=["((l_returnflag * lit(2)) + l_linestatus)"], exact=False)
+    assert got[0].num_rows == 6
