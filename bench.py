@@ -199,24 +199,41 @@ def run_ours(args):
     ctx.synchronize()
     db2, dp2 = ctx.alloc(nb, np.int64), ctx.alloc(npb, np.int64)
 
+    # Pipelined through the public build-once / probe-per-batch API: the probe side arrives in n_batches batches (the
+    # reference executor's Vec<RecordBatch>); H2D of batch i+1, the join of batch i and D2H of batch i-1's pairs overlap
+    # on three streams.  Everything -- every copy, every kernel -- is inside the timed region.
+    n_batches = 8
+    bsz = npb // n_batches
+    s_comp = torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 0))
+    s_h2d = torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 4))
+    s_d2h = torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 5))
+
     def e2e_step():
-        g._lib.check(ctx.lib.olap_memcpy_h2d(ctx.handle, db2.ptr, hb, nb * 8, None))
-        g._lib.check(ctx.lib.olap_memcpy_h2d(ctx.handle, dp2.ptr, hp, npb * 8, None))
-        c, _ = ctx.hash_join_i64(db2, nb, dp2, npb, max_matches=npb, strategy=g.JOIN_RADIX, out_pairs=pairs)
-        g._lib.check(ctx.lib.olap_memcpy_d2h(ctx.handle, hout, pairs.ptr, c * 8, None))
-        g._lib.check(ctx.lib.olap_stream_synchronize(ctx.handle, None))
-        return c
+        ev_b = torch.cuda.Event(); ev_p = [torch.cuda.Event() for _ in range(n_batches)]
+        g._lib.check(ctx.lib.olap_memcpy_h2d(ctx.handle, db2.ptr, hb, nb * 8, s_h2d.cuda_stream)); ev_b.record(s_h2d)
+        for i in range(n_batches):
+            g._lib.check(ctx.lib.olap_memcpy_h2d(ctx.handle, dp2.ptr + 8 * i * bsz, hp.value + 8 * i * bsz, bsz * 8, s_h2d.cuda_stream))
+            ev_p[i].record(s_h2d)
+        s_comp.wait_event(ev_b)
+        total = 0
+        with g.JoinBuild(ctx, db2, nb, g.JOIN_RADIX) as jb:
+            for i in range(n_batches):
+                s_comp.wait_event(ev_p[i])
+                c = jb.probe(dp2.ptr + 8 * i * bsz, bsz, probe_row_base=i * bsz, out_pairs=pairs.ptr + 8 * total, max_matches=npb - total)
+                ev_j = torch.cuda.Event(); ev_j.record(s_comp); s_d2h.wait_event(ev_j)
+                g._lib.check(ctx.lib.olap_memcpy_d2h(ctx.handle, hout.value + 8 * total, pairs.ptr + 8 * total, c * 8, s_d2h.cuda_stream))
+                total += c
+        s_d2h.synchronize()
+        return total
 
     e2e_step()
     e2e_steps = max(1, min(args.steps, 3))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    ev0.record(stream)
     for _ in range(e2e_steps):
         c = e2e_step()
-    ev1.record(stream)
     torch.cuda.synchronize()
-    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     clocks = sampler.stop()
     # spot-check the host-visible result of the last e2e step
     out = np.ctypeslib.as_array(C.cast(hout, C.POINTER(C.c_uint32)), shape=(2 * npb,)).reshape(-1, 2)
@@ -254,7 +271,8 @@ def run_ours(args):
                    "strategy": "RadixHashJoin"},
         "clocks": clocks,
         "e2e": {"value": rows / (e2e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": rows * 8, "d2h_bytes_per_step": npb * 8 + 8,
-                "ms_per_step": e2e_ms, "steps": e2e_steps},
+                "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "how": "olap_join_build_create + 8 x olap_join_probe on pinned host buffers; H2D / join / D2H pipelined on 3 streams; wall clock"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "partition_kernel<0,true> (probe side)", "achieved": achieved, "peak": peak,
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,

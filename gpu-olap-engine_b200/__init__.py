@@ -5,7 +5,7 @@ this package is the host-side mirror of the reference's operator / kernel-wrappe
 """
 from ._lib import LIB_PATH, OlapError, load  # noqa: F401
 from .core import (AVG, COUNT, EQ, F64, GE, GT, I64, JOIN_AUTO, JOIN_BROADCAST, JOIN_RADIX, JOIN_SORT_MERGE, LE, LT, MAX, MIN,  # noqa: F401
-                   NE, SUM, Context, DeviceBuffer, Term, typed_agg_results)
+                   NE, SUM, Context, DeviceBuffer, JoinBuild, Term, typed_agg_results)
 from . import kernels, plan  # noqa: F401,E402
 from .executor import GpuExecutor, execute  # noqa: F401,E402
 from .plan import (Avg, BinaryExpr, Column, Count, EngineConfig, GpuAggregate, GpuFilter, GpuHashJoin, GpuProjection, GpuTableScan,  # noqa: F401,E402

@@ -274,6 +274,44 @@ class Context:
         return self.lib.olap_launch_count(self.handle)
 
 
+class JoinBuild:
+    """Build side prepared once, probed batch by batch (olap_join_build_create / olap_join_probe)."""
+
+    def __init__(self, ctx: Context, build_keys, n_build: int, strategy: int = JOIN_AUTO, stream=None):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(ctx.lib.olap_join_build_create(ctx.handle, _ptr(build_keys), n_build, strategy, stream, C.byref(h)))
+        self.handle = h.value
+
+    def probe(self, probe_keys, n_probe: int, probe_row_base: int = 0, out_pairs=None, max_matches: int = 0, stream=None) -> int:
+        """Returns this batch's exact match count; pairs (left_row, probe_row_base + local row) go to out_pairs."""
+        cnt = C.c_uint64()
+        st = self.ctx.lib.olap_join_probe(self.handle, _ptr(probe_keys), n_probe, probe_row_base, _ptr(out_pairs),
+                                          max_matches if out_pairs is not None else 0, None, C.byref(cnt), stream)
+        if st == _lib.ERR_OVERFLOW:
+            err = OlapError(st, self.ctx.lib.olap_last_error().decode()); err.count = cnt.value
+            raise err
+        check(st)
+        return cnt.value
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.olap_join_build_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def typed_agg_results(out_aggs: np.ndarray, cap: int, n_groups: int, aggs: Sequence[tuple]):
     """Split the agg-major 8-byte slots (aggregate_kernel.rs:98) into typed arrays."""
     res = []

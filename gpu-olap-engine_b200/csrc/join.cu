@@ -318,6 +318,7 @@ __device__ __forceinline__ uint64_t home_bucket(uint64_t key, int bits, uint64_t
 constexpr int kMaxRound = 8;
 struct Tables {
   Bucket* arena; uint64_t stride; int nr; int bits;
+  uint32_t pid_base;  // added to every probe row id (probe side arriving in batches)
   uint32_t nb[kMaxRound], bb[kMaxRound + 1], pb[kMaxRound + 1];
 };
 __device__ __forceinline__ int table_of(const uint32_t* begin, int nr, uint64_t row) {
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(kBuildThreads) build_kernel(const uint64_t* __
                                                               uint64_t begin, uint64_t end, Bucket* __restrict__ table,
                                                               uint64_t n_buckets, int bits) {
   Tables t;
-  t.arena = table; t.stride = 0; t.nr = 1; t.bits = bits; t.nb[0] = (uint32_t)n_buckets;
+  t.arena = table; t.stride = 0; t.nr = 1; t.bits = bits; t.pid_base = 0; t.nb[0] = (uint32_t)n_buckets;
   const uint64_t stride = (uint64_t)gridDim.x * kBuildThreads;
   for (uint64_t row = begin + blockIdx.x * (uint64_t)kBuildThreads + threadIdx.x; row < end; row += stride)
     build_row(t, 0, ld_stream_u64(keys + row), ids ? ld_stream_u32(ids + row) : (uint32_t)row);
@@ -412,6 +413,8 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Tables& t, con
         pid[j] = live[j] ? (ids ? ld_stream_u32(ids + row) : (uint32_t)row) : 0;
       }
     }
+#pragma unroll
+    for (int j = 0; j < kProbeRows; j++) pid[j] += t.pid_base;
     uint32_t b[kProbeRows];
     int tab[kProbeRows];
     Bucket e[kProbeRows];
@@ -500,11 +503,12 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Tables& t, con
 template <bool VEC>
 __global__ void __launch_bounds__(kProbeThreads, 4) probe_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
                                                                  uint64_t begin, uint64_t end, const Bucket* __restrict__ table,
-                                                                 uint64_t n_buckets, int bits, olap_pair* __restrict__ out,
-                                                                 uint64_t max_matches, unsigned long long* __restrict__ count) {
+                                                                 uint64_t n_buckets, int bits, uint32_t pid_base,
+                                                                 olap_pair* __restrict__ out, uint64_t max_matches,
+                                                                 unsigned long long* __restrict__ count) {
   __shared__ ProbeShared sh;
   __shared__ Tables t;
-  if (threadIdx.x == 0) { t.arena = const_cast<Bucket*>(table); t.stride = 0; t.nr = 1; t.bits = bits; t.nb[0] = (uint32_t)n_buckets; t.pb[0] = 0; t.pb[1] = 0; }
+  if (threadIdx.x == 0) { t.arena = const_cast<Bucket*>(table); t.stride = 0; t.nr = 1; t.bits = bits; t.pid_base = pid_base; t.nb[0] = (uint32_t)n_buckets; t.pb[0] = 0; t.pb[1] = 0; }
   __syncthreads();
   const uint64_t first = begin & ~3ULL;  // tiles start 4-row aligned so vector loads stay aligned; rows < begin are masked
   for (uint64_t tile = first + blockIdx.x * (uint64_t)kProbeTile; tile < end; tile += (uint64_t)gridDim.x * kProbeTile)
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(kProbeThreads, 4) join_rounds_kernel(RoundsArg
   const uint64_t gtid = blockIdx.x * (uint64_t)kProbeThreads + tid, gthreads = (uint64_t)gridDim.x * kProbeThreads;
   for (uint32_t p0 = 0; p0 < a.P; p0 += a.R) {
     const int nr = (int)min((uint32_t)a.R, a.P - p0);
-    if (tid == 0) { t.arena = a.arena; t.stride = a.stride; t.nr = nr; t.bits = a.bits; }
+    if (tid == 0) { t.arena = a.arena; t.stride = a.stride; t.nr = nr; t.bits = a.bits; t.pid_base = 0; }
     if (tid <= nr) { t.bb[tid] = a.bbegin[p0 + tid]; t.pb[tid] = a.pbegin[p0 + tid]; }
     if (tid < nr) t.nb[tid] = max(a.bbegin[p0 + tid + 1] - a.bbegin[p0 + tid], 64u);
     __syncthreads();
@@ -581,71 +585,108 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
   return strtoull(v, nullptr, 10);
 }
 
-static olap_status join_broadcast(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, const uint64_t* pk, uint64_t np, olap_pair* out,
-                                  uint64_t max_matches, unsigned long long* d_count, cudaStream_t s) {
-  const uint64_t nbk = std::max<uint64_t>(nb, 64);  // one 2-slot bucket per build row: load factor 0.5
-  OLAP_TRY(ensure_arena(ctx, nbk * 32));
-  Bucket* table = (Bucket*)ctx->table_arena;
-  OLAP_CUDA(cudaMemsetAsync(table, 0, nbk * 32, s));
-  build_kernel<<<grid_rows(ctx, nb, kBuildThreads, 16), kBuildThreads, 0, s>>>(bk, nullptr, 0, nb, table, nbk, 0);
-  phase_mark(ctx, s, "build");
-  if (aligned32(pk))
-    probe_kernel<true><<<grid_rows(ctx, np, kProbeTile, 8), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, table, nbk, 0, out, max_matches, d_count);
-  else
-    probe_kernel<false><<<grid_rows(ctx, np, kProbeTile, 8), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, table, nbk, 0, out, max_matches, d_count);
-  phase_mark(ctx, s, "probe");
-  count_launch(ctx, 3);
-  OLAP_CUDA(cudaGetLastError());
+// The build side of a join, prepared once and probed by one or many batches of the probe side (the reference executor hands
+// the right side over as a Vec<RecordBatch>; gpu-olap-core/src/executor.rs:66-69).
+struct BuildSide {
+  olap_ctx* ctx = nullptr;
+  int strategy = OLAP_JOIN_RADIX;
+  uint64_t nb = 0;
+  // broadcast: one table for the whole build side
+  Bucket* table = nullptr; uint64_t nbk = 0;
+  // radix: the partitioned build side
+  uint64_t* pkb = nullptr; uint32_t* pib = nullptr; int bits = 0; uint32_t P = 0;
+  std::vector<uint32_t> hb;  // partition boundaries on the host
+  uint64_t max_part = 0;
+};
+
+static olap_status build_side_free(BuildSide& b, cudaStream_t s) {
+  if (b.table) { pool_free(b.ctx, b.table, s); b.table = nullptr; }
+  if (b.pkb) { pool_free(b.ctx, b.pkb, s); b.pkb = nullptr; }
+  if (b.pib) { pool_free(b.ctx, b.pib, s); b.pib = nullptr; }
   return OLAP_OK;
 }
 
-static olap_status join_radix(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, const uint64_t* pk, uint64_t np, olap_pair* out,
-                              uint64_t max_matches, unsigned long long* d_count, cudaStream_t s) {
+static olap_status build_side_prepare(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, int strategy, cudaStream_t s, BuildSide* b) {
+  b->ctx = ctx; b->strategy = strategy; b->nb = nb;
+  if (nb == 0) return OLAP_OK;
+  if (strategy == OLAP_JOIN_BROADCAST) {
+    b->nbk = std::max<uint64_t>(nb, 64);  // one 2-slot bucket per build row: load factor 0.5
+    OLAP_TRY(pool_alloc(ctx, b->nbk * 32, s, (void**)&b->table));
+    OLAP_CUDA(cudaMemsetAsync(b->table, 0, b->nbk * 32, s));
+    build_kernel<<<grid_rows(ctx, nb, kBuildThreads, 16), kBuildThreads, 0, s>>>(bk, nullptr, 0, nb, b->table, b->nbk, 0);
+    count_launch(ctx, 2);
+    phase_mark(ctx, s, "build");
+    OLAP_CUDA(cudaGetLastError());
+    return OLAP_OK;
+  }
   // partitions of ~512 Ki build rows: a 16 MB table each, so a few tables in flight stay L2-resident
   const uint64_t target = env_u64("OLAP_JOIN_PART_ROWS", 512 * 1024);
   int bits = 1;
   while (bits < kMaxPartBits && ((nb + target - 1) / target) > (1ULL << bits)) bits++;
-  const uint32_t P = 1u << bits;
-  const unsigned gmax = (unsigned)ctx->sm_count * kPartCtasPerSm;
-
+  b->bits = bits; b->P = 1u << bits;
   Scratch sc(ctx, s);
-  uint64_t *pkb = nullptr, *pkp = nullptr;
-  uint32_t *pib = nullptr, *pip = nullptr, *hist_b = nullptr, *hist_p = nullptr, *beg = nullptr;
-  OLAP_TRY(sc.get<uint64_t>(nb, &pkb));
-  OLAP_TRY(sc.get<uint32_t>(nb, &pib));
-  OLAP_TRY(sc.get<uint64_t>(np, &pkp));
-  OLAP_TRY(sc.get<uint32_t>(np, &pip));
-  OLAP_TRY(sc.get<uint32_t>((uint64_t)P * gmax, &hist_b));
-  OLAP_TRY(sc.get<uint32_t>((uint64_t)P * gmax, &hist_p));
-  OLAP_TRY(sc.get<uint32_t>(2 * (P + 1), &beg));
-
+  uint32_t *hist = nullptr, *beg = nullptr;
+  OLAP_TRY(pool_alloc(ctx, nb * 8 + 16, s, (void**)&b->pkb));
+  OLAP_TRY(pool_alloc(ctx, nb * 4 + 16, s, (void**)&b->pib));
+  OLAP_TRY(sc.get<uint32_t>((uint64_t)b->P * ctx->sm_count * kPartCtasPerSm, &hist));
+  OLAP_TRY(sc.get<uint32_t>(b->P + 1, &beg));
   PartArgs a;
   memset(&a, 0, sizeof(a));
-  a.bits = bits;
-  a.keys = bk; a.n = nb; a.hist = hist_b; a.out_keys = pkb; a.out_ids = pib;
+  a.bits = bits; a.keys = bk; a.n = nb; a.hist = hist; a.out_keys = b->pkb; a.out_ids = b->pib;
   OLAP_TRY(run_partition(ctx, a, 0, true, beg, s, "hist_build", "partition_build"));
-  a.keys = pk; a.n = np; a.hist = hist_p; a.out_keys = pkp; a.out_ids = pip;
-  OLAP_TRY(run_partition(ctx, a, 0, true, beg + P + 1, s, "hist_probe", "partition_probe"));
-
-  std::vector<uint32_t> h(2 * (P + 1));
-  OLAP_CUDA(cudaMemcpyAsync(h.data(), beg, h.size() * 4, cudaMemcpyDeviceToHost, s));
+  b->hb.resize(b->P + 1);
+  OLAP_CUDA(cudaMemcpyAsync(b->hb.data(), beg, (b->P + 1) * 4, cudaMemcpyDeviceToHost, s));
   OLAP_CUDA(cudaStreamSynchronize(s));
-  const uint32_t* hb = h.data();
-  const uint32_t* hp = h.data() + P + 1;
-  uint64_t max_part = 0;
-  for (uint32_t p = 0; p < P; p++) max_part = std::max<uint64_t>(max_part, hb[p + 1] - hb[p]);
-  const uint64_t nbk = std::max<uint64_t>(max_part, 64);  // buckets per table: exactly 32 B per build row of the largest partition
+  b->max_part = 0;
+  for (uint32_t p = 0; p < b->P; p++) b->max_part = std::max<uint64_t>(b->max_part, b->hb[p + 1] - b->hb[p]);
+  return OLAP_OK;
+}
+
+static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t np, uint32_t pid_base, olap_pair* out, uint64_t max_matches,
+                                    unsigned long long* d_count, cudaStream_t s) {
+  olap_ctx* ctx = b.ctx;
+  if (b.nb == 0 || np == 0) return OLAP_OK;  // executor.rs:231-233: an empty side yields no rows
+  if (b.strategy == OLAP_JOIN_BROADCAST) {
+    if (aligned32(pk))
+      probe_kernel<true><<<grid_rows(ctx, np, kProbeTile, 8), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, b.table, b.nbk, 0, pid_base, out, max_matches, d_count);
+    else
+      probe_kernel<false><<<grid_rows(ctx, np, kProbeTile, 8), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, b.table, b.nbk, 0, pid_base, out, max_matches, d_count);
+    count_launch(ctx);
+    phase_mark(ctx, s, "probe");
+    OLAP_CUDA(cudaGetLastError());
+    return OLAP_OK;
+  }
+  const uint32_t P = b.P;
+  const int bits = b.bits;
+  Scratch sc(ctx, s);
+  uint64_t* pkp = nullptr;
+  uint32_t *pip = nullptr, *hist = nullptr, *beg = nullptr;
+  OLAP_TRY(sc.get<uint64_t>(np, &pkp));
+  OLAP_TRY(sc.get<uint32_t>(np, &pip));
+  OLAP_TRY(sc.get<uint32_t>((uint64_t)P * ctx->sm_count * kPartCtasPerSm, &hist));
+  OLAP_TRY(sc.get<uint32_t>(P + 1, &beg));
+  PartArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bits = bits; a.keys = pk; a.n = np; a.hist = hist; a.out_keys = pkp; a.out_ids = pip;
+  OLAP_TRY(run_partition(ctx, a, 0, true, beg, s, "hist_probe", "partition_probe"));
+  std::vector<uint32_t> hp(P + 1);
+  OLAP_CUDA(cudaMemcpyAsync(hp.data(), beg, (P + 1) * 4, cudaMemcpyDeviceToHost, s));
+  OLAP_CUDA(cudaStreamSynchronize(s));
+  const uint32_t* hb = b.hb.data();
+  const uint64_t nbk = std::max<uint64_t>(b.max_part, 64);  // buckets per table: exactly 32 B per build row of the largest partition
   const uint64_t dbg = env_u64("OLAP_JOIN_DEBUG", 0);  // timing decomposition only: 1 skips probes, 2 skips builds, 4 marks every kernel
   if (env_u64("OLAP_JOIN_ROUND", 0) && !dbg) {
     // opt-in (OLAP_JOIN_ROUND=R): one cooperative persistent kernel, R tables per round.  Measured 23 ms vs 13.8 ms for the
     // stream-overlapped per-partition kernels at C2: the same dependent-latency chains, now exposed between grid syncs.
-    int R = (int)std::min<uint64_t>(kMaxRound, std::max<uint64_t>(1, (72ull << 20) / (nbk * 32)));
-    R = (int)env_u64("OLAP_JOIN_ROUND", R);
+    int R = (int)env_u64("OLAP_JOIN_ROUND", 4);
     if (R > kMaxRound) R = kMaxRound;
     if (R < 1) R = 1;
     OLAP_TRY(ensure_arena(ctx, (uint64_t)R * nbk * 32));
+    uint32_t* dbeg = nullptr;
+    OLAP_TRY(sc.get<uint32_t>(P + 1, &dbeg));
+    OLAP_CUDA(cudaMemcpyAsync(dbeg, hb, (P + 1) * 4, cudaMemcpyHostToDevice, s));
     RoundsArgs ra;
-    ra.bkeys = pkb; ra.bids = pib; ra.pkeys = pkp; ra.pids = pip; ra.bbegin = beg; ra.pbegin = beg + P + 1;
+    ra.bkeys = b.pkb; ra.bids = b.pib; ra.pkeys = pkp; ra.pids = pip; ra.bbegin = dbeg; ra.pbegin = beg;
     ra.P = P; ra.bits = bits; ra.R = R; ra.arena = (Bucket*)ctx->table_arena; ra.stride = nbk;
     ra.out = out; ra.max_matches = max_matches; ra.count = d_count;
     int occ = 0;
@@ -656,6 +697,7 @@ static olap_status join_radix(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, co
     count_launch(ctx);
     phase_mark(ctx, s, "build_probe");
     OLAP_CUDA(cudaGetLastError());
+    OLAP_CUDA(cudaStreamSynchronize(s));  // dbeg / hb stay valid until the kernel is done
     return OLAP_OK;
   }
   int S = (int)std::min<uint64_t>(ctx->streams.size(), env_u64("OLAP_JOIN_STREAMS", 3));
@@ -678,12 +720,12 @@ static olap_status join_radix(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, co
     if (!(dbg & 2)) {
       OLAP_CUDA(cudaMemsetAsync(table, 0, tb * 32, st));
       if (dbg & 4) phase_mark(ctx, st, "p_clear");
-      build_kernel<<<grid_rows(ctx, b1 - b0, kBuildThreads, 16), kBuildThreads, 0, st>>>(pkb, pib, b0, b1, table, tb, bits);
+      build_kernel<<<grid_rows(ctx, b1 - b0, kBuildThreads, 16), kBuildThreads, 0, st>>>(b.pkb, b.pib, b0, b1, table, tb, bits);
       if (dbg & 4) phase_mark(ctx, st, "p_build");
     }
     if (!(dbg & 1))
-      probe_kernel<true><<<grid_rows(ctx, p1 - p0, kProbeTile, 8), kProbeThreads, 0, st>>>(pkp, pip, p0, p1, table, tb, bits, out, max_matches,
-                                                                                        d_count);
+      probe_kernel<true><<<grid_rows(ctx, p1 - p0, kProbeTile, 8), kProbeThreads, 0, st>>>(pkp, pip, p0, p1, table, tb, bits, pid_base, out,
+                                                                                        max_matches, d_count);
     if (dbg & 4) phase_mark(ctx, st, "p_probe");
     launches += 3;
   }
@@ -718,6 +760,19 @@ using namespace olap;
 
 extern "C" {
 
+static olap_status finish_count(olap_ctx* ctx, unsigned long long* d_count, uint64_t* host_count, olap_pair* out_pairs, uint64_t max_matches,
+                                cudaStream_t s) {
+  if (!host_count) return OLAP_OK;
+  OLAP_CUDA(cudaMemcpyAsync(host_count, d_count, 8, cudaMemcpyDeviceToHost, s));
+  OLAP_CUDA(cudaStreamSynchronize(s));
+  if (out_pairs && *host_count > max_matches) {
+    set_error("join produced %llu pairs but max_matches is %llu (count is exact, pairs truncated)", (unsigned long long)*host_count,
+              (unsigned long long)max_matches);
+    return OLAP_ERR_OVERFLOW;
+  }
+  return OLAP_OK;
+}
+
 olap_status olap_hash_join_i64(olap_ctx* ctx, const int64_t* build_keys, uint64_t n_build, const int64_t* probe_keys, uint64_t n_probe,
                                olap_pair* out_pairs, uint64_t max_matches, uint64_t* out_count_dptr, uint64_t* host_count,
                                int32_t strategy, void* stream) {
@@ -741,22 +796,68 @@ olap_status olap_hash_join_i64(olap_ctx* ctx, const int64_t* build_keys, uint64_
   if (!d_count) OLAP_TRY(sc.get<unsigned long long>(1, &d_count));
   OLAP_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
   phase_begin(ctx, s);
+  BuildSide b;
+  olap_status st = OLAP_OK;
   if (n_build && n_probe) {  // executor.rs:231-233: an empty side yields no rows
-    if (strategy == OLAP_JOIN_BROADCAST)
-      OLAP_TRY(join_broadcast(ctx, (const uint64_t*)build_keys, n_build, (const uint64_t*)probe_keys, n_probe, out_pairs, max_matches, d_count, s));
-    else
-      OLAP_TRY(join_radix(ctx, (const uint64_t*)build_keys, n_build, (const uint64_t*)probe_keys, n_probe, out_pairs, max_matches, d_count, s));
+    st = build_side_prepare(ctx, (const uint64_t*)build_keys, n_build, strategy, s, &b);
+    if (st == OLAP_OK) st = build_side_probe(b, (const uint64_t*)probe_keys, n_probe, 0, out_pairs, max_matches, d_count, s);
+    build_side_free(b, s);
   }
   phase_end(ctx, s);
-  if (host_count) {
-    OLAP_CUDA(cudaMemcpyAsync(host_count, d_count, 8, cudaMemcpyDeviceToHost, s));
-    OLAP_CUDA(cudaStreamSynchronize(s));
-    if (out_pairs && *host_count > max_matches) {
-      set_error("join produced %llu pairs but max_matches is %llu (count is exact, pairs truncated)", (unsigned long long)*host_count,
-                (unsigned long long)max_matches);
-      return OLAP_ERR_OVERFLOW;
-    }
+  OLAP_TRY(st);
+  return finish_count(ctx, d_count, host_count, out_pairs, max_matches, s);
+}
+
+}  // extern "C"
+
+struct olap_join_build { BuildSide b; };
+
+extern "C" {
+
+olap_status olap_join_build_create(olap_ctx* ctx, const int64_t* build_keys, uint64_t n_build, int32_t strategy, void* stream,
+                                   olap_join_build** out) {
+  OLAP_REQUIRE(ctx && out, "NULL argument");
+  OLAP_REQUIRE(n_build == 0 || build_keys, "build_keys is NULL");
+  OLAP_REQUIRE(n_build < 0xFFFFFFFFULL, "row ids are u32: the build side must have < 2^32 - 1 rows");
+  OLAP_REQUIRE(strategy == OLAP_JOIN_AUTO || strategy == OLAP_JOIN_RADIX || strategy == OLAP_JOIN_BROADCAST, "unknown join strategy");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream_of(stream);
+  if (strategy == OLAP_JOIN_AUTO) strategy = olap_choose_join_strategy(n_build);
+  auto* h = new olap_join_build();
+  olap_status st = build_side_prepare(ctx, (const uint64_t*)build_keys, n_build, strategy, s, &h->b);
+  if (st != OLAP_OK) { build_side_free(h->b, s); delete h; return st; }
+  *out = h;
+  return OLAP_OK;
+}
+
+olap_status olap_join_probe(olap_join_build* build, const int64_t* probe_keys, uint64_t n_probe, uint32_t probe_row_base, olap_pair* out_pairs,
+                            uint64_t max_matches, uint64_t* out_count_dptr, uint64_t* host_count, void* stream) {
+  OLAP_REQUIRE(build, "build handle is NULL");
+  OLAP_REQUIRE(n_probe == 0 || probe_keys, "probe_keys is NULL");
+  OLAP_REQUIRE(n_probe < 0xFFFFFFFFULL && (uint64_t)probe_row_base + n_probe < 0xFFFFFFFFULL, "row ids are u32");
+  olap_ctx* ctx = build->b.ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream_of(stream);
+  if (!out_pairs) max_matches = 0;
+  Scratch sc(ctx, s);
+  unsigned long long* d_count = (unsigned long long*)out_count_dptr;
+  if (!d_count) OLAP_TRY(sc.get<unsigned long long>(1, &d_count));
+  OLAP_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+  OLAP_TRY(build_side_probe(build->b, (const uint64_t*)probe_keys, n_probe, probe_row_base, out_pairs, max_matches, d_count, s));
+  return finish_count(ctx, d_count, host_count, out_pairs, max_matches, s);
+}
+
+olap_status olap_join_build_destroy(olap_join_build* build) {
+  if (!build) return OLAP_OK;
+  olap_ctx* ctx = build->b.ctx;
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaSetDevice(ctx->device);
+    build_side_free(build->b, ctx->streams[0]);
   }
+  delete build;
   return OLAP_OK;
 }
 

@@ -142,6 +142,16 @@ OLAP_API olap_status olap_hash_join_i64(olap_ctx* ctx, const int64_t* build_keys
                                         const int64_t* probe_keys, uint64_t n_probe, olap_pair* out_pairs,
                                         uint64_t max_matches, uint64_t* out_count_dptr, uint64_t* host_count,
                                         int32_t strategy, void* stream);
+/* Build once, probe per batch: the reference executor receives the right side as a Vec<RecordBatch> (executor.rs:66-69,
+ * EngineConfig.batch_size), so the probe side can stream through while host<->device copies of the neighbouring batches
+ * overlap.  probe_row_base is added to every right_row of this batch; pairs/count are per call.                   */
+typedef struct olap_join_build olap_join_build;
+OLAP_API olap_status olap_join_build_create(olap_ctx* ctx, const int64_t* build_keys, uint64_t n_build, int32_t strategy,
+                                            void* stream, olap_join_build** out);
+OLAP_API olap_status olap_join_probe(olap_join_build* build, const int64_t* probe_keys, uint64_t n_probe, uint32_t probe_row_base,
+                                     olap_pair* out_pairs, uint64_t max_matches, uint64_t* out_count_dptr, uint64_t* host_count,
+                                     void* stream);
+OLAP_API olap_status olap_join_build_destroy(olap_join_build* build);
 /* JoinKernel::choose_strategy (join_kernel.rs:71-77) */
 OLAP_API int32_t olap_choose_join_strategy(uint64_t n_build);
 

@@ -148,6 +148,23 @@ def test_join_edge_keys(ctx, strategy):
     check_join(ctx, np.full(3000, 7, np.int64), np.full(500, 7, np.int64), strategy)  # all-same key: 1.5 M pairs
 
 
+@pytest.mark.parametrize("strategy", [2, 0])
+def test_join_build_once_probe_in_batches(ctx, strategy):
+    # the executor hands the right side over batch by batch (executor.rs:66-69): same match set as the one-shot join
+    import gpu_olap_engine_b200 as g
+    b = O.gen_uniform_i64(300000, 11, 200000); p = O.gen_uniform_i64(700001, 12, 250000)
+    exp_c, exp_pairs = O.hash_join_i64(b, p)
+    db, dp = dev(ctx, b), dev(ctx, p)
+    out = ctx.alloc(2 * exp_c, np.uint32)
+    total, edges = 0, [0, 100000, 100001, 433334, 700001]
+    with g.JoinBuild(ctx, db, len(b), strategy) as jb:
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            total += jb.probe(dp.ptr + 8 * lo, hi - lo, probe_row_base=lo, out_pairs=out.ptr + 8 * total, max_matches=exp_c - total)
+        assert jb.probe(dp.ptr, 0) == 0
+    assert total == exp_c
+    assert (O.sort_pairs(out.to_numpy(2 * total).reshape(-1, 2)) == exp_pairs).all()
+
+
 def test_join_overflow_is_reported(ctx):
     import gpu_olap_engine_b200 as g
     b = np.arange(1000, dtype=np.int64); p = np.arange(1000, dtype=np.int64)
