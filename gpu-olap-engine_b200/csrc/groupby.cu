@@ -382,7 +382,7 @@ __device__ __forceinline__ void smem_table_clear(const GbParams& p, const SmemTa
 // rows whose key finds no room fall through to the global table
 template <int NV>
 __device__ __forceinline__ void smem_update_row(const GbParams& p, const SmemTable& t, uint32_t copy_base, uint64_t key, const uint64_t (&v)[NV],
-                                                bool active) {
+                                                bool active, uint32_t* spill_flag) {
   const uint32_t smask = p.s_slots - 1;
   uint32_t s = (uint32_t)(mix64(key) >> 40) & smask, slot = 0xFFFFFFFFu, probes = 0;
   bool pending = active;
@@ -404,7 +404,10 @@ __device__ __forceinline__ void smem_update_row(const GbParams& p, const SmemTab
     }
   }
   const bool spill = active && slot == 0xFFFFFFFFu;
-  if (__any_sync(0xffffffffu, spill)) global_update_row<NV>(p, key, v, spill);
+  if (__any_sync(0xffffffffu, spill)) {
+    if (spill && spill_flag) *spill_flag = 1;
+    global_update_row<NV>(p, key, v, spill);
+  }
   if (!active || spill) return;
   atomicAdd(t.count + slot, 1u);
 #pragma unroll
@@ -416,6 +419,41 @@ __device__ __forceinline__ void smem_update_row(const GbParams& p, const SmemTab
     }
 }
 
+// folds one pre-aggregated shared-memory slot into the global table (warp-uniform)
+__device__ __forceinline__ void global_merge_slot(const GbParams& p, const SmemTable& t, uint64_t key, uint32_t cnt, uint32_t src, bool active) {
+  const uint64_t s = global_slot(p, key, active);
+  if (!active || s == ~0ULL) return;
+  atomicAdd(p.g_count + s, (unsigned long long)cnt);
+  for (int c = 0; c < p.n_cells; c++) cell_atomic_global(p.cell_op[c], p.g_cells + (uint64_t)c * (p.g_cap + 1) + s, t.cells[(uint64_t)c * t.total + src]);
+}
+
+// folds one pre-aggregated slot (count + cell values of copy c > 0) into copy 0; warp-uniform like smem_update_row
+__device__ __forceinline__ void smem_merge_slot(const GbParams& p, const SmemTable& t, uint64_t key, uint32_t cnt, uint32_t src, bool active) {
+  const uint32_t smask = p.s_slots - 1;
+  uint32_t s = (uint32_t)(mix64(key) >> 40) & smask, slot = 0xFFFFFFFFu, probes = 0;
+  bool pending = active;
+  if (pending && key == kEmptyKey) { slot = p.s_slots; pending = false; }
+  while (__any_sync(0xffffffffu, pending)) {
+    if (pending) {
+      const uint64_t k = *(volatile uint64_t*)(t.keys + s);
+      if (k == key) { slot = s; pending = false; }
+      else {
+        if (k == kEmptyKey) {
+          const uint64_t old = atomicCAS((unsigned long long*)(t.keys + s), (unsigned long long)kEmptyKey, (unsigned long long)key);
+          if (old == kEmptyKey || old == key) { slot = s; pending = false; }
+        }
+        if (pending) { s = (s + 1) & smask; if (++probes >= p.s_slots) pending = false; }
+      }
+    }
+  }
+  // copy 0 is full (the union of the copies' keys exceeds it): this key lives in the global table only
+  const bool spill = active && slot == 0xFFFFFFFFu;
+  if (__any_sync(0xffffffffu, spill)) global_merge_slot(p, t, key, cnt, src, spill);
+  if (!active || spill) return;
+  atomicAdd(t.count + slot, cnt);
+  for (int c = 0; c < p.n_cells; c++) cell_atomic_shared(p.cell_op[c], t.cells + (uint64_t)c * t.total + slot, t.cells[(uint64_t)c * t.total + src]);
+}
+
 template <int NV>
 __global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -423,14 +461,25 @@ __global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
   smem_table_clear(p, t);
   __syncthreads();
   const uint32_t copy_base = (threadIdx.x & (p.s_copies - 1)) * t.slots1;
-  const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
-  for (uint64_t base = blockIdx.x * tile; base < p.n; base += (uint64_t)gridDim.x * tile) {
+  const uint64_t tile = (uint64_t)kGbThreads * kGbRows, stride = (uint64_t)gridDim.x * tile;
+  // software pipeline: the next tile's rows are in flight while this tile's dependent shared-memory updates run
+  uint64_t nkey[kGbRows], nv[kGbRows][NV];
+  bool npass[kGbRows];
+  uint64_t base = blockIdx.x * tile;
+  if (base < p.n) load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, 0, p.n, nkey, nv, npass);
+  for (; base < p.n; base += stride) {
     uint64_t key[kGbRows], v[kGbRows][NV];
     bool pass[kGbRows];
-    load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, 0, p.n, key, v, pass);
 #pragma unroll
     for (int j = 0; j < kGbRows; j++) {
-      smem_update_row<NV>(p, t, copy_base, key[j], v[j], pass[j]);
+      key[j] = nkey[j]; pass[j] = npass[j];
+#pragma unroll
+      for (int q = 0; q < NV; q++) v[j][q] = nv[j][q];
+    }
+    if (base + stride < p.n) load_rows<NV, true>(p, base + stride + (uint64_t)threadIdx.x * kGbRows, 0, p.n, nkey, nv, npass);
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++) {
+      smem_update_row<NV>(p, t, copy_base, key[j], v[j], pass[j], nullptr);
       __syncwarp();
     }
   }
@@ -440,10 +489,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
     const uint32_t i = i0 + threadIdx.x;
     const uint32_t cnt = i < t.total ? t.count[i] : 0;
     const uint64_t key = (cnt && i % t.slots1 != p.s_slots) ? t.keys[i] : kEmptyKey;
-    const uint64_t s = global_slot(p, key, cnt != 0);
-    if (!cnt || s == ~0ULL) continue;
-    atomicAdd(p.g_count + s, (unsigned long long)cnt);
-    for (int c = 0; c < p.n_cells; c++) cell_atomic_global(p.cell_op[c], p.g_cells + (uint64_t)c * (p.g_cap + 1) + s, t.cells[(uint64_t)c * t.total + i]);
+    global_merge_slot(p, t, key, cnt, i, cnt != 0);
   }
 }
 
@@ -453,35 +499,66 @@ template <int NV>
 __global__ void __launch_bounds__(kGbThreads) gb_part_smem_kernel(GbParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_base;
-  __shared__ uint32_t s_groups;
+  __shared__ uint32_t s_groups, s_spill;
   const SmemTable t = smem_table(p, smem_raw);
   const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
   for (uint32_t part = blockIdx.x; part < p.n_parts; part += gridDim.x) {
     smem_table_clear(p, t);
-    if (threadIdx.x == 0) s_groups = 0;
+    if (threadIdx.x == 0) { s_groups = 0; s_spill = 0; }
     __syncthreads();
     const uint64_t begin = p.part_begin[part], end = p.part_begin[part + 1];
-    for (uint64_t base = begin & ~3ULL; base < end; base += tile) {
+    const uint32_t copy_base = (threadIdx.x & (p.s_copies - 1)) * t.slots1;
+    uint64_t nkey[kGbRows], nv[kGbRows][NV];
+    bool npass[kGbRows];
+    uint64_t base = begin & ~3ULL;
+    if (base < end) load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, begin, end, nkey, nv, npass);
+    for (; base < end; base += tile) {
       uint64_t key[kGbRows], v[kGbRows][NV];
       bool pass[kGbRows];
-      load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, begin, end, key, v, pass);
 #pragma unroll
       for (int j = 0; j < kGbRows; j++) {
-        smem_update_row<NV>(p, t, 0, key[j], v[j], pass[j]);
+        key[j] = nkey[j]; pass[j] = npass[j];
+#pragma unroll
+        for (int q = 0; q < NV; q++) v[j][q] = nv[j][q];
+      }
+      if (base + tile < end) load_rows<NV, true>(p, base + tile + (uint64_t)threadIdx.x * kGbRows, begin, end, nkey, nv, npass);
+#pragma unroll
+      for (int j = 0; j < kGbRows; j++) {
+        smem_update_row<NV>(p, t, copy_base, key[j], v[j], pass[j], &s_spill);
         __syncwarp();
       }
     }
     __syncthreads();
+    if (s_spill) {  // some row went to the global table while its key may sit in another copy: this partition goes there entirely
+      for (uint32_t i0 = 0; i0 < t.total; i0 += kGbThreads) {
+        const uint32_t i = i0 + threadIdx.x;
+        const uint32_t cnt = i < t.total ? t.count[i] : 0;
+        const uint64_t key = (cnt && i % t.slots1 != p.s_slots) ? t.keys[i] : kEmptyKey;
+        global_merge_slot(p, t, key, cnt, i, cnt != 0);
+      }
+      __syncthreads();
+      continue;
+    }
+    // fold copies 1.. into copy 0; a slot that finds copy 0 full goes (pre-aggregated) to the global table instead, so the
+    // direct output below and the final extraction of the global table stay disjoint
+    for (uint32_t i0 = t.slots1; i0 < t.total; i0 += kGbThreads) {
+      const uint32_t i = i0 + threadIdx.x;
+      const uint32_t cnt = i < t.total ? t.count[i] : 0;
+      const uint64_t key = (cnt && i % t.slots1 != p.s_slots) ? t.keys[i] : kEmptyKey;
+      smem_merge_slot(p, t, key, cnt, i, cnt != 0);
+      __syncwarp();
+    }
+    __syncthreads();
     // count the groups, reserve a dense output range with one global atomic, write them out
     uint32_t mine = 0;
-    for (uint32_t i = threadIdx.x; i < t.total; i += kGbThreads) mine += t.count[i] != 0;
+    for (uint32_t i = threadIdx.x; i < t.slots1; i += kGbThreads) mine += t.count[i] != 0;
     uint32_t my_off = 0;
     if (mine) my_off = atomicAdd(&s_groups, mine);
     __syncthreads();
     if (threadIdx.x == 0 && s_groups) s_base = atomicAdd(p.out_n, (unsigned long long)s_groups);
     __syncthreads();
     uint64_t g = s_base + my_off;
-    for (uint32_t i = threadIdx.x; i < t.total; i += kGbThreads) {
+    for (uint32_t i = threadIdx.x; i < t.slots1; i += kGbThreads) {
       const uint32_t cnt = t.count[i];
       if (!cnt) continue;
       if (g < p.out_cap) {
@@ -606,7 +683,10 @@ static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups
   if (need < 64) need = 64;
   const uint64_t bytes = (need + 1) * slot_bytes(p) + 16;
   if (bytes <= 200 * 1024) {
-    q.s_slots = (uint32_t)need; q.s_copies = 1;
+    uint64_t copies = 1;  // replicate small tables so that 512 threads do not hammer a few dozen slots (2 CTAs per SM: 100 KB each)
+    while (copies < 16 && ((need + 1) * slot_bytes(p) * copies * 2 + 16) <= 100 * 1024) copies <<= 1;
+    q.s_slots = (uint32_t)need; q.s_copies = (uint32_t)copies;
+    const uint64_t bytes = (need + 1) * slot_bytes(p) * copies + 16;
     const unsigned per_sm = bytes <= 100 * 1024 ? 2 : 1;
     GB_DISPATCH_NV(p.n_vcols, {
       OLAP_CUDA(cudaFuncSetAttribute(gb_part_smem_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -681,7 +761,7 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
   for (int attempt = 0;; attempt++) {
     Scratch tsc(ctx, s);
     // regime
-    const uint64_t sbytes = slot_bytes(p), budget = 96 * 1024;  // shared regime: two CTAs per SM
+    const uint64_t sbytes = slot_bytes(p), budget = 96 * 1024;  // shared regime: two CTAs per SM (a 50 KB budget / 4 CTAs measured no faster)
     uint64_t need = pow2_at_least((n_groups_hint * 4 + 2) / 3);
     if (need < 16) need = 16;
     const bool shared = keys && attempt == 0 && (need + 1) * sbytes + 16 <= budget;

@@ -242,6 +242,23 @@ def test_group_by_i64_regimes(ctx, G, hint):
     check_group_by(ctx, k, [v] * 5, ALL5, hint)
 
 
+@pytest.mark.parametrize("G,hint", [(50000, 50000), (50000, 20000), (50000, 3000), (700000, 700000), (3000000, 3000000)])
+def test_group_by_partitioned_regime(ctx, G, hint):
+    # >= 2^20 rows and more groups than a shared-memory table holds: radix-partitioned aggregation.  hint < G makes the
+    # per-partition tables overflow (rows spill to the global table) -- the result must not change
+    n = (1 << 21) + 5
+    k = O.gen_uniform_i64(n, 4, G) * 7919 - 1000; v = O.gen_uniform_i64(n, 5, 1 << 20) - (1 << 19); f = O.gen_dyadic_f64(n, 6, 1 << 20)
+    check_group_by(ctx, k, [v, v, v, v, v, f, f], ALL5 + [O.SUM, O.MIN], hint)
+
+
+def test_group_by_partitioned_with_fused_filter(ctx):
+    import gpu_olap_engine_b200 as g
+    n = 1 << 21
+    k = O.gen_uniform_i64(n, 4, 40000); v = O.gen_uniform_i64(n, 5, 1 << 20)
+    mask = O.filter_mask_i64(v, O.GT, literal=1 << 19)
+    check_group_by(ctx, k, [v, v], [O.SUM, O.COUNT], 40000, terms_fn=lambda d: [g.Term(d[0], g.GT, 1 << 19)], mask=mask)
+
+
 def test_group_by_f64_dyadic_bit_exact_and_random_tolerance(ctx):
     n = 300000
     k = O.gen_uniform_i64(n, 4, 500); f = O.gen_dyadic_f64(n, 6, 1 << 20); r = O.gen_unit_f64(n, 7) - 0.5
