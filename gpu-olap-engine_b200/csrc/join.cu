@@ -15,7 +15,6 @@
 // Table slots carry a generation tag, so the table arena is never cleared between partitions or joins.
 #include "common.cuh"
 
-#include <cooperative_groups.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -280,27 +279,29 @@ static olap_status run_partition(olap_ctx* ctx, PartArgs& a, int npay, bool ids,
 //           atomicMax(table[h].maxdisp, d).
 //   probe : reads the home bucket (one sector) and must look further only if maxdisp[h] > 0 -- i.e. only when a key
 //           with the SAME home was displaced (about 8 % of probes at load 0.5), no matter how long the linear-probing
-//           cluster around it is.  Those continuations go to a per-CTA queue and are processed in parallel phases
-//           (one dependent L2 round trip per phase for the whole tile).
+//           cluster around it is.
 // Measured on the way here (scratch/micro2.cu, profiles/r01_*): a CAS-per-slot build of 512 Ki rows took 29 us even
 // with the table in L2 (every failed CAS is a dependent ~1 us round trip; the kernel waits for its longest chain);
 // recycling slots through a generation tag instead of clearing made every insert a read-modify-write of a DRAM-resident
-// line (20 G/s); "walk while the bucket is full / was passed" made each warp loop ~5 times per row group with 4 lanes
-// active (28 us per 2048-row tile of pure dependent latency).  The table is cleared right before its build: a pure
-// write allocates the lines in L2 without a DRAM read.
-// Home bucket = mulhi(hash << partition_bits, n_buckets): any table size (exactly 32 B per build row at load 0.5, no
-// power-of-two rounding), independent of the bits that chose the partition.
-constexpr int kBuildThreads = 256;
-constexpr int kProbeThreads = 256;
-constexpr int kProbeRows = 4;                            // rows per thread per sub-round (one 256-bit key load)
-constexpr int kProbeSub = 2;                             // sub-rounds per tile: the sync/atomic/flush chain is paid once per tile
-constexpr int kProbeTile = kProbeThreads * kProbeRows * kProbeSub;   // 2048 probe rows per tile
+// line (20 G/s).  The table is cleared right before its build: a pure write allocates the lines in L2 without a DRAM read.
+//
+// The first version of these kernels (per-lane loops, a shared-memory continuation queue, two ballots per row) executed
+// 363 warp instructions per probe row and 148 per build row (ncu, profiles/r01_ncu_join_v2_*): it was issue-bound, not
+// memory-bound.  This version keeps every loop warp-uniform, ranks the hits of four rows with one warp scan, walks the
+// rare continuations with all of a thread's chains in flight together, and reuses the partition hash (one multiply).
+constexpr int kJoinThreads = 256;
+constexpr int kJoinRows = 4;                             // rows per thread per sub-round (one 256-bit key load)
+constexpr int kJoinSub = 2;                              // sub-rounds per tile: the sync / flush chain is paid once per tile
+constexpr int kJoinTile = kJoinThreads * kJoinRows * kJoinSub;   // 2048 rows per work item
 constexpr int kProbeStage = 3072;                        // staged pairs per tile (24 KB)
-constexpr int kProbeQueue = 512;                         // continuation queue entries per phase buffer
+constexpr int kClearTile = 8192;                         // buckets zeroed per work item (256 KB)
+constexpr int kMaxParts = 1 << kMaxPartBits;
+constexpr uint32_t kPipeRing = 4;                        // table slots the pipeline cycles through (clear / build / probe / draining)
 
 struct Bucket { uint64_t k0, k1; uint32_t r0, r1, cnt, maxdisp; };  // 32 bytes
 
-// table reads: 256-bit, L2 only (.cg): the rounds kernel rebuilds tables in place, so the non-coherent path is out
+// table reads: 256-bit, L2 only (.cg): tables are rebuilt in place by other CTAs of the same kernel, so the non-coherent
+// path is out
 __device__ __forceinline__ Bucket ld_bucket(const Bucket* p) {
   uint64_t a, b, c, d;
   asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
@@ -309,58 +310,76 @@ __device__ __forceinline__ Bucket ld_bucket(const Bucket* p) {
   return r;
 }
 
-__device__ __forceinline__ uint64_t home_bucket(uint64_t key, int bits, uint64_t n_buckets) {
-  return __umul64hi(mix64(key) << bits, n_buckets);
+// Home bucket: the 32 hash bits below the ones that chose the partition, scaled to the table (any size: exactly one
+// bucket per build row, no power-of-two rounding).  Same multiply as the partition pass.
+__device__ __forceinline__ uint32_t home_bucket(uint64_t key, int bits, uint32_t n_buckets) {
+  return __umulhi((uint32_t)((part_hash(key, 0) << bits) >> 32), n_buckets);
 }
 
-// The tables one kernel works on: table r lives at arena + r * stride and has nb[r] buckets; build rows
-// [bb[r], bb[r+1]) and probe rows [pb[r], pb[r+1]) belong to it.  nr == 1 for the per-partition kernels.
-constexpr int kMaxRound = 8;
-struct Tables {
-  Bucket* arena; uint64_t stride; int nr; int bits;
-  uint32_t pid_base;  // added to every probe row id (probe side arriving in batches)
-  uint32_t nb[kMaxRound], bb[kMaxRound + 1], pb[kMaxRound + 1];
-};
-__device__ __forceinline__ int table_of(const uint32_t* begin, int nr, uint64_t row) {
-  int r = 0;
-  for (int q = 1; q < nr; q++) r += row >= begin[q];
-  return r;
-}
-
-__device__ __forceinline__ void build_row(const Tables& t, int r, uint64_t key, uint32_t id) {
-  Bucket* table = t.arena + (uint64_t)r * t.stride;
-  const uint64_t nb = t.nb[r];
-  const uint64_t home = home_bucket(key, t.bits, nb);
-  uint64_t b = home;
-  uint32_t d = 0;
-  for (;;) {
-    Bucket* bk = table + b;
-    const uint32_t slot = atomicAdd(&bk->cnt, 1u);
-    if (slot == 0) { bk->k0 = key; bk->r0 = id; break; }
-    if (slot == 1) { bk->k1 = key; bk->r1 = id; break; }
-    if (++b == nb) b = 0;
-    d++;
+// four consecutive rows of a partitioned (or plain) relation; rows outside [begin, end) are dead
+template <bool VEC>
+__device__ __forceinline__ void load_rows4(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids, uint64_t begin, uint64_t end,
+                                           uint64_t row0, uint64_t key[4], uint32_t id[4], bool live[4]) {
+  if (VEC && row0 >= begin && row0 + 3 < end) {
+    u64x4 v = ld_stream_u64x4(keys + row0);
+    key[0] = v.a; key[1] = v.b; key[2] = v.c; key[3] = v.d;
+    if (ids) { uint4 w = ld_stream_u32x4(ids + row0); id[0] = w.x; id[1] = w.y; id[2] = w.z; id[3] = w.w; }
+    else { id[0] = (uint32_t)row0; id[1] = (uint32_t)row0 + 1; id[2] = (uint32_t)row0 + 2; id[3] = (uint32_t)row0 + 3; }
+    live[0] = live[1] = live[2] = live[3] = true;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint64_t row = row0 + j;
+      live[j] = row >= begin && row < end;
+      key[j] = live[j] ? ld_stream_u64(keys + row) : 0;
+      id[j] = live[j] ? (ids ? ld_stream_u32(ids + row) : (uint32_t)row) : 0;
+    }
   }
-  if (d) atomicMax(&table[home].maxdisp, d);
 }
 
-// one row per thread: every insert's key load, atomic and stores are in flight together
-__global__ void __launch_bounds__(kBuildThreads) build_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
-                                                              uint64_t begin, uint64_t end, Bucket* __restrict__ table,
-                                                              uint64_t n_buckets, int bits) {
-  Tables t;
-  t.arena = table; t.stride = 0; t.nr = 1; t.bits = bits; t.pid_base = 0; t.nb[0] = (uint32_t)n_buckets;
-  const uint64_t stride = (uint64_t)gridDim.x * kBuildThreads;
-  for (uint64_t row = begin + blockIdx.x * (uint64_t)kBuildThreads + threadIdx.x; row < end; row += stride)
-    build_row(t, 0, ld_stream_u64(keys + row), ids ? ld_stream_u32(ids + row) : (uint32_t)row);
+// Insert one tile of kJoinTile rows starting at `tile` (a multiple of 4 rows).  Called by the whole CTA; no barriers.
+template <bool VEC>
+__device__ __forceinline__ void build_tile(Bucket* __restrict__ table, uint32_t nb, int bits, const uint64_t* __restrict__ keys,
+                                           const uint32_t* __restrict__ ids, uint64_t begin, uint64_t end, uint64_t tile) {
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int sub = 0; sub < kJoinSub; sub++) {
+    const uint64_t row0 = tile + (uint64_t)(sub * kJoinThreads + tid) * kJoinRows;
+    uint64_t key[kJoinRows];
+    uint32_t id[kJoinRows];
+    bool pend[kJoinRows];
+    load_rows4<VEC>(keys, ids, begin, end, row0, key, id, pend);
+    uint32_t home[kJoinRows], b[kJoinRows], d[kJoinRows];
+#pragma unroll
+    for (int j = 0; j < kJoinRows; j++) { home[j] = b[j] = home_bucket(key[j], bits, nb); d[j] = 0; }
+    for (;;) {  // warp-uniform: every lane stays until no lane has an insert pending
+      uint32_t slot[kJoinRows];
+#pragma unroll
+      for (int j = 0; j < kJoinRows; j++) slot[j] = pend[j] ? atomicAdd(&table[b[j]].cnt, 1u) : 0u;  // four L2 atomics in flight
+      bool more = false;
+#pragma unroll
+      for (int j = 0; j < kJoinRows; j++)
+        if (pend[j]) {
+          if (slot[j] < 2) {
+            Bucket* bk = table + b[j];
+            (&bk->k0)[slot[j]] = key[j];
+            (&bk->r0)[slot[j]] = id[j];
+            pend[j] = false;
+          } else {
+            if (++b[j] == nb) b[j] = 0;
+            d[j]++;
+            more = true;
+          }
+        }
+      if (!__any_sync(0xffffffffu, more)) break;
+    }
+#pragma unroll
+    for (int j = 0; j < kJoinRows; j++) if (d[j]) atomicMax(&table[home[j]].maxdisp, d[j]);
+  }
 }
 
 struct ProbeShared {
   uint2 stage[kProbeStage];
-  uint64_t q_key[2][kProbeQueue];
-  uint32_t q_pid[2][kProbeQueue], q_bkt[2][kProbeQueue], q_rem[2][kProbeQueue];
-  uint8_t q_tab[2][kProbeQueue];
-  uint32_t q_n[2];
   uint32_t n;
   unsigned long long base;
 };
@@ -374,117 +393,73 @@ __device__ __forceinline__ void stage_or_spill(uint2* stage, uint32_t idx, uint3
   }
 }
 
-// one continuation step: look at bucket bk for key, emit hits (per-thread smem atomic: continuations are rare)
-__device__ __forceinline__ void probe_step(ProbeShared& sh, const Bucket* table, uint32_t bk, uint64_t key, uint32_t pid, olap_pair* out,
-                                           uint64_t max_matches, unsigned long long* count) {
-  const Bucket x = ld_bucket(table + bk);
-  if (x.cnt >= 1 && x.k0 == key) stage_or_spill(sh.stage, atomicAdd(&sh.n, 1u), x.r0, pid, out, max_matches, count);
-  if (x.cnt >= 2 && x.k1 == key) stage_or_spill(sh.stage, atomicAdd(&sh.n, 1u), x.r1, pid, out, max_matches, count);
-}
-
-// Probe one tile of kProbeTile rows starting at `tile` (a multiple of 4 rows) against the tables in t; rows outside
-// [begin, end) are masked.  Called by the whole CTA.  VEC: keys / ids may be read with 256 / 128-bit loads.
+// Probe one tile of kJoinTile rows starting at `tile` (a multiple of 4 rows) against one table.  Called by the whole CTA.
 template <bool VEC>
-__device__ __forceinline__ void probe_tile(ProbeShared& sh, const Tables& t, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
-                                           uint64_t begin, uint64_t end, uint64_t tile, olap_pair* __restrict__ out, uint64_t max_matches,
+__device__ __forceinline__ void probe_tile(ProbeShared& sh, const Bucket* __restrict__ table, uint32_t nb, int bits, uint32_t pid_base,
+                                           const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids, uint64_t begin, uint64_t end,
+                                           uint64_t tile, olap_pair* __restrict__ out, uint64_t max_matches,
                                            unsigned long long* __restrict__ count) {
   const int tid = threadIdx.x, lane = tid & 31;
-  const unsigned lt = (1u << lane) - 1;
-  if (tid == 0) { sh.n = 0; sh.q_n[0] = 0; sh.q_n[1] = 0; }
+  if (tid == 0) sh.n = 0;
   __syncthreads();
 #pragma unroll 1
-  for (int sub = 0; sub < kProbeSub; sub++) {
-    const uint64_t row0 = tile + (uint64_t)(sub * kProbeThreads + tid) * kProbeRows;
-    uint64_t key[kProbeRows];
-    uint32_t pid[kProbeRows];
-    bool live[kProbeRows];
-    if (VEC && row0 >= begin && row0 + 3 < end) {
-      u64x4 v = ld_stream_u64x4(keys + row0);
-      key[0] = v.a; key[1] = v.b; key[2] = v.c; key[3] = v.d;
-      if (ids) { uint4 w = ld_stream_u32x4(ids + row0); pid[0] = w.x; pid[1] = w.y; pid[2] = w.z; pid[3] = w.w; }
-      else { pid[0] = (uint32_t)row0; pid[1] = (uint32_t)row0 + 1; pid[2] = (uint32_t)row0 + 2; pid[3] = (uint32_t)row0 + 3; }
-      live[0] = live[1] = live[2] = live[3] = true;
-    } else {
+  for (int sub = 0; sub < kJoinSub; sub++) {
+    const uint64_t row0 = tile + (uint64_t)(sub * kJoinThreads + tid) * kJoinRows;
+    uint64_t key[kJoinRows];
+    uint32_t pid[kJoinRows];
+    bool live[kJoinRows];
+    load_rows4<VEC>(keys, ids, begin, end, row0, key, pid, live);
+    uint32_t b[kJoinRows], rem[kJoinRows];
+    Bucket e[kJoinRows];
 #pragma unroll
-      for (int j = 0; j < kProbeRows; j++) {
-        const uint64_t row = row0 + j;
-        live[j] = row >= begin && row < end;
-        key[j] = live[j] ? ld_stream_u64(keys + row) : 0;
-        pid[j] = live[j] ? (ids ? ld_stream_u32(ids + row) : (uint32_t)row) : 0;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kProbeRows; j++) pid[j] += t.pid_base;
-    uint32_t b[kProbeRows];
-    int tab[kProbeRows];
-    Bucket e[kProbeRows];
-#pragma unroll
-    for (int j = 0; j < kProbeRows; j++) {  // all home-bucket loads are in flight before any is consumed
-      tab[j] = table_of(t.pb, t.nr, row0 + j);
-      b[j] = (uint32_t)home_bucket(key[j], t.bits, t.nb[tab[j]]);
+    for (int j = 0; j < kJoinRows; j++) {  // all home-bucket loads are in flight before any is consumed
+      pid[j] += pid_base;
+      b[j] = home_bucket(key[j], bits, nb);
       e[j].cnt = 0; e[j].maxdisp = 0;
-      if (live[j]) e[j] = ld_bucket(t.arena + (uint64_t)tab[j] * t.stride + b[j]);
+      if (live[j]) e[j] = ld_bucket(table + b[j]);
     }
+    // hits of the four rows are ranked with one warp scan and appended with ONE shared-memory atomic per warp
+    bool h0[kJoinRows], h1[kJoinRows];
+    uint32_t nh = 0;
 #pragma unroll
-    for (int j = 0; j < kProbeRows; j++) {
-      const Bucket x = e[j];
-      // every lane is here (convergent): hits are ranked with two ballots and appended with ONE shared-memory atomic
-      // per warp -- a same-address ATOMS costs ~5 cycles, one per hit would dominate the tile
-      const bool h0 = x.cnt >= 1 && x.k0 == key[j], h1 = x.cnt >= 2 && x.k1 == key[j];
-      const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
-      if (m0 | m1) {
-        const uint32_t n0 = __popc(m0);
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&sh.n, n0 + __popc(m1));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (h0) stage_or_spill(sh.stage, base + __popc(m0 & lt), x.r0, pid[j], out, max_matches, count);
-        if (h1) stage_or_spill(sh.stage, base + n0 + __popc(m1 & lt), x.r1, pid[j], out, max_matches, count);
-      }
-      // a key with this home bucket was displaced: queue the row for the continuation phases
-      const bool cont = x.maxdisp != 0;
-      const unsigned mc = __ballot_sync(0xffffffffu, cont);
-      if (mc) {
-        uint32_t qb = 0;
-        if (lane == 0) qb = atomicAdd(&sh.q_n[0], __popc(mc));
-        qb = __shfl_sync(0xffffffffu, qb, 0);
-        if (cont) {
-          const uint32_t qi = qb + __popc(mc & lt);
-          const uint32_t nbk = t.nb[tab[j]];
-          uint32_t nb1 = b[j] + 1;
-          if (nb1 == nbk) nb1 = 0;
-          if (qi < kProbeQueue) {
-            sh.q_key[0][qi] = key[j]; sh.q_pid[0][qi] = pid[j]; sh.q_bkt[0][qi] = nb1; sh.q_rem[0][qi] = x.maxdisp; sh.q_tab[0][qi] = (uint8_t)tab[j];
-          } else {  // queue full (pathological skew): walk the chain right here
-            const Bucket* table = t.arena + (uint64_t)tab[j] * t.stride;
-            for (uint32_t r = x.maxdisp; r; r--) { probe_step(sh, table, nb1, key[j], pid[j], out, max_matches, count); if (++nb1 == nbk) nb1 = 0; }
-          }
-        }
+    for (int j = 0; j < kJoinRows; j++) {
+      h0[j] = e[j].cnt >= 1 && e[j].k0 == key[j];
+      h1[j] = e[j].cnt >= 2 && e[j].k1 == key[j];
+      nh += (uint32_t)h0[j] + (uint32_t)h1[j];
+      rem[j] = e[j].maxdisp;
+    }
+    uint32_t inc = nh;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total) {
+      uint32_t base = 0;
+      if (lane == 31) base = atomicAdd(&sh.n, total);
+      uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + inc - nh;
+#pragma unroll
+      for (int j = 0; j < kJoinRows; j++) {
+        if (h0[j]) stage_or_spill(sh.stage, pos++, e[j].r0, pid[j], out, max_matches, count);
+        if (h1[j]) stage_or_spill(sh.stage, pos++, e[j].r1, pid[j], out, max_matches, count);
       }
     }
-  }
-  __syncthreads();
-  // continuation phases: every queued row looks at its next bucket; rows with displacement left re-queue
-  for (int cur = 0;; cur ^= 1) {
-    const uint32_t qn = min(sh.q_n[cur], (uint32_t)kProbeQueue);
-    if (qn == 0) break;
-    for (uint32_t i = tid; i < qn; i += kProbeThreads) {
-      const uint64_t k = sh.q_key[cur][i];
-      const uint32_t p = sh.q_pid[cur][i], rem = sh.q_rem[cur][i] - 1;
-      const int r = sh.q_tab[cur][i];
-      const uint32_t nbk = t.nb[r];
-      const Bucket* table = t.arena + (uint64_t)r * t.stride;
-      uint32_t bk = sh.q_bkt[cur][i];
-      probe_step(sh, table, bk, k, p, out, max_matches, count);
-      if (rem) {
-        if (++bk == nbk) bk = 0;
-        const uint32_t qi = atomicAdd(&sh.q_n[cur ^ 1], 1u);
-        if (qi < kProbeQueue) { sh.q_key[cur ^ 1][qi] = k; sh.q_pid[cur ^ 1][qi] = p; sh.q_bkt[cur ^ 1][qi] = bk; sh.q_rem[cur ^ 1][qi] = rem; sh.q_tab[cur ^ 1][qi] = (uint8_t)r; }
-        else for (uint32_t q = rem; q; q--) { probe_step(sh, table, bk, k, p, out, max_matches, count); if (++bk == nbk) bk = 0; }
+    // continuations: a key with this home bucket was displaced by up to rem buckets (8 % of rows).  Warp-uniform loop; each
+    // pass moves the first pending chain of every lane one bucket on (one bucket in registers, not four).
+    while (__any_sync(0xffffffffu, (rem[0] | rem[1] | rem[2] | rem[3]) != 0)) {
+      const int js = rem[0] ? 0 : rem[1] ? 1 : rem[2] ? 2 : 3;
+      const bool act = (rem[0] | rem[1] | rem[2] | rem[3]) != 0;
+      uint64_t ks = key[3]; uint32_t bs = b[3], ps = pid[3];
+      if (js == 0) { ks = key[0]; bs = b[0]; ps = pid[0]; }
+      if (js == 1) { ks = key[1]; bs = b[1]; ps = pid[1]; }
+      if (js == 2) { ks = key[2]; bs = b[2]; ps = pid[2]; }
+      if (act) {
+        if (++bs == nb) bs = 0;
+        const Bucket x = ld_bucket(table + bs);
+        if (x.cnt >= 1 && x.k0 == ks) stage_or_spill(sh.stage, atomicAdd(&sh.n, 1u), x.r0, ps, out, max_matches, count);
+        if (x.cnt >= 2 && x.k1 == ks) stage_or_spill(sh.stage, atomicAdd(&sh.n, 1u), x.r1, ps, out, max_matches, count);
+#pragma unroll
+        for (int j = 0; j < kJoinRows; j++) if (js == j) { b[j] = bs; rem[j]--; }
       }
     }
-    __syncthreads();
-    if (tid == 0) sh.q_n[cur] = 0;
-    __syncthreads();
   }
   __syncthreads();
   const uint32_t n = min(sh.n, (uint32_t)kProbeStage);
@@ -492,7 +467,7 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Tables& t, con
   __syncthreads();
   if (out && n) {
     const unsigned long long base = sh.base;
-    for (uint32_t i = tid; i < n; i += kProbeThreads) {
+    for (uint32_t i = tid; i < n; i += kJoinThreads) {
       const unsigned long long pos = base + i;
       if (pos < max_matches) st_stream_u64(out + pos, (uint64_t)sh.stage[i].x | ((uint64_t)sh.stage[i].y << 32));
     }
@@ -500,70 +475,136 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Tables& t, con
   __syncthreads();
 }
 
+// one table, one relation: the single-table (broadcast) strategy and the per-partition fallback
 template <bool VEC>
-__global__ void __launch_bounds__(kProbeThreads, 4) probe_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
-                                                                 uint64_t begin, uint64_t end, const Bucket* __restrict__ table,
-                                                                 uint64_t n_buckets, int bits, uint32_t pid_base,
-                                                                 olap_pair* __restrict__ out, uint64_t max_matches,
-                                                                 unsigned long long* __restrict__ count) {
-  __shared__ ProbeShared sh;
-  __shared__ Tables t;
-  if (threadIdx.x == 0) { t.arena = const_cast<Bucket*>(table); t.stride = 0; t.nr = 1; t.bits = bits; t.pid_base = pid_base; t.nb[0] = (uint32_t)n_buckets; t.pb[0] = 0; t.pb[1] = 0; }
-  __syncthreads();
+__global__ void __launch_bounds__(kJoinThreads) build_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
+                                                             uint64_t begin, uint64_t end, Bucket* __restrict__ table,
+                                                             uint32_t n_buckets, int bits) {
   const uint64_t first = begin & ~3ULL;  // tiles start 4-row aligned so vector loads stay aligned; rows < begin are masked
-  for (uint64_t tile = first + blockIdx.x * (uint64_t)kProbeTile; tile < end; tile += (uint64_t)gridDim.x * kProbeTile)
-    probe_tile<VEC>(sh, t, keys, ids, begin, end, tile, out, max_matches, count);
+  for (uint64_t tile = first + blockIdx.x * (uint64_t)kJoinTile; tile < end; tile += (uint64_t)gridDim.x * kJoinTile)
+    build_tile<VEC>(table, n_buckets, bits, keys, ids, begin, end, tile);
 }
 
-// All partitions in ONE cooperative persistent kernel, R partitions (tables) per round:
-//   clear the R tables -> grid.sync -> build them -> grid.sync -> probe them -> grid.sync
-// Every phase runs across the whole GPU over thousands of rows/tiles (instead of 3 small launches per partition whose
-// ~1.5 waves of CTAs were latency-chain-bound), while the R tables (<= ~64 MB) stay L2-resident between build and probe.
-struct RoundsArgs {
+template <bool VEC>
+__global__ void __launch_bounds__(kJoinThreads, 4) probe_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
+                                                                uint64_t begin, uint64_t end, const Bucket* __restrict__ table,
+                                                                uint32_t n_buckets, int bits, uint32_t pid_base,
+                                                                olap_pair* __restrict__ out, uint64_t max_matches,
+                                                                unsigned long long* __restrict__ count) {
+  __shared__ ProbeShared sh;
+  const uint64_t first = begin & ~3ULL;
+  for (uint64_t tile = first + blockIdx.x * (uint64_t)kJoinTile; tile < end; tile += (uint64_t)gridDim.x * kJoinTile)
+    probe_tile<VEC>(sh, table, n_buckets, bits, pid_base, keys, ids, begin, end, tile, out, max_matches, count);
+}
+
+// ------------------------------------------------------------------------------------------- the join pipeline
+// All partitions in ONE persistent kernel.  Work items (a 256 KB clear, a 2048-row build tile, a 2048-row probe tile) are
+// handed out by a global ticket in this order:
+//     step s = { clear(table of partition s), build(partition s-1), probe(partition s-2) }
+// so three partitions are in flight, ~1300 items apart.  An item waits (thread 0 spins on an acquire load, the CTA on a
+// barrier) until the items it depends on -- all earlier in ticket order, hence already claimed by running CTAs -- have
+// signalled their per-partition counter: build(p) needs every clear(p), probe(p) every build(p), and clear(p) every
+// probe(p - R) because table p reuses slot p mod R of a ring of R L2-resident tables.  No grid-wide barrier, no host
+// round trip per partition, no ramp / tail per partition: the per-partition launches this replaces (768 at C2) were
+// ~1.5 waves of CTAs each.
+struct PipeArgs {
   const uint64_t* bkeys; const uint32_t* bids; const uint64_t* pkeys; const uint32_t* pids;
   const uint32_t* bbegin; const uint32_t* pbegin;  // device, [P + 1]
-  uint32_t P; int bits; int R;
-  Bucket* arena; uint64_t stride;
+  uint32_t P; int bits; uint32_t R; uint32_t pid_base;
+  Bucket* arena; uint64_t stride;                  // ring slot r = arena + r * stride buckets
+  uint32_t* sync;                                  // [0] ticket, then cleared[P], built[P], probed[P]; zeroed before the launch
   olap_pair* out; uint64_t max_matches; unsigned long long* count;
+  uint32_t step_start[kMaxParts + 3];              // first ticket of every step; [P + 2] = number of items
 };
 
-__global__ void __launch_bounds__(kProbeThreads, 4) join_rounds_kernel(RoundsArgs a) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+// tiles of `tile` rows covering [begin & ~3, end)
+__host__ __device__ __forceinline__ uint32_t tiles_of(uint32_t begin, uint32_t end, uint32_t tile) {
+  if (end <= begin) return 0;
+  return (uint32_t)(((uint64_t)end - (begin & ~3u) + tile - 1) / tile);
+}
+struct PartWork { uint32_t n_clear, n_build, n_probe, nbk; };
+__host__ __device__ __forceinline__ PartWork part_work(uint32_t b0, uint32_t b1, uint32_t p0, uint32_t p1) {
+  PartWork w;
+  w.nbk = b1 - b0 > 64u ? b1 - b0 : 64u;           // one bucket per build row
+  const bool active = b1 > b0 && p1 > p0;          // inner join: an empty side yields nothing
+  w.n_clear = active ? (w.nbk + kClearTile - 1) / kClearTile : 0;
+  w.n_build = active ? tiles_of(b0, b1, kJoinTile) : 0;
+  w.n_probe = active ? tiles_of(p0, p1, kJoinTile) : 0;
+  return w;
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void pipe_wait(const uint32_t* counter, uint32_t need) {
+  if (threadIdx.x == 0 && need) while (ld_acquire_u32(counter) < need) __nanosleep(128);
+  __syncthreads();
+}
+__device__ __forceinline__ void pipe_signal(uint32_t* counter) {
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); atomicAdd(counter, 1u); }
+}
+
+__global__ void __launch_bounds__(kJoinThreads, 4) join_pipeline_kernel(const __grid_constant__ PipeArgs a) {
   __shared__ ProbeShared sh;
-  __shared__ Tables t;
+  __shared__ uint32_t s_ticket;
   const int tid = threadIdx.x;
-  const uint64_t gtid = blockIdx.x * (uint64_t)kProbeThreads + tid, gthreads = (uint64_t)gridDim.x * kProbeThreads;
-  for (uint32_t p0 = 0; p0 < a.P; p0 += a.R) {
-    const int nr = (int)min((uint32_t)a.R, a.P - p0);
-    if (tid == 0) { t.arena = a.arena; t.stride = a.stride; t.nr = nr; t.bits = a.bits; t.pid_base = 0; }
-    if (tid <= nr) { t.bb[tid] = a.bbegin[p0 + tid]; t.pb[tid] = a.pbegin[p0 + tid]; }
-    if (tid < nr) t.nb[tid] = max(a.bbegin[p0 + tid + 1] - a.bbegin[p0 + tid], 64u);
+  const uint32_t P = a.P;
+  uint32_t *ticket = a.sync, *cleared = a.sync + 1, *built = cleared + P, *probed = built + P;
+  const uint32_t total = a.step_start[P + 2];
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  for (;;) {
+    const uint32_t t = s_ticket;
     __syncthreads();
-    // 1. clear (a pure write: the lines are allocated in L2 without a DRAM read)
-    for (int r = 0; r < nr; r++) {
-      uint4* tb = reinterpret_cast<uint4*>(a.arena + (uint64_t)r * a.stride);
-      const uint64_t n16 = (uint64_t)t.nb[r] * 2;
-      for (uint64_t i = gtid; i < n16; i += gthreads) tb[i] = make_uint4(0, 0, 0, 0);
+    if (t >= total) break;
+    uint32_t next = 0;
+    if (tid == 0) next = atomicAdd(ticket, 1u);  // in flight while this item runs
+    uint32_t lo = 0, hi = P + 2;                 // step s with step_start[s] <= t < step_start[s + 1]
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.step_start[mid] <= t) lo = mid; else hi = mid; }
+    const uint32_t s = lo;
+    uint32_t idx = t - a.step_start[s];
+    int phase = 0;
+    uint32_t p = s;
+    if (s < P) {
+      const PartWork w = part_work(a.bbegin[s], a.bbegin[s + 1], a.pbegin[s], a.pbegin[s + 1]);
+      if (idx >= w.n_clear) { idx -= w.n_clear; phase = 1; }
+    } else phase = 1;
+    if (phase == 1) {
+      p = s - 1;
+      uint32_t nbd = 0;
+      if (s >= 1 && s <= P) nbd = part_work(a.bbegin[p], a.bbegin[p + 1], a.pbegin[p], a.pbegin[p + 1]).n_build;
+      if (idx >= nbd) { idx -= nbd; phase = 2; p = s - 2; }
     }
-    __threadfence();
-    grid.sync();
-    // 2. build
-    for (uint64_t row = t.bb[0] + gtid; row < t.bb[nr]; row += gthreads)
-      build_row(t, table_of(t.bb, nr, row), ld_stream_u64(a.bkeys + row), ld_stream_u32(a.bids + row));
-    __threadfence();
-    grid.sync();
-    // 3. probe
-    const uint64_t begin = t.pb[0], end = t.pb[nr];
-    for (uint64_t tile = (begin & ~3ULL) + blockIdx.x * (uint64_t)kProbeTile; tile < end; tile += (uint64_t)gridDim.x * kProbeTile)
-      probe_tile<true>(sh, t, a.pkeys, a.pids, begin, end, tile, a.out, a.max_matches, a.count);
-    grid.sync();  // the tables are reused by the next round
+    const uint32_t b0 = a.bbegin[p], b1 = a.bbegin[p + 1], p0 = a.pbegin[p], p1 = a.pbegin[p + 1];
+    const PartWork w = part_work(b0, b1, p0, p1);
+    Bucket* table = a.arena + (uint64_t)(p % a.R) * a.stride;
+    if (phase == 0) {
+      uint32_t need = 0;
+      if (p >= a.R) { const uint32_t q = p - a.R; need = part_work(a.bbegin[q], a.bbegin[q + 1], a.pbegin[q], a.pbegin[q + 1]).n_probe; }
+      pipe_wait(probed + (p >= a.R ? p - a.R : 0), need);
+      const uint32_t c0 = idx * kClearTile, c1 = min(w.nbk, c0 + kClearTile);
+      const u64x4 z = {0, 0, 0, 0};
+      for (uint32_t i = c0 + tid; i < c1; i += kJoinThreads) st_stream_u64x4(table + i, z);
+      pipe_signal(cleared + p);
+    } else if (phase == 1) {
+      pipe_wait(cleared + p, w.n_clear);
+      build_tile<true>(table, w.nbk, a.bits, a.bkeys, a.bids, b0, b1, (b0 & ~3u) + (uint64_t)idx * kJoinTile);
+      pipe_signal(built + p);
+    } else {
+      pipe_wait(built + p, w.n_build);
+      probe_tile<true>(sh, table, w.nbk, a.bits, a.pid_base, a.pkeys, a.pids, p0, p1, (p0 & ~3u) + (uint64_t)idx * kJoinTile, a.out,
+                       a.max_matches, a.count);
+      pipe_signal(probed + p);
+    }
+    if (tid == 0) s_ticket = next;
+    __syncthreads();
   }
 }
 
-static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
-
-// table arena: grown on demand, kept across calls; every table is cleared on its stream right before its build
+// table arena: grown on demand, kept across calls; every table is cleared right before its build
 static olap_status ensure_arena(olap_ctx* ctx, uint64_t bytes) {
   if (ctx->table_arena_bytes >= bytes) return OLAP_OK;
   if (ctx->table_arena) { OLAP_CUDA(cudaDeviceSynchronize()); OLAP_CUDA(cudaFree(ctx->table_arena)); ctx->table_arena = nullptr; ctx->table_arena_bytes = 0; }
@@ -585,6 +626,27 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
   return strtoull(v, nullptr, 10);
 }
 
+static void launch_build(olap_ctx* ctx, const uint64_t* keys, const uint32_t* ids, uint64_t begin, uint64_t end, Bucket* table, uint64_t nbk,
+                         int bits, cudaStream_t s) {
+  const unsigned grid = grid_rows(ctx, end - (begin & ~3ULL), kJoinTile, 8);
+  if (aligned32(keys) && (!ids || aligned32(ids)))
+    build_kernel<true><<<grid, kJoinThreads, 0, s>>>(keys, ids, begin, end, table, (uint32_t)nbk, bits);
+  else
+    build_kernel<false><<<grid, kJoinThreads, 0, s>>>(keys, ids, begin, end, table, (uint32_t)nbk, bits);
+  count_launch(ctx);
+}
+
+static void launch_probe(olap_ctx* ctx, const uint64_t* keys, const uint32_t* ids, uint64_t begin, uint64_t end, const Bucket* table,
+                         uint64_t nbk, int bits, uint32_t pid_base, olap_pair* out, uint64_t max_matches, unsigned long long* count,
+                         cudaStream_t s) {
+  const unsigned grid = grid_rows(ctx, end - (begin & ~3ULL), kJoinTile, 8);
+  if (aligned32(keys) && (!ids || aligned32(ids)))
+    probe_kernel<true><<<grid, kJoinThreads, 0, s>>>(keys, ids, begin, end, table, (uint32_t)nbk, bits, pid_base, out, max_matches, count);
+  else
+    probe_kernel<false><<<grid, kJoinThreads, 0, s>>>(keys, ids, begin, end, table, (uint32_t)nbk, bits, pid_base, out, max_matches, count);
+  count_launch(ctx);
+}
+
 // The build side of a join, prepared once and probed by one or many batches of the probe side (the reference executor hands
 // the right side over as a Vec<RecordBatch>; gpu-olap-core/src/executor.rs:66-69).
 struct BuildSide {
@@ -595,7 +657,8 @@ struct BuildSide {
   Bucket* table = nullptr; uint64_t nbk = 0;
   // radix: the partitioned build side
   uint64_t* pkb = nullptr; uint32_t* pib = nullptr; int bits = 0; uint32_t P = 0;
-  std::vector<uint32_t> hb;  // partition boundaries on the host
+  uint32_t* d_begin = nullptr;  // partition boundaries on the device, [P + 1]
+  std::vector<uint32_t> hb;     // ... and on the host
   uint64_t max_part = 0;
 };
 
@@ -603,6 +666,7 @@ static olap_status build_side_free(BuildSide& b, cudaStream_t s) {
   if (b.table) { pool_free(b.ctx, b.table, s); b.table = nullptr; }
   if (b.pkb) { pool_free(b.ctx, b.pkb, s); b.pkb = nullptr; }
   if (b.pib) { pool_free(b.ctx, b.pib, s); b.pib = nullptr; }
+  if (b.d_begin) { pool_free(b.ctx, b.d_begin, s); b.d_begin = nullptr; }
   return OLAP_OK;
 }
 
@@ -613,29 +677,29 @@ static olap_status build_side_prepare(olap_ctx* ctx, const uint64_t* bk, uint64_
     b->nbk = std::max<uint64_t>(nb, 64);  // one 2-slot bucket per build row: load factor 0.5
     OLAP_TRY(pool_alloc(ctx, b->nbk * 32, s, (void**)&b->table));
     OLAP_CUDA(cudaMemsetAsync(b->table, 0, b->nbk * 32, s));
-    build_kernel<<<grid_rows(ctx, nb, kBuildThreads, 16), kBuildThreads, 0, s>>>(bk, nullptr, 0, nb, b->table, b->nbk, 0);
-    count_launch(ctx, 2);
+    count_launch(ctx);
+    launch_build(ctx, bk, nullptr, 0, nb, b->table, b->nbk, 0, s);
     phase_mark(ctx, s, "build");
     OLAP_CUDA(cudaGetLastError());
     return OLAP_OK;
   }
-  // partitions of ~512 Ki build rows: a 16 MB table each, so a few tables in flight stay L2-resident
+  // partitions of ~512 Ki build rows: a 16 MB table each, so the few tables the pipeline has in flight stay L2-resident
   const uint64_t target = env_u64("OLAP_JOIN_PART_ROWS", 512 * 1024);
   int bits = 1;
   while (bits < kMaxPartBits && ((nb + target - 1) / target) > (1ULL << bits)) bits++;
   b->bits = bits; b->P = 1u << bits;
   Scratch sc(ctx, s);
-  uint32_t *hist = nullptr, *beg = nullptr;
-  OLAP_TRY(pool_alloc(ctx, nb * 8 + 16, s, (void**)&b->pkb));
-  OLAP_TRY(pool_alloc(ctx, nb * 4 + 16, s, (void**)&b->pib));
+  uint32_t* hist = nullptr;
+  OLAP_TRY(pool_alloc(ctx, nb * 8 + 32, s, (void**)&b->pkb));
+  OLAP_TRY(pool_alloc(ctx, nb * 4 + 32, s, (void**)&b->pib));
+  OLAP_TRY(pool_alloc(ctx, (b->P + 1) * 4, s, (void**)&b->d_begin));
   OLAP_TRY(sc.get<uint32_t>((uint64_t)b->P * ctx->sm_count * kPartCtasPerSm, &hist));
-  OLAP_TRY(sc.get<uint32_t>(b->P + 1, &beg));
   PartArgs a;
   memset(&a, 0, sizeof(a));
   a.bits = bits; a.keys = bk; a.n = nb; a.hist = hist; a.out_keys = b->pkb; a.out_ids = b->pib;
-  OLAP_TRY(run_partition(ctx, a, 0, true, beg, s, "hist_build", "partition_build"));
+  OLAP_TRY(run_partition(ctx, a, 0, true, b->d_begin, s, "hist_build", "partition_build"));
   b->hb.resize(b->P + 1);
-  OLAP_CUDA(cudaMemcpyAsync(b->hb.data(), beg, (b->P + 1) * 4, cudaMemcpyDeviceToHost, s));
+  OLAP_CUDA(cudaMemcpyAsync(b->hb.data(), b->d_begin, (b->P + 1) * 4, cudaMemcpyDeviceToHost, s));
   OLAP_CUDA(cudaStreamSynchronize(s));
   b->max_part = 0;
   for (uint32_t p = 0; p < b->P; p++) b->max_part = std::max<uint64_t>(b->max_part, b->hb[p + 1] - b->hb[p]);
@@ -647,11 +711,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   olap_ctx* ctx = b.ctx;
   if (b.nb == 0 || np == 0) return OLAP_OK;  // executor.rs:231-233: an empty side yields no rows
   if (b.strategy == OLAP_JOIN_BROADCAST) {
-    if (aligned32(pk))
-      probe_kernel<true><<<grid_rows(ctx, np, kProbeTile, 8), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, b.table, b.nbk, 0, pid_base, out, max_matches, d_count);
-    else
-      probe_kernel<false><<<grid_rows(ctx, np, kProbeTile, 8), kProbeThreads, 0, s>>>(pk, nullptr, 0, np, b.table, b.nbk, 0, pid_base, out, max_matches, d_count);
-    count_launch(ctx);
+    launch_probe(ctx, pk, nullptr, 0, np, b.table, b.nbk, 0, pid_base, out, max_matches, d_count, s);
     phase_mark(ctx, s, "probe");
     OLAP_CUDA(cudaGetLastError());
     return OLAP_OK;
@@ -661,8 +721,8 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   Scratch sc(ctx, s);
   uint64_t* pkp = nullptr;
   uint32_t *pip = nullptr, *hist = nullptr, *beg = nullptr;
-  OLAP_TRY(sc.get<uint64_t>(np, &pkp));
-  OLAP_TRY(sc.get<uint32_t>(np, &pip));
+  OLAP_TRY(sc.get<uint64_t>(np + 4, &pkp));
+  OLAP_TRY(sc.get<uint32_t>(np + 8, &pip));
   OLAP_TRY(sc.get<uint32_t>((uint64_t)P * ctx->sm_count * kPartCtasPerSm, &hist));
   OLAP_TRY(sc.get<uint32_t>(P + 1, &beg));
   PartArgs a;
@@ -674,42 +734,51 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   OLAP_CUDA(cudaStreamSynchronize(s));
   const uint32_t* hb = b.hb.data();
   const uint64_t nbk = std::max<uint64_t>(b.max_part, 64);  // buckets per table: exactly 32 B per build row of the largest partition
-  const uint64_t dbg = env_u64("OLAP_JOIN_DEBUG", 0);  // timing decomposition only: 1 skips probes, 2 skips builds, 4 marks every kernel
-  if (env_u64("OLAP_JOIN_ROUND", 0) && !dbg) {
-    // opt-in (OLAP_JOIN_ROUND=R): one cooperative persistent kernel, R tables per round.  Measured 23 ms vs 13.8 ms for the
-    // stream-overlapped per-partition kernels at C2: the same dependent-latency chains, now exposed between grid syncs.
-    int R = (int)env_u64("OLAP_JOIN_ROUND", 4);
-    if (R > kMaxRound) R = kMaxRound;
-    if (R < 1) R = 1;
-    OLAP_TRY(ensure_arena(ctx, (uint64_t)R * nbk * 32));
-    uint32_t* dbeg = nullptr;
-    OLAP_TRY(sc.get<uint32_t>(P + 1, &dbeg));
-    OLAP_CUDA(cudaMemcpyAsync(dbeg, hb, (P + 1) * 4, cudaMemcpyHostToDevice, s));
-    RoundsArgs ra;
-    ra.bkeys = b.pkb; ra.bids = b.pib; ra.pkeys = pkp; ra.pids = pip; ra.bbegin = dbeg; ra.pbegin = beg;
-    ra.P = P; ra.bits = bits; ra.R = R; ra.arena = (Bucket*)ctx->table_arena; ra.stride = nbk;
-    ra.out = out; ra.max_matches = max_matches; ra.count = d_count;
-    int occ = 0;
-    OLAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, join_rounds_kernel, kProbeThreads, 0));
-    if (occ < 1) { set_error("join_rounds_kernel does not fit on an SM"); return OLAP_ERR_CUDA; }
-    void* kargs[] = {&ra};
-    OLAP_CUDA(cudaLaunchCooperativeKernel((void*)join_rounds_kernel, dim3((unsigned)(occ * ctx->sm_count)), dim3(kProbeThreads), kargs, 0, s));
-    count_launch(ctx);
+
+  if (env_u64("OLAP_JOIN_PIPE", 1)) {
+    // the join pipeline: one persistent kernel over all partitions (see join_pipeline_kernel)
+    PipeArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    uint64_t R = std::min<uint64_t>(env_u64("OLAP_JOIN_RING", kPipeRing), P);
+    while (R > 1 && R * nbk * 32 > (96ULL << 20)) R--;  // keep the ring within the L2 (skewed partitions: fewer, larger tables)
+    OLAP_TRY(ensure_arena(ctx, R * nbk * 32));
+    uint32_t* sync = nullptr;
+    OLAP_TRY(sc.get<uint32_t>(1 + 3 * (uint64_t)P, &sync));
+    OLAP_CUDA(cudaMemsetAsync(sync, 0, (1 + 3 * (uint64_t)P) * 4, s));
+    pa.bkeys = b.pkb; pa.bids = b.pib; pa.pkeys = pkp; pa.pids = pip; pa.bbegin = b.d_begin; pa.pbegin = beg;
+    pa.P = P; pa.bits = bits; pa.R = (uint32_t)R; pa.pid_base = pid_base;
+    pa.arena = (Bucket*)ctx->table_arena; pa.stride = nbk; pa.sync = sync;
+    pa.out = out; pa.max_matches = max_matches; pa.count = d_count;
+    uint64_t items = 0;
+    for (uint32_t st = 0; st < P + 2; st++) {
+      pa.step_start[st] = (uint32_t)items;
+      if (st < P) items += part_work(hb[st], hb[st + 1], hp[st], hp[st + 1]).n_clear;
+      if (st >= 1 && st <= P) items += part_work(hb[st - 1], hb[st], hp[st - 1], hp[st]).n_build;
+      if (st >= 2) items += part_work(hb[st - 2], hb[st - 1], hp[st - 2], hp[st - 1]).n_probe;
+    }
+    pa.step_start[P + 2] = (uint32_t)items;
+    if (items) {
+      int occ = 0;
+      OLAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, join_pipeline_kernel, kJoinThreads, 0));
+      if (occ < 1) { set_error("join_pipeline_kernel does not fit on an SM"); return OLAP_ERR_CUDA; }
+      const uint64_t grid = std::min<uint64_t>((uint64_t)occ * ctx->sm_count, items);
+      join_pipeline_kernel<<<(unsigned)grid, kJoinThreads, 0, s>>>(pa);
+      count_launch(ctx, 2);
+    }
     phase_mark(ctx, s, "build_probe");
     OLAP_CUDA(cudaGetLastError());
-    OLAP_CUDA(cudaStreamSynchronize(s));  // dbeg / hb stay valid until the kernel is done
     return OLAP_OK;
   }
+
+  // OLAP_JOIN_PIPE=0: three launches per partition on S side streams (kept for A/B timing; 13.8 ms vs the pipeline at C2)
+  const uint64_t dbg = env_u64("OLAP_JOIN_DEBUG", 0);  // timing decomposition only: 1 skips probes, 2 skips builds, 4 marks every kernel
   int S = (int)std::min<uint64_t>(ctx->streams.size(), env_u64("OLAP_JOIN_STREAMS", 3));
   if (dbg & 4) S = 1;
   if (S < 1) S = 1;
   if (S > 8) S = 8;
   OLAP_TRY(ensure_arena(ctx, (uint64_t)S * nbk * 32));
-
-  // fork: tables of different partitions are built and probed on S side streams so their ramps and tails overlap
   OLAP_CUDA(cudaEventRecord(ctx->fork_ev, s));
   for (int k = 0; k < S; k++) OLAP_CUDA(cudaStreamWaitEvent(ctx->streams[k], ctx->fork_ev, 0));
-  uint64_t launches = 0;
   for (uint32_t p = 0; p < P; p++) {
     const uint64_t b0 = hb[p], b1 = hb[p + 1], p0 = hp[p], p1 = hp[p + 1];
     if (b1 == b0 || p1 == p0) continue;  // inner join: an empty side yields nothing
@@ -719,17 +788,14 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     const uint64_t tb = std::max<uint64_t>(b1 - b0, 64);  // this partition's table: one bucket per build row
     if (!(dbg & 2)) {
       OLAP_CUDA(cudaMemsetAsync(table, 0, tb * 32, st));
+      count_launch(ctx);
       if (dbg & 4) phase_mark(ctx, st, "p_clear");
-      build_kernel<<<grid_rows(ctx, b1 - b0, kBuildThreads, 16), kBuildThreads, 0, st>>>(b.pkb, b.pib, b0, b1, table, tb, bits);
+      launch_build(ctx, b.pkb, b.pib, b0, b1, table, tb, bits, st);
       if (dbg & 4) phase_mark(ctx, st, "p_build");
     }
-    if (!(dbg & 1))
-      probe_kernel<true><<<grid_rows(ctx, p1 - p0, kProbeTile, 8), kProbeThreads, 0, st>>>(pkp, pip, p0, p1, table, tb, bits, pid_base, out,
-                                                                                        max_matches, d_count);
+    if (!(dbg & 1)) launch_probe(ctx, pkp, pip, p0, p1, table, tb, bits, pid_base, out, max_matches, d_count, st);
     if (dbg & 4) phase_mark(ctx, st, "p_probe");
-    launches += 3;
   }
-  count_launch(ctx, launches);
   for (int k = 0; k < S; k++) {
     OLAP_CUDA(cudaEventRecord(ctx->join_ev[k], ctx->streams[k]));
     OLAP_CUDA(cudaStreamWaitEvent(s, ctx->join_ev[k], 0));
