@@ -37,6 +37,8 @@ struct PartArgs {
   int bits;
   uint64_t salt;                         // xor-ed into the key before hashing: the multi-GPU shuffle uses bits independent of the local join's
   uint32_t* hist;                        // [P][gridDim.x]: counts, then exclusive offsets after the scan
+  uint32_t* cursor;                      // ALLOC mode: rows handed out so far per partition (global atomics), [P]
+  uint32_t cap;                          // ALLOC mode: partition p owns output rows [p * cap, (p + 1) * cap)
   uint64_t* out_keys;
   uint32_t* out_ids;
   uint64_t* pay_out[kMaxPay];
@@ -136,7 +138,11 @@ __global__ void __launch_bounds__(1024) part_scan_kernel(uint32_t* hist, uint32_
   }
 }
 
-template <int NPAY, bool IDS>
+// ALLOC = false: exact layout; every CTA's output offsets come from the histogram pass (contiguous partitions, no atomics).
+// ALLOC = true : no histogram pass; partition p owns a fixed-capacity region and every tile reserves its run in it with
+//                one global atomic per (tile, partition).  Saves a full read of the keys; a region that overflows (skewed
+//                keys) is reported through cursor[p] > cap and the caller falls back to the exact layout.
+template <int NPAY, bool IDS, bool ALLOC>
 __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) partition_kernel(PartArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* s_key = reinterpret_cast<uint64_t*>(smem_raw);
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
 
   const int P = 1 << a.bits, sh = 64 - a.bits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < P; i += kPartThreads) { s_cnt[i] = 0; s_cursor[i] = a.hist[(uint64_t)i * gridDim.x + blockIdx.x]; }
+  for (int i = tid; i < P; i += kPartThreads) { s_cnt[i] = 0; s_cursor[i] = ALLOC ? 0u : a.hist[(uint64_t)i * gridDim.x + blockIdx.x]; }
   __syncthreads();
   const uint64_t begin = blockIdx.x * a.chunk, end = min(a.n, begin + a.chunk);
 
@@ -186,10 +192,18 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
       uint32_t wbase = 0;
       for (int w = 0; w < warp; w++) wbase += s_wtot[w];
       if (tid < P) {
-        const uint32_t off = wbase + inc - c, cur = s_cursor[tid];
+        const uint32_t off = wbase + inc - c;
+        uint32_t cur;
+        if (ALLOC) {
+          const uint32_t got = c ? atomicAdd(&a.cursor[tid], c) : 0u;
+          cur = (uint32_t)tid * a.cap + got;
+          s_cursor[tid] = got + c > a.cap ? 0u : c;  // rows of this run that fit (all or none: an overflowing region is redone)
+        } else {
+          cur = s_cursor[tid];
+          s_cursor[tid] = cur + c;
+        }
         s_off[tid] = off;
         s_gbase[tid] = cur - off;  // destination of staged element i of this partition = s_gbase + i (mod 2^32)
-        s_cursor[tid] = cur + c;
         s_cnt[tid] = 0;
         if (tid == P - 1) s_total = off + c;
       }
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
           const uint64_t row = tile + (uint64_t)(j * kPartThreads + tid) * 4 + e;
           const uint32_t pos = s_off[part[j][e]] + rank[j][e];
           s_key[pos] = k[j][e];
-          s_dst[pos] = s_gbase[part[j][e]] + pos;
+          s_dst[pos] = (ALLOC && s_cursor[part[j][e]] == 0) ? 0xFFFFFFFFu : s_gbase[part[j][e]] + pos;
           if (IDS) s_id[pos] = a.ids_in ? ld_stream_u32(a.ids_in + row) : (uint32_t)row;
 #pragma unroll
           for (int q = 0; q < NPAY; q++) s_pay[(size_t)q * kPartTile + pos] = ld_stream_u64(a.pay_in[q] + row);
@@ -214,6 +228,7 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
     const uint32_t total = s_total;
     for (uint32_t i = tid; i < total; i += kPartThreads) {
       const uint32_t dst = s_dst[i];
+      if (ALLOC && dst == 0xFFFFFFFFu) continue;
       a.out_keys[dst] = s_key[i];
       if (IDS) a.out_ids[dst] = s_id[i];
 #pragma unroll
@@ -234,12 +249,41 @@ static PartPlan plan_partition(olap_ctx* ctx, uint64_t n) {
   return {grid, chunk};
 }
 
-template <int NPAY, bool IDS>
+template <int NPAY, bool IDS, bool ALLOC = false>
 static olap_status launch_partition(olap_ctx* ctx, PartArgs& a, unsigned grid, cudaStream_t s) {
   const size_t smem = (size_t)kPartTile * (8 + 8 * NPAY + (IDS ? 4 : 0) + 4);
-  OLAP_CUDA(cudaFuncSetAttribute(partition_kernel<NPAY, IDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  partition_kernel<NPAY, IDS><<<grid, kPartThreads, smem, s>>>(a);
+  OLAP_CUDA((cudaFuncSetAttribute(partition_kernel<NPAY, IDS, ALLOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  partition_kernel<NPAY, IDS, ALLOC><<<grid, kPartThreads, smem, s>>>(a);
   count_launch(ctx);
+  return OLAP_OK;
+}
+
+// partition bounds as two device arrays: rows of partition p are [bounds[p], bounds[P + p])
+__global__ void part_bounds_kernel(const uint32_t* __restrict__ part_begin, const uint32_t* __restrict__ cursor, uint32_t cap, uint32_t P,
+                                   uint32_t* __restrict__ bounds) {
+  for (uint32_t p = threadIdx.x; p < P; p += blockDim.x) {
+    if (cursor) { bounds[p] = p * cap; bounds[P + p] = p * cap + min(cursor[p], cap); }
+    else { bounds[p] = part_begin[p]; bounds[P + p] = part_begin[p + 1]; }
+  }
+}
+
+// Capacity of one partition's region in ALLOC mode: 25 % + two tiles above the mean (hash partitions of a relation without
+// heavy hitters stay within a fraction of a percent of the mean), a multiple of the tile so regions stay vector-aligned.
+static uint64_t alloc_capacity(uint64_t n, uint32_t P) {
+  const uint64_t mean = (n + P - 1) / P;
+  return (mean + mean / 4 + 2 * kPartTile + kPartTile - 1) / kPartTile * kPartTile;
+}
+
+// one pass: (key, row id) of one relation into fixed-capacity regions; cursor[P] must be zeroed by the caller's stream order
+static olap_status run_partition_alloc(olap_ctx* ctx, PartArgs& a, cudaStream_t s, const char* part_mark) {
+  PartPlan pl = plan_partition(ctx, a.n);
+  a.chunk = pl.chunk;
+  a.vec = aligned32(a.keys);
+  OLAP_CUDA(cudaMemsetAsync(a.cursor, 0, (size_t)(1u << a.bits) * 4, s));
+  OLAP_TRY((launch_partition<0, true, true>(ctx, a, pl.grid, s)));
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  if (part_mark) phase_mark(ctx, s, part_mark);
   return OLAP_OK;
 }
 
@@ -435,11 +479,22 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Bucket* __rest
     if (total) {
       uint32_t base = 0;
       if (lane == 31) base = atomicAdd(&sh.n, total);
-      uint32_t pos = __shfl_sync(0xffffffffu, base, 31) + inc - nh;
+      base = __shfl_sync(0xffffffffu, base, 31);
+      uint32_t pos = base + inc - nh;
+      if (base + total <= (uint32_t)kProbeStage) {  // warp-uniform: the usual case, plain predicated stores
 #pragma unroll
-      for (int j = 0; j < kJoinRows; j++) {
-        if (h0[j]) stage_or_spill(sh.stage, pos++, e[j].r0, pid[j], out, max_matches, count);
-        if (h1[j]) stage_or_spill(sh.stage, pos++, e[j].r1, pid[j], out, max_matches, count);
+        for (int j = 0; j < kJoinRows; j++) {
+          if (h0[j]) sh.stage[pos] = make_uint2(e[j].r0, pid[j]);
+          pos += h0[j];
+          if (h1[j]) sh.stage[pos] = make_uint2(e[j].r1, pid[j]);
+          pos += h1[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kJoinRows; j++) {
+          if (h0[j]) stage_or_spill(sh.stage, pos++, e[j].r0, pid[j], out, max_matches, count);
+          if (h1[j]) stage_or_spill(sh.stage, pos++, e[j].r1, pid[j], out, max_matches, count);
+        }
       }
     }
     // continuations: a key with this home bucket was displaced by up to rem buckets (8 % of rows).  Warp-uniform loop; each
@@ -467,9 +522,21 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Bucket* __rest
   __syncthreads();
   if (out && n) {
     const unsigned long long base = sh.base;
-    for (uint32_t i = tid; i < n; i += kJoinThreads) {
-      const unsigned long long pos = base + i;
-      if (pos < max_matches) st_stream_u64(out + pos, (uint64_t)sh.stage[i].x | ((uint64_t)sh.stage[i].y << 32));
+    if (base + n <= max_matches) {
+      // 16-byte stores: pairs (lead + 2k, lead + 2k + 1) start on a 16-byte aligned output address
+      const uint32_t lead = (uint32_t)((reinterpret_cast<uintptr_t>(out + base) >> 3) & 1);
+      if (tid == 0 && lead) st_stream_u64(out + base, (uint64_t)sh.stage[0].x | ((uint64_t)sh.stage[0].y << 32));
+      uint32_t i = lead + 2 * tid;
+      for (; i + 1 < n; i += 2 * kJoinThreads) {
+        const uint2 a = sh.stage[i], b = sh.stage[i + 1];
+        st_stream_u64x2(out + base + i, make_ulonglong2((uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)b.x | ((uint64_t)b.y << 32)));
+      }
+      if (i < n) st_stream_u64(out + base + i, (uint64_t)sh.stage[i].x | ((uint64_t)sh.stage[i].y << 32));
+    } else {
+      for (uint32_t i = tid; i < n; i += kJoinThreads) {
+        const unsigned long long pos = base + i;
+        if (pos < max_matches) st_stream_u64(out + pos, (uint64_t)sh.stage[i].x | ((uint64_t)sh.stage[i].y << 32));
+      }
     }
   }
   __syncthreads();
@@ -509,10 +576,12 @@ __global__ void __launch_bounds__(kJoinThreads, 4) probe_kernel(const uint64_t* 
 // ~1.5 waves of CTAs each.
 struct PipeArgs {
   const uint64_t* bkeys; const uint32_t* bids; const uint64_t* pkeys; const uint32_t* pids;
-  const uint32_t* bbegin; const uint32_t* pbegin;  // device, [P + 1]
+  const uint32_t* bb; const uint32_t* pb;          // device, [2P]: rows of partition p are [x[p], x[P + p])
   uint32_t P; int bits; uint32_t R; uint32_t pid_base;
   Bucket* arena; uint64_t stride;                  // ring slot r = arena + r * stride buckets
   uint32_t* sync;                                  // [0] ticket, then cleared[P], built[P], probed[P]; zeroed before the launch
+  uint32_t grid_dbg;
+  unsigned long long* waited;                      // [6]: cycles waited by clear / build / probe items, then the number of waits
   olap_pair* out; uint64_t max_matches; unsigned long long* count;
   uint32_t step_start[kMaxParts + 3];              // first ticket of every step; [P + 2] = number of items
 };
@@ -538,8 +607,13 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void pipe_wait(const uint32_t* counter, uint32_t need) {
-  if (threadIdx.x == 0 && need) while (ld_acquire_u32(counter) < need) __nanosleep(128);
+__device__ __forceinline__ void pipe_wait(const uint32_t* counter, uint32_t need, unsigned long long* waited) {
+  if (threadIdx.x == 0 && need && ld_acquire_u32(counter) < need) {
+    const long long t0 = clock64();
+    while (ld_acquire_u32(counter) < need) __nanosleep(128);
+    atomicAdd(waited, (unsigned long long)(clock64() - t0));  // cycles spent waiting, per phase (OLAP_JOIN_DEBUG=8 prints them)
+    atomicAdd(waited + 3, 1ULL);
+  }
   __syncthreads();
 }
 __device__ __forceinline__ void pipe_signal(uint32_t* counter) {
@@ -569,32 +643,32 @@ __global__ void __launch_bounds__(kJoinThreads, 4) join_pipeline_kernel(const __
     int phase = 0;
     uint32_t p = s;
     if (s < P) {
-      const PartWork w = part_work(a.bbegin[s], a.bbegin[s + 1], a.pbegin[s], a.pbegin[s + 1]);
+      const PartWork w = part_work(a.bb[s], a.bb[P + s], a.pb[s], a.pb[P + s]);
       if (idx >= w.n_clear) { idx -= w.n_clear; phase = 1; }
     } else phase = 1;
     if (phase == 1) {
       p = s - 1;
       uint32_t nbd = 0;
-      if (s >= 1 && s <= P) nbd = part_work(a.bbegin[p], a.bbegin[p + 1], a.pbegin[p], a.pbegin[p + 1]).n_build;
+      if (s >= 1 && s <= P) nbd = part_work(a.bb[p], a.bb[P + p], a.pb[p], a.pb[P + p]).n_build;
       if (idx >= nbd) { idx -= nbd; phase = 2; p = s - 2; }
     }
-    const uint32_t b0 = a.bbegin[p], b1 = a.bbegin[p + 1], p0 = a.pbegin[p], p1 = a.pbegin[p + 1];
+    const uint32_t b0 = a.bb[p], b1 = a.bb[P + p], p0 = a.pb[p], p1 = a.pb[P + p];
     const PartWork w = part_work(b0, b1, p0, p1);
     Bucket* table = a.arena + (uint64_t)(p % a.R) * a.stride;
     if (phase == 0) {
       uint32_t need = 0;
-      if (p >= a.R) { const uint32_t q = p - a.R; need = part_work(a.bbegin[q], a.bbegin[q + 1], a.pbegin[q], a.pbegin[q + 1]).n_probe; }
-      pipe_wait(probed + (p >= a.R ? p - a.R : 0), need);
+      if (p >= a.R) { const uint32_t q = p - a.R; need = part_work(a.bb[q], a.bb[P + q], a.pb[q], a.pb[P + q]).n_probe; }
+      pipe_wait(probed + (p >= a.R ? p - a.R : 0), need, a.waited + 0);
       const uint32_t c0 = idx * kClearTile, c1 = min(w.nbk, c0 + kClearTile);
       const u64x4 z = {0, 0, 0, 0};
       for (uint32_t i = c0 + tid; i < c1; i += kJoinThreads) st_stream_u64x4(table + i, z);
       pipe_signal(cleared + p);
     } else if (phase == 1) {
-      pipe_wait(cleared + p, w.n_clear);
+      pipe_wait(cleared + p, w.n_clear, a.waited + 1);
       build_tile<true>(table, w.nbk, a.bits, a.bkeys, a.bids, b0, b1, (b0 & ~3u) + (uint64_t)idx * kJoinTile);
       pipe_signal(built + p);
     } else {
-      pipe_wait(built + p, w.n_build);
+      pipe_wait(built + p, w.n_build, a.waited + 2);
       probe_tile<true>(sh, table, w.nbk, a.bits, a.pid_base, a.pkeys, a.pids, p0, p1, (p0 & ~3u) + (uint64_t)idx * kJoinTile, a.out,
                        a.max_matches, a.count);
       pipe_signal(probed + p);
@@ -647,6 +721,51 @@ static void launch_probe(olap_ctx* ctx, const uint64_t* keys, const uint32_t* id
   count_launch(ctx);
 }
 
+// Radix-partition (key, row id) of one side of the join.  out_keys / out_ids must hold side_rows_cap(n, bits) rows.  First choice
+// is the one-pass ALLOC layout; if a region overflows (heavy hitters) the exact histogram layout is used instead.
+// d_bounds / h_bounds: [2P], rows of partition p are [x[p], x[P + p]).
+static uint64_t side_rows_cap(uint64_t n, int bits) {
+  const uint32_t P = 1u << bits;
+  const uint64_t cap = alloc_capacity(n, P);
+  return std::max<uint64_t>(n, (uint64_t)P * cap);
+}
+
+static olap_status partition_side(olap_ctx* ctx, const uint64_t* keys, uint64_t n, int bits, uint64_t* out_keys, uint32_t* out_ids,
+                                  uint32_t* d_bounds, std::vector<uint32_t>& h_bounds, Scratch& sc, cudaStream_t s, const char* hist_mark,
+                                  const char* part_mark) {
+  const uint32_t P = 1u << bits;
+  h_bounds.resize(2 * (size_t)P);
+  PartArgs a;
+  memset(&a, 0, sizeof(a));
+  a.bits = bits; a.keys = keys; a.n = n; a.out_keys = out_keys; a.out_ids = out_ids;
+  const uint64_t cap = alloc_capacity(n, P);
+  if (env_u64("OLAP_JOIN_ALLOC", 1) && (uint64_t)P * cap < 0xFFFFFFFFULL) {
+    uint32_t* cursor = nullptr;
+    OLAP_TRY(sc.get<uint32_t>(P, &cursor));
+    a.cursor = cursor; a.cap = (uint32_t)cap;
+    OLAP_TRY(run_partition_alloc(ctx, a, s, part_mark));
+    part_bounds_kernel<<<1, 256, 0, s>>>(nullptr, cursor, a.cap, P, d_bounds);
+    count_launch(ctx);
+    std::vector<uint32_t> used(P);
+    OLAP_CUDA(cudaMemcpyAsync(used.data(), cursor, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+    OLAP_CUDA(cudaMemcpyAsync(h_bounds.data(), d_bounds, 2 * (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+    OLAP_CUDA(cudaStreamSynchronize(s));
+    bool overflow = false;
+    for (uint32_t p = 0; p < P; p++) overflow |= used[p] > a.cap;
+    if (!overflow) return OLAP_OK;
+  }
+  uint32_t *hist = nullptr, *beg = nullptr;
+  OLAP_TRY(sc.get<uint32_t>((uint64_t)P * ctx->sm_count * kPartCtasPerSm, &hist));
+  OLAP_TRY(sc.get<uint32_t>(P + 1, &beg));
+  a.cursor = nullptr; a.cap = 0; a.hist = hist;
+  OLAP_TRY(run_partition(ctx, a, 0, true, beg, s, hist_mark, part_mark));
+  part_bounds_kernel<<<1, 256, 0, s>>>(beg, nullptr, 0, P, d_bounds);
+  count_launch(ctx);
+  OLAP_CUDA(cudaMemcpyAsync(h_bounds.data(), d_bounds, 2 * (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+  OLAP_CUDA(cudaStreamSynchronize(s));
+  return OLAP_OK;
+}
+
 // The build side of a join, prepared once and probed by one or many batches of the probe side (the reference executor hands
 // the right side over as a Vec<RecordBatch>; gpu-olap-core/src/executor.rs:66-69).
 struct BuildSide {
@@ -657,8 +776,8 @@ struct BuildSide {
   Bucket* table = nullptr; uint64_t nbk = 0;
   // radix: the partitioned build side
   uint64_t* pkb = nullptr; uint32_t* pib = nullptr; int bits = 0; uint32_t P = 0;
-  uint32_t* d_begin = nullptr;  // partition boundaries on the device, [P + 1]
-  std::vector<uint32_t> hb;     // ... and on the host
+  uint32_t* d_bounds = nullptr;  // partition bounds on the device, [2P]
+  std::vector<uint32_t> hb;      // ... and on the host
   uint64_t max_part = 0;
 };
 
@@ -666,7 +785,7 @@ static olap_status build_side_free(BuildSide& b, cudaStream_t s) {
   if (b.table) { pool_free(b.ctx, b.table, s); b.table = nullptr; }
   if (b.pkb) { pool_free(b.ctx, b.pkb, s); b.pkb = nullptr; }
   if (b.pib) { pool_free(b.ctx, b.pib, s); b.pib = nullptr; }
-  if (b.d_begin) { pool_free(b.ctx, b.d_begin, s); b.d_begin = nullptr; }
+  if (b.d_bounds) { pool_free(b.ctx, b.d_bounds, s); b.d_bounds = nullptr; }
   return OLAP_OK;
 }
 
@@ -689,20 +808,13 @@ static olap_status build_side_prepare(olap_ctx* ctx, const uint64_t* bk, uint64_
   while (bits < kMaxPartBits && ((nb + target - 1) / target) > (1ULL << bits)) bits++;
   b->bits = bits; b->P = 1u << bits;
   Scratch sc(ctx, s);
-  uint32_t* hist = nullptr;
-  OLAP_TRY(pool_alloc(ctx, nb * 8 + 32, s, (void**)&b->pkb));
-  OLAP_TRY(pool_alloc(ctx, nb * 4 + 32, s, (void**)&b->pib));
-  OLAP_TRY(pool_alloc(ctx, (b->P + 1) * 4, s, (void**)&b->d_begin));
-  OLAP_TRY(sc.get<uint32_t>((uint64_t)b->P * ctx->sm_count * kPartCtasPerSm, &hist));
-  PartArgs a;
-  memset(&a, 0, sizeof(a));
-  a.bits = bits; a.keys = bk; a.n = nb; a.hist = hist; a.out_keys = b->pkb; a.out_ids = b->pib;
-  OLAP_TRY(run_partition(ctx, a, 0, true, b->d_begin, s, "hist_build", "partition_build"));
-  b->hb.resize(b->P + 1);
-  OLAP_CUDA(cudaMemcpyAsync(b->hb.data(), b->d_begin, (b->P + 1) * 4, cudaMemcpyDeviceToHost, s));
-  OLAP_CUDA(cudaStreamSynchronize(s));
+  const uint64_t rows = side_rows_cap(nb, bits);
+  OLAP_TRY(pool_alloc(ctx, rows * 8 + 32, s, (void**)&b->pkb));
+  OLAP_TRY(pool_alloc(ctx, rows * 4 + 32, s, (void**)&b->pib));
+  OLAP_TRY(pool_alloc(ctx, 2 * (size_t)b->P * 4, s, (void**)&b->d_bounds));
+  OLAP_TRY(partition_side(ctx, bk, nb, bits, b->pkb, b->pib, b->d_bounds, b->hb, sc, s, "hist_build", "partition_build"));
   b->max_part = 0;
-  for (uint32_t p = 0; p < b->P; p++) b->max_part = std::max<uint64_t>(b->max_part, b->hb[p + 1] - b->hb[p]);
+  for (uint32_t p = 0; p < b->P; p++) b->max_part = std::max<uint64_t>(b->max_part, b->hb[b->P + p] - b->hb[p]);
   return OLAP_OK;
 }
 
@@ -720,20 +832,16 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   const int bits = b.bits;
   Scratch sc(ctx, s);
   uint64_t* pkp = nullptr;
-  uint32_t *pip = nullptr, *hist = nullptr, *beg = nullptr;
-  OLAP_TRY(sc.get<uint64_t>(np + 4, &pkp));
-  OLAP_TRY(sc.get<uint32_t>(np + 8, &pip));
-  OLAP_TRY(sc.get<uint32_t>((uint64_t)P * ctx->sm_count * kPartCtasPerSm, &hist));
-  OLAP_TRY(sc.get<uint32_t>(P + 1, &beg));
-  PartArgs a;
-  memset(&a, 0, sizeof(a));
-  a.bits = bits; a.keys = pk; a.n = np; a.hist = hist; a.out_keys = pkp; a.out_ids = pip;
-  OLAP_TRY(run_partition(ctx, a, 0, true, beg, s, "hist_probe", "partition_probe"));
-  std::vector<uint32_t> hp(P + 1);
-  OLAP_CUDA(cudaMemcpyAsync(hp.data(), beg, (P + 1) * 4, cudaMemcpyDeviceToHost, s));
-  OLAP_CUDA(cudaStreamSynchronize(s));
+  uint32_t *pip = nullptr, *d_pb = nullptr;
+  const uint64_t rows = side_rows_cap(np, bits);
+  OLAP_TRY(sc.get<uint64_t>(rows + 4, &pkp));
+  OLAP_TRY(sc.get<uint32_t>(rows + 8, &pip));
+  OLAP_TRY(sc.get<uint32_t>(2 * (uint64_t)P, &d_pb));
+  std::vector<uint32_t> hp;
+  OLAP_TRY(partition_side(ctx, pk, np, bits, pkp, pip, d_pb, hp, sc, s, "hist_probe", "partition_probe"));
   const uint32_t* hb = b.hb.data();
   const uint64_t nbk = std::max<uint64_t>(b.max_part, 64);  // buckets per table: exactly 32 B per build row of the largest partition
+  auto work = [&](uint32_t p) { return part_work(hb[p], hb[P + p], hp[p], hp[P + p]); };
 
   if (env_u64("OLAP_JOIN_PIPE", 1)) {
     // the join pipeline: one persistent kernel over all partitions (see join_pipeline_kernel)
@@ -743,18 +851,20 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     while (R > 1 && R * nbk * 32 > (96ULL << 20)) R--;  // keep the ring within the L2 (skewed partitions: fewer, larger tables)
     OLAP_TRY(ensure_arena(ctx, R * nbk * 32));
     uint32_t* sync = nullptr;
-    OLAP_TRY(sc.get<uint32_t>(1 + 3 * (uint64_t)P, &sync));
-    OLAP_CUDA(cudaMemsetAsync(sync, 0, (1 + 3 * (uint64_t)P) * 4, s));
-    pa.bkeys = b.pkb; pa.bids = b.pib; pa.pkeys = pkp; pa.pids = pip; pa.bbegin = b.d_begin; pa.pbegin = beg;
+    const uint64_t sync_words = 1 + 3 * (uint64_t)P + 1 + 12;  // counters, padding to 8 bytes, 6 x u64 wait statistics
+    OLAP_TRY(sc.get<uint32_t>(sync_words, &sync));
+    OLAP_CUDA(cudaMemsetAsync(sync, 0, sync_words * 4, s));
+    pa.waited = reinterpret_cast<unsigned long long*>(sync + ((1 + 3 * (uint64_t)P + 1) & ~1ULL));
+    pa.bkeys = b.pkb; pa.bids = b.pib; pa.pkeys = pkp; pa.pids = pip; pa.bb = b.d_bounds; pa.pb = d_pb;
     pa.P = P; pa.bits = bits; pa.R = (uint32_t)R; pa.pid_base = pid_base;
     pa.arena = (Bucket*)ctx->table_arena; pa.stride = nbk; pa.sync = sync;
     pa.out = out; pa.max_matches = max_matches; pa.count = d_count;
     uint64_t items = 0;
     for (uint32_t st = 0; st < P + 2; st++) {
       pa.step_start[st] = (uint32_t)items;
-      if (st < P) items += part_work(hb[st], hb[st + 1], hp[st], hp[st + 1]).n_clear;
-      if (st >= 1 && st <= P) items += part_work(hb[st - 1], hb[st], hp[st - 1], hp[st]).n_build;
-      if (st >= 2) items += part_work(hb[st - 2], hb[st - 1], hp[st - 2], hp[st - 1]).n_probe;
+      if (st < P) items += work(st).n_clear;
+      if (st >= 1 && st <= P) items += work(st - 1).n_build;
+      if (st >= 2) items += work(st - 2).n_probe;
     }
     pa.step_start[P + 2] = (uint32_t)items;
     if (items) {
@@ -762,15 +872,23 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
       OLAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, join_pipeline_kernel, kJoinThreads, 0));
       if (occ < 1) { set_error("join_pipeline_kernel does not fit on an SM"); return OLAP_ERR_CUDA; }
       const uint64_t grid = std::min<uint64_t>((uint64_t)occ * ctx->sm_count, items);
+      pa.grid_dbg = (uint32_t)grid;
       join_pipeline_kernel<<<(unsigned)grid, kJoinThreads, 0, s>>>(pa);
       count_launch(ctx, 2);
     }
     phase_mark(ctx, s, "build_probe");
     OLAP_CUDA(cudaGetLastError());
+    if (env_u64("OLAP_JOIN_DEBUG", 0) & 8) {
+      unsigned long long w[6];
+      OLAP_CUDA(cudaMemcpyAsync(w, pa.waited, sizeof(w), cudaMemcpyDeviceToHost, s));
+      OLAP_CUDA(cudaStreamSynchronize(s));
+      fprintf(stderr, "[join pipeline] items %llu grid %u ring %llu | waits clear %llu (%.1f Mcyc) build %llu (%.1f Mcyc) probe %llu (%.1f Mcyc)\n",
+              (unsigned long long)items, pa.grid_dbg, (unsigned long long)R, w[3], w[0] / 1e6, w[4], w[1] / 1e6, w[5], w[2] / 1e6);
+    }
     return OLAP_OK;
   }
 
-  // OLAP_JOIN_PIPE=0: three launches per partition on S side streams (kept for A/B timing; 13.8 ms vs the pipeline at C2)
+  // OLAP_JOIN_PIPE=0: three launches per partition on S side streams (kept for A/B timing; same time as the pipeline at C2)
   const uint64_t dbg = env_u64("OLAP_JOIN_DEBUG", 0);  // timing decomposition only: 1 skips probes, 2 skips builds, 4 marks every kernel
   int S = (int)std::min<uint64_t>(ctx->streams.size(), env_u64("OLAP_JOIN_STREAMS", 3));
   if (dbg & 4) S = 1;
@@ -780,7 +898,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   OLAP_CUDA(cudaEventRecord(ctx->fork_ev, s));
   for (int k = 0; k < S; k++) OLAP_CUDA(cudaStreamWaitEvent(ctx->streams[k], ctx->fork_ev, 0));
   for (uint32_t p = 0; p < P; p++) {
-    const uint64_t b0 = hb[p], b1 = hb[p + 1], p0 = hp[p], p1 = hp[p + 1];
+    const uint64_t b0 = hb[p], b1 = hb[P + p], p0 = hp[p], p1 = hp[P + p];
     if (b1 == b0 || p1 == p0) continue;  // inner join: an empty side yields nothing
     const int k = p % S;
     cudaStream_t st = (dbg & 4) ? s : ctx->streams[k];
