@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
   const int P = 1 << a.bits, sh = 64 - a.bits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < P; i += kPartThreads) { s_cnt[i] = 0; s_cursor[i] = ALLOC ? 0u : a.hist[(uint64_t)i * gridDim.x + blockIdx.x]; }
+  static_assert(kPartTile <= 65536, "rank is packed into 16 bits");
   __syncthreads();
   const uint64_t begin = blockIdx.x * a.chunk, end = min(a.n, begin + a.chunk);
 
@@ -165,46 +166,46 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
   for (int j = 0; j < 2; j++) load_keys4(a, begin + (uint64_t)(j * kPartThreads + tid) * 4, end, kn[j], okn[j]);
   for (uint64_t tile = begin; tile < end; tile += kPartTile) {
     // phase 1: pick the partition from the high hash bits, rank inside the tile with one smem atomic per row
-    uint64_t k[2][4]; bool ok[2][4]; uint32_t part[2][4], rank[2][4];
+    uint64_t k[2][4]; uint32_t pr[2][4];  // pr = partition << 16 | rank in the tile; ~0 = dead row
 #pragma unroll
     for (int j = 0; j < 2; j++)
 #pragma unroll
-      for (int e = 0; e < 4; e++) { k[j][e] = kn[j][e]; ok[j][e] = okn[j][e]; }
+      for (int e = 0; e < 4; e++) { k[j][e] = kn[j][e]; pr[j][e] = okn[j][e] ? 0u : 0xFFFFFFFFu; }
 #pragma unroll
     for (int j = 0; j < 2; j++) load_keys4(a, tile + kPartTile + (uint64_t)(j * kPartThreads + tid) * 4, end, kn[j], okn[j]);
 #pragma unroll
     for (int j = 0; j < 2; j++)
 #pragma unroll
       for (int e = 0; e < 4; e++)
-        if (ok[j][e]) { part[j][e] = (uint32_t)(part_hash(k[j][e], a.salt) >> sh); rank[j][e] = atomicAdd(&s_cnt[part[j][e]], 1u); }
+        if (pr[j][e] == 0) {
+          const uint32_t part = (uint32_t)(part_hash(k[j][e], a.salt) >> sh);
+          pr[j][e] = (part << 16) | atomicAdd(&s_cnt[part], 1u);
+        }
     __syncthreads();
     // phase 2: exclusive scan of the tile histogram; advance this CTA's global cursors
-    uint32_t c = 0, inc = 0;
+    uint32_t c = 0, inc = 0, off = 0, got = 0;
     if (tid < 256) {
       c = tid < P ? s_cnt[tid] : 0;
       inc = c;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
       if (lane == 31) s_wtot[warp] = inc;
+      // ALLOC: reserve this tile's run in partition tid's region; the round trip overlaps the scan and the whole of phase 3
+      if (ALLOC && c) got = atomicAdd(&a.cursor[tid], c);
     }
     __syncthreads();
     if (tid < 256) {
       uint32_t wbase = 0;
       for (int w = 0; w < warp; w++) wbase += s_wtot[w];
       if (tid < P) {
-        const uint32_t off = wbase + inc - c;
-        uint32_t cur;
-        if (ALLOC) {
-          const uint32_t got = c ? atomicAdd(&a.cursor[tid], c) : 0u;
-          cur = (uint32_t)tid * a.cap + got;
-          s_cursor[tid] = got + c > a.cap ? 0u : c;  // rows of this run that fit (all or none: an overflowing region is redone)
-        } else {
-          cur = s_cursor[tid];
+        off = wbase + inc - c;
+        s_off[tid] = off;
+        s_cnt[tid] = 0;
+        if (!ALLOC) {
+          const uint32_t cur = s_cursor[tid];
+          s_gbase[tid] = cur - off;  // destination of staged element i of this partition = s_gbase + i (mod 2^32)
           s_cursor[tid] = cur + c;
         }
-        s_off[tid] = off;
-        s_gbase[tid] = cur - off;  // destination of staged element i of this partition = s_gbase + i (mod 2^32)
-        s_cnt[tid] = 0;
         if (tid == P - 1) s_total = off + c;
       }
     }
@@ -214,21 +215,28 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
     for (int j = 0; j < 2; j++)
 #pragma unroll
       for (int e = 0; e < 4; e++)
-        if (ok[j][e]) {
+        if (pr[j][e] != 0xFFFFFFFFu) {
           const uint64_t row = tile + (uint64_t)(j * kPartThreads + tid) * 4 + e;
-          const uint32_t pos = s_off[part[j][e]] + rank[j][e];
+          const uint32_t part = pr[j][e] >> 16, pos = s_off[part] + (pr[j][e] & 0xFFFFu);
           s_key[pos] = k[j][e];
-          s_dst[pos] = (ALLOC && s_cursor[part[j][e]] == 0) ? 0xFFFFFFFFu : s_gbase[part[j][e]] + pos;
+          s_dst[pos] = ALLOC ? part : s_gbase[part] + pos;
           if (IDS) s_id[pos] = a.ids_in ? ld_stream_u32(a.ids_in + row) : (uint32_t)row;
 #pragma unroll
           for (int q = 0; q < NPAY; q++) s_pay[(size_t)q * kPartTile + pos] = ld_stream_u64(a.pay_in[q] + row);
         }
+    if (ALLOC && tid < P) {
+      s_gbase[tid] = (uint32_t)tid * a.cap + got - off;
+      s_cursor[tid] = got + c <= a.cap;  // the run fits (all or none: an overflowing region is redone by the caller)
+    }
     __syncthreads();
-    // phase 4: each partition's run leaves with coalesced stores (write-combined per CTA, no global atomics)
+    // phase 4: each partition's run leaves with coalesced stores (write-combined per CTA)
     const uint32_t total = s_total;
     for (uint32_t i = tid; i < total; i += kPartThreads) {
-      const uint32_t dst = s_dst[i];
-      if (ALLOC && dst == 0xFFFFFFFFu) continue;
+      uint32_t dst = s_dst[i];
+      if (ALLOC) {
+        if (!s_cursor[dst]) continue;
+        dst = s_gbase[dst] + i;
+      }
       a.out_keys[dst] = s_key[i];
       if (IDS) a.out_ids[dst] = s_id[i];
 #pragma unroll
