@@ -9,8 +9,8 @@ Metric (BASELINE.json): join rows/sec, rows = |build| + |probe|, on the single-G
 * value     device-resident inputs, CUDA events around K joins on the launching stream, max over ranks
 * e2e       the same join through the C-ABI with HOST (pinned) buffers: H2D of both key columns, join, D2H of the
             count and of the row-id pairs, all inside the timed region
-* roofline  dominant kernel (the probe-side radix partition): algorithmic bytes / its CUDA-event duration in the
-            timed region, against MEASURED_PEAKS.json's hbm_gbs
+* roofline  dominant kernel (join_pipeline_kernel: one persistent launch per step): algorithmic bytes / its CUDA-event
+            duration in the timed region, against MEASURED_PEAKS.json's hbm_gbs; the partition kernel next to it
 * cpu_baseline / --impl reference   the oracle's multi-threaded port of the reference CPU path on this box's cores
 N > 1: weak scaling, one process per GPU (torchrun); the join is key-sharded with an NCCL all-to-all shuffle
 (gpu_olap_engine_b200/sharded.py); value = rows of all ranks / max-over-ranks time.
@@ -245,11 +245,11 @@ def run_ours(args):
     sl = out[:: max(1, npb // 100000)]
     assert c == npb and (hbv[sl[:, 0]] == hpv[sl[:, 1]]).all(), "e2e result check failed"
 
-    # ---- roofline.  Dominant by share of the step (profiles/r01_ncu_launches_final_summary.csv: 54 % probe_kernel + 19 %
-    # build_kernel of the serialised kernel time): the build+probe phase, 256 partitions on 3 streams.  Algorithmic bytes =
-    # partitioned (key 8 B + row id 4 B) of both sides read once + 8 B per pair written.  Its duration is the CUDA-event
-    # time of that phase inside the timed steps.  The largest single launch (probe-side partition_kernel: reads 8 B key,
-    # writes 8 B key + 4 B row id per row) is reported next to it.
+    # ---- roofline.  Dominant kernel by share of the step (profiles/r01_ncu_launches_*_summary.csv): join_pipeline_kernel,
+    # ONE persistent launch per step that clears, builds and probes the L2-resident tables of all partitions.  Algorithmic
+    # bytes per launch = partitioned (key 8 B + row id 4 B) of both sides read once + 8 B per pair written.  Its duration is
+    # the CUDA-event time between the marks around that launch inside the timed steps.  The second kernel (probe-side
+    # partition_kernel: reads 8 B key, writes 8 B key + 4 B row id per row) is reported next to it.
     traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -284,11 +284,11 @@ def run_ours(args):
                 "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "how": "olap_join_build_create + 8 x olap_join_probe on pinned host buffers; H2D / join / D2H pipelined on 3 streams; wall clock"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "probe_kernel + build_kernel + table clear, 256 partitions on 3 streams (54 % + 19 % of the step's kernel time)",
+        "roofline": {"bound": "hbm", "kernel": "join_pipeline_kernel (one persistent launch per step: clear + build + probe of all partitions' L2-resident tables)",
                      "achieved": bp_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": (bp_gbs / peak) if bp_gbs else None,
-                     "traffic": traffic.get("build_probe_dram_bytes_per_step"), "algorithmic_bytes_per_step": bp_bytes, "ms_per_step": bp_ms,
-                     "note": "L2-latency-bound (per-partition tables live in L2), not HBM-bound: see DESIGN.md section 4; traffic is ncu's cold-cache sum"},
-        "roofline_partition": {"bound": "hbm", "kernel": "partition_kernel<0,true> (probe side; largest single launch, 23 % of the step)",
+                     "traffic": traffic.get("join_pipeline_dram_bytes_per_launch"), "algorithmic_bytes_per_launch": bp_bytes, "ms_per_launch": bp_ms,
+                     "note": "bound by L2 sector traffic (one 32 B bucket gather per probe row, atomic + 2 stores per build row), not by HBM: DESIGN.md section 4"},
+        "roofline_partition": {"bound": "hbm", "kernel": "partition_kernel<0,true,true> (probe side; second largest launch)",
                                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                                "traffic": traffic.get("partition_probe_dram_bytes_per_launch"), "algorithmic_bytes_per_launch": part_bytes,
                                "ms_per_launch": part_ms},

@@ -188,6 +188,16 @@ def test_join_large_radix_fk(ctx):
     assert exp_c == cnt and (O.sort_pairs(got) == O.sort_pairs(exp_pairs)).all()
 
 
+def test_join_skewed_sides_take_the_exact_layout(ctx):
+    # a heavy hitter overflows its fixed-capacity partition region (one-pass layout) on either side: the join must fall back
+    # to the exact histogram layout and still return the oracle's match set
+    rng = np.random.default_rng(5)
+    b = rng.integers(0, 1 << 40, 200000).astype(np.int64); b[: 160000] = 424242           # 80 % of the build side is one key
+    p = rng.integers(0, 1 << 40, 300000).astype(np.int64); p[:3] = 424242; p[1000:271000] = b[199999]  # 90 % of the probe side too
+    rng.shuffle(b); rng.shuffle(p)
+    check_join(ctx, b, p, 0)
+
+
 @pytest.mark.parametrize("bits", [1, 4, 8])
 def test_radix_partition_unit(ctx, bits):
     import gpu_olap_engine_b200 as g
