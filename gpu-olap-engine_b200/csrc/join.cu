@@ -855,8 +855,13 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     // the join pipeline: one persistent kernel over all partitions (see join_pipeline_kernel)
     PipeArgs pa;
     memset(&pa, 0, sizeof(pa));
-    uint64_t R = std::min<uint64_t>(env_u64("OLAP_JOIN_RING", kPipeRing), P);
-    while (R > 1 && R * nbk * 32 > (96ULL << 20)) R--;  // keep the ring within the L2 (skewed partitions: fewer, larger tables)
+    // Ring of table slots.  clear(p) waits for probe(p - R), and with the step order {clear(s), build(s-1), probe(s-2)} that
+    // probe is EARLIER in ticket order only if R >= 3 (R == P: no slot is ever reused).  Fewer slots would let a CTA spin
+    // on items it -- or CTAs queued behind it -- still has to run: a deadlock, not a slowdown.  Large (skewed) partitions
+    // therefore get at least 3 slots even when those no longer fit the L2.
+    uint64_t R = std::max<uint64_t>(env_u64("OLAP_JOIN_RING", kPipeRing), 3);
+    while (R > 3 && R * nbk * 32 > (96ULL << 20)) R--;
+    R = std::min<uint64_t>(R, P);
     OLAP_TRY(ensure_arena(ctx, R * nbk * 32));
     uint32_t* sync = nullptr;
     const uint64_t sync_words = 1 + 3 * (uint64_t)P + 1 + 12;  // counters, padding to 8 bytes, 6 x u64 wait statistics

@@ -198,6 +198,28 @@ def test_join_skewed_sides_take_the_exact_layout(ctx):
     check_join(ctx, b, p, 0)
 
 
+@pytest.mark.timeout(180)
+def test_join_large_skewed_partition_keeps_three_ring_slots(ctx):
+    # 4 partitions, one of them > 1 Mi build rows (a 40 MB table): the pipeline's table ring must not shrink below 3 slots
+    # (with 2 the clear of partition p would wait for probe tiles queued behind it -- a deadlock); unique heavy-partition keys
+    # are produced by giving half of the build side keys that all hash to the same radix partition
+    import gpu_olap_engine_b200 as g
+    lib = g.load()
+    rng = np.random.default_rng(9)
+    cand = rng.integers(0, 1 << 50, 6_000_000).astype(np.int64)
+    part = np.array([lib.olap_partition_of(int(k), 2) for k in cand[:200]])   # spot check of the vectorised formula below
+    u = cand.astype(np.uint64); h = ((u ^ (u >> np.uint64(29))) * np.uint64(0x9E3779B97F4A7C15)) >> np.uint64(62)
+    assert (h[:200] == part).all()
+    heavy = cand[h == 0][:1_200_000]; rest = cand[h != 0][:800_000]
+    b = np.concatenate([heavy, rest]); rng.shuffle(b)
+    p = np.concatenate([b[:500_000], rng.integers(0, 1 << 50, 300_000).astype(np.int64)])
+    db, dp = dev(ctx, b), dev(ctx, p)
+    exp_c, exp_pairs = O.hash_join_i64(b, p, threads=8)
+    cnt, pairs = ctx.hash_join_i64(db, len(b), dp, len(p), max_matches=exp_c, strategy=0)
+    assert cnt == exp_c
+    assert (O.sort_pairs(pairs.to_numpy(2 * cnt).reshape(-1, 2)) == O.sort_pairs(exp_pairs)).all()
+
+
 @pytest.mark.parametrize("bits", [1, 4, 8])
 def test_radix_partition_unit(ctx, bits):
     import gpu_olap_engine_b200 as g
