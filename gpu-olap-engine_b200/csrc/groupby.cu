@@ -54,6 +54,8 @@ struct GbParams {
   // shared-memory tables
   uint32_t s_slots;   // power of two, per copy
   uint32_t s_copies;  // power of two
+  int s_hskip;        // hash bits already used to choose the radix partition (0 in the shared regime)
+  int s_hshift;       // 64 - log2(s_slots)
   // partitioned input (keys / vcol point at the partitioned copies)
   const uint32_t* part_begin;
   uint32_t n_parts;
@@ -190,6 +192,85 @@ __device__ __forceinline__ void global_update_row(const GbParams& p, uint64_t ke
       const uint64_t x = cell_encode(p.cell_op[c], pick<NV>(v, p.cell_vcol[c]), valid);
       if (valid) cell_atomic_global(p.cell_op[c], p.g_cells + (uint64_t)c * (p.g_cap + 1) + s, x);
     }
+}
+
+// Four rows per thread into the global table: same structure as smem_update_rows (first probe of all rows up front, one
+// shared insert / collision loop, operator switch outside the row loop).  Every lane calls it.
+template <int NV>
+__device__ __forceinline__ void global_update_rows(const GbParams& p, const uint64_t (&key)[4], const uint64_t (&v)[4][NV], const bool (&pass)[4]) {
+  const uint64_t mask = p.g_cap - 1, kNone = ~0ULL;
+  uint64_t s[4], slot[4];
+  uint32_t pend = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) { s[j] = mix64(key[j]) & mask; slot[j] = kNone; }
+  uint64_t k0[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) k0[j] = pass[j] ? ld_cg_u64(p.g_keys + s[j]) : 0;  // four L2 reads in flight
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (pass[j]) {
+      if (key[j] == kEmptyKey) slot[j] = p.g_cap;
+      else if (k0[j] == key[j]) slot[j] = s[j];
+      else pend |= 1u << j;
+    }
+  uint64_t probes = 0;
+  while (__any_sync(0xffffffffu, pend != 0)) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (pend & (1u << j)) {
+        uint64_t k = ld_cg_u64(p.g_keys + s[j]);
+        if (k == kEmptyKey) k = atomicCAS((unsigned long long*)(p.g_keys + s[j]), (unsigned long long)kEmptyKey, (unsigned long long)key[j]);
+        if (k == key[j] || k == kEmptyKey) { slot[j] = s[j]; pend &= ~(1u << j); }
+        else s[j] = (s[j] + 1) & mask;
+      }
+    if (++probes > mask) { if (pend) atomicExch(p.g_overflow, 1u); break; }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) if (slot[j] != kNone) atomicAdd(p.g_count + slot[j], 1ULL);
+#pragma unroll 1
+  for (int c = 0; c < p.n_cells; c++) {
+    const int op = p.cell_op[c], q = p.cell_vcol[c];
+    uint64_t* cells = p.g_cells + (uint64_t)c * (p.g_cap + 1);
+    uint64_t x[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) x[j] = pick<NV>(v[j], q);
+    switch (op) {
+      case ADD_I64:
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (slot[j] != kNone) atomicAdd((unsigned long long*)(cells + slot[j]), (unsigned long long)x[j]);
+        break;
+      case ADD_F64:
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (slot[j] != kNone) atomicAdd((double*)(cells + slot[j]), __longlong_as_double((long long)x[j]));
+        break;
+      case MIN_I64: case MAX_I64: {
+        long long cur[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) cur[j] = slot[j] != kNone ? (long long)ld_cg_u64(cells + slot[j]) : 0;  // read before the atomic
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (slot[j] != kNone) {
+            if (op == MIN_I64) { if ((long long)x[j] < cur[j]) atomicMin((long long*)(cells + slot[j]), (long long)x[j]); }
+            else if ((long long)x[j] > cur[j]) atomicMax((long long*)(cells + slot[j]), (long long)x[j]);
+          }
+        break;
+      }
+      default: {  // MIN_F64 / MAX_F64 in the ordered encoding; NaN never wins
+        long long cur[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) cur[j] = slot[j] != kNone ? (long long)ld_cg_u64(cells + slot[j]) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const double d = __longlong_as_double((long long)x[j]);
+          const long long o = f64_ord(x[j]);
+          if (slot[j] != kNone && d == d) {
+            if (op == MIN_F64) { if (o < cur[j]) atomicMin((long long*)(cells + slot[j]), o); }
+            else if (o > cur[j]) atomicMax((long long*)(cells + slot[j]), o);
+          }
+        }
+      }
+    }
+  }
 }
 
 // finalise one group into the output (COUNT, AVG = sum / count, f64 MIN/MAX decoding); slot layout aggregate_kernel.rs:98
@@ -352,8 +433,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(GbParams p, uint6
     uint64_t key[kGbRows], v[kGbRows][NV];
     bool pass[kGbRows];
     load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, begin, end, key, v, pass);
-#pragma unroll
-    for (int j = 0; j < kGbRows; j++) global_update_row<NV>(p, key[j], v[j], pass[j]);
+    global_update_rows<NV>(p, key, v, pass);
   }
 }
 
@@ -378,45 +458,105 @@ __device__ __forceinline__ void smem_table_clear(const GbParams& p, const SmemTa
   }
 }
 
-// aggregate one row per lane into the lane's copy (warp-uniform: every lane calls it, active = false without a row);
-// rows whose key finds no room fall through to the global table
+// Home slot of a key in a shared-memory table: one multiply (Fibonacci hashing of the folded key), the bits right below
+// the ones that chose the radix partition (s_hskip = partition bits, 0 in the shared regime).
+__device__ __forceinline__ uint32_t smem_home(const GbParams& p, uint64_t key) {
+  const uint64_t h = (key ^ (key >> 29)) * 0x9E3779B97F4A7C15ULL;
+  return (uint32_t)((h << p.s_hskip) >> p.s_hshift);  // the TOP remaining bits: a lower window of a multiplicative hash clusters
+}
+
+// Aggregate this thread's kGbRows rows into the thread's copy of the table.  Every lane calls it (pass = false without a row).
+// The first version handled one row at a time -- a warp-uniform probe loop per row and a runtime switch over the cell list
+// per row and cell: 322 warp instructions per row (ncu), issue-bound at 13-15 % of HBM.  Here the home slots of all four
+// rows are probed up front (a hit, the steady state, never enters the loop), the insert / collision loop is shared by the
+// four rows, and the cell list is walked once per four rows with the operator switch outside the row loop.
+// Rows whose key finds no room fall through to the global table.
 template <int NV>
-__device__ __forceinline__ void smem_update_row(const GbParams& p, const SmemTable& t, uint32_t copy_base, uint64_t key, const uint64_t (&v)[NV],
-                                                bool active, uint32_t* spill_flag) {
+__device__ __forceinline__ void smem_update_rows(const GbParams& p, const SmemTable& t, uint32_t copy_base, const uint64_t (&key)[kGbRows],
+                                                 const uint64_t (&v)[kGbRows][NV], const bool (&pass)[kGbRows], uint32_t* spill_flag) {
+  constexpr uint32_t kNone = 0xFFFFFFFFu;
   const uint32_t smask = p.s_slots - 1;
-  uint32_t s = (uint32_t)(mix64(key) >> 40) & smask, slot = 0xFFFFFFFFu, probes = 0;
-  bool pending = active;
-  if (pending && key == kEmptyKey) { slot = copy_base + p.s_slots; pending = false; }
-  while (__any_sync(0xffffffffu, pending)) {
-    if (pending) {
-      const uint64_t k = *(volatile uint64_t*)(t.keys + copy_base + s);
-      if (k == key) { slot = copy_base + s; pending = false; }
-      else {
-        if (k == kEmptyKey) {
-          const uint64_t old = atomicCAS((unsigned long long*)(t.keys + copy_base + s), (unsigned long long)kEmptyKey, (unsigned long long)key);
-          if (old == kEmptyKey || old == key) { slot = copy_base + s; pending = false; }
-        }
-        if (pending) {
-          s = (s + 1) & smask;
-          if (++probes >= p.s_slots) pending = false;  // copy is full: spill
-        }
-      }
-    }
-  }
-  const bool spill = active && slot == 0xFFFFFFFFu;
-  if (__any_sync(0xffffffffu, spill)) {
-    if (spill && spill_flag) *spill_flag = 1;
-    global_update_row<NV>(p, key, v, spill);
-  }
-  if (!active || spill) return;
-  atomicAdd(t.count + slot, 1u);
+  uint32_t s[kGbRows], slot[kGbRows], pend = 0;
 #pragma unroll
-  for (int c = 0; c < kMaxCells; c++)
-    if (c < p.n_cells) {
-      bool valid;
-      const uint64_t x = cell_encode(p.cell_op[c], pick<NV>(v, p.cell_vcol[c]), valid);
-      if (valid) cell_atomic_shared(p.cell_op[c], t.cells + (uint64_t)c * t.total + slot, x);
+  for (int j = 0; j < kGbRows; j++) {
+    s[j] = smem_home(p, key[j]);
+    slot[j] = kNone;
+    if (pass[j]) {
+      if (key[j] == kEmptyKey) slot[j] = copy_base + p.s_slots;
+      else if (*(volatile uint64_t*)(t.keys + copy_base + s[j]) == key[j]) slot[j] = copy_base + s[j];
+      else pend |= 1u << j;
     }
+  }
+  uint32_t probes = 0;
+  while (__any_sync(0xffffffffu, pend != 0)) {  // first sight of a key, or a collision
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++)
+      if (pend & (1u << j)) {
+        uint64_t* kp = t.keys + copy_base + s[j];
+        uint64_t k = *(volatile uint64_t*)kp;
+        if (k == kEmptyKey) k = atomicCAS((unsigned long long*)kp, (unsigned long long)kEmptyKey, (unsigned long long)key[j]);
+        if (k == key[j] || k == kEmptyKey) { slot[j] = copy_base + s[j]; pend &= ~(1u << j); }
+        else s[j] = (s[j] + 1) & smask;
+      }
+    if (++probes > p.s_slots) break;  // the copy is full (same trip count in every lane): what is still pending spills
+  }
+  if (__any_sync(0xffffffffu, pend != 0)) {
+    if (pend && spill_flag) *spill_flag = 1;
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++) global_update_row<NV>(p, key[j], v[j], (pend >> j) & 1u);
+  }
+#pragma unroll
+  for (int j = 0; j < kGbRows; j++) if (slot[j] != kNone) atomicAdd(t.count + slot[j], 1u);
+#pragma unroll 1
+  for (int c = 0; c < p.n_cells; c++) {
+    const int op = p.cell_op[c], q = p.cell_vcol[c];
+    uint64_t* cells = t.cells + (uint64_t)c * t.total;
+    uint64_t x[kGbRows];
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++) x[j] = pick<NV>(v[j], q);
+    switch (op) {
+      case ADD_I64:
+#pragma unroll
+        for (int j = 0; j < kGbRows; j++)
+          if (slot[j] != kNone) {
+            uint32_t* w = reinterpret_cast<uint32_t*>(cells + slot[j]);
+            const uint32_t lo = (uint32_t)x[j], hi = (uint32_t)(x[j] >> 32);
+            const uint32_t old = atomicAdd(w, lo);
+            const uint32_t carry = (uint32_t)(old + lo) < lo;
+            if (hi + carry) atomicAdd(w + 1, hi + carry);
+          }
+        break;
+      case ADD_F64:
+#pragma unroll
+        for (int j = 0; j < kGbRows; j++) if (slot[j] != kNone) atomicAdd((double*)(cells + slot[j]), __longlong_as_double((long long)x[j]));
+        break;
+      case MIN_I64:
+#pragma unroll
+        for (int j = 0; j < kGbRows; j++)
+          if (slot[j] != kNone && (long long)x[j] < *(volatile long long*)(cells + slot[j])) atomicMin((long long*)(cells + slot[j]), (long long)x[j]);
+        break;
+      case MAX_I64:
+#pragma unroll
+        for (int j = 0; j < kGbRows; j++)
+          if (slot[j] != kNone && (long long)x[j] > *(volatile long long*)(cells + slot[j])) atomicMax((long long*)(cells + slot[j]), (long long)x[j]);
+        break;
+      case MIN_F64:
+#pragma unroll
+        for (int j = 0; j < kGbRows; j++) {
+          const double d = __longlong_as_double((long long)x[j]);
+          const long long o = f64_ord(x[j]);
+          if (slot[j] != kNone && d == d && o < *(volatile long long*)(cells + slot[j])) atomicMin((long long*)(cells + slot[j]), o);
+        }
+        break;
+      default:
+#pragma unroll
+        for (int j = 0; j < kGbRows; j++) {
+          const double d = __longlong_as_double((long long)x[j]);
+          const long long o = f64_ord(x[j]);
+          if (slot[j] != kNone && d == d && o > *(volatile long long*)(cells + slot[j])) atomicMax((long long*)(cells + slot[j]), o);
+        }
+    }
+  }
 }
 
 // folds one pre-aggregated shared-memory slot into the global table (warp-uniform)
@@ -430,7 +570,7 @@ __device__ __forceinline__ void global_merge_slot(const GbParams& p, const SmemT
 // folds one pre-aggregated slot (count + cell values of copy c > 0) into copy 0; warp-uniform like smem_update_row
 __device__ __forceinline__ void smem_merge_slot(const GbParams& p, const SmemTable& t, uint64_t key, uint32_t cnt, uint32_t src, bool active) {
   const uint32_t smask = p.s_slots - 1;
-  uint32_t s = (uint32_t)(mix64(key) >> 40) & smask, slot = 0xFFFFFFFFu, probes = 0;
+  uint32_t s = smem_home(p, key), slot = 0xFFFFFFFFu, probes = 0;
   bool pending = active;
   if (pending && key == kEmptyKey) { slot = p.s_slots; pending = false; }
   while (__any_sync(0xffffffffu, pending)) {
@@ -477,11 +617,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
       for (int q = 0; q < NV; q++) v[j][q] = nv[j][q];
     }
     if (base + stride < p.n) load_rows<NV, true>(p, base + stride + (uint64_t)threadIdx.x * kGbRows, 0, p.n, nkey, nv, npass);
-#pragma unroll
-    for (int j = 0; j < kGbRows; j++) {
-      smem_update_row<NV>(p, t, copy_base, key[j], v[j], pass[j], nullptr);
-      __syncwarp();
-    }
+    smem_update_rows<NV>(p, t, copy_base, key, v, pass, nullptr);
   }
   __syncthreads();
   // merge every copy into the global table (warp-uniform trip count: global_slot is a convergent call)
@@ -522,11 +658,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_part_smem_kernel(GbParams p) {
         for (int q = 0; q < NV; q++) v[j][q] = nv[j][q];
       }
       if (base + tile < end) load_rows<NV, true>(p, base + tile + (uint64_t)threadIdx.x * kGbRows, begin, end, nkey, nv, npass);
-#pragma unroll
-      for (int j = 0; j < kGbRows; j++) {
-        smem_update_row<NV>(p, t, copy_base, key[j], v[j], pass[j], &s_spill);
-        __syncwarp();
-      }
+      smem_update_rows<NV>(p, t, copy_base, key, v, pass, &s_spill);
     }
     __syncthreads();
     if (s_spill) {  // some row went to the global table while its key may sit in another copy: this partition goes there entirely
@@ -641,6 +773,7 @@ static olap_status build_cells(const olap_agg_spec* specs, int n_aggs, GbParams*
 }
 
 static uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+static int ilog2_u64(uint64_t x) { int l = 0; while ((1ULL << l) < x) l++; return l; }
 static unsigned capped_grid(uint64_t want, uint64_t cap) { return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want)); }
 
 #define GB_DISPATCH_NV(nv, ...)                                 \
@@ -685,7 +818,7 @@ static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups
   if (bytes <= 200 * 1024) {
     uint64_t copies = 1;  // replicate small tables so that 512 threads do not hammer a few dozen slots (2 CTAs per SM: 100 KB each)
     while (copies < 16 && ((need + 1) * slot_bytes(p) * copies * 2 + 16) <= 100 * 1024) copies <<= 1;
-    q.s_slots = (uint32_t)need; q.s_copies = (uint32_t)copies;
+    q.s_slots = (uint32_t)need; q.s_copies = (uint32_t)copies; q.s_hskip = bits; q.s_hshift = 64 - ilog2_u64(need);
     const uint64_t bytes = (need + 1) * slot_bytes(p) * copies + 16;
     const unsigned per_sm = bytes <= 100 * 1024 ? 2 : 1;
     GB_DISPATCH_NV(p.n_vcols, {
@@ -786,7 +919,7 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
       } else if (shared) {
         uint64_t copies = 1;
         while (copies < 64 && (need + 1) * sbytes * copies * 2 + 16 <= budget) copies <<= 1;
-        p.s_slots = (uint32_t)need; p.s_copies = (uint32_t)copies;
+        p.s_slots = (uint32_t)need; p.s_copies = (uint32_t)copies; p.s_hskip = 0; p.s_hshift = 64 - ilog2_u64(need);
         const size_t smem = (size_t)((need + 1) * copies * sbytes + 16);
         GB_DISPATCH_NV(p.n_vcols, {
           OLAP_CUDA(cudaFuncSetAttribute(gb_shared_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
