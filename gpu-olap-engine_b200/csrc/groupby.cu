@@ -58,6 +58,7 @@ struct GbParams {
   int s_hshift;       // 64 - log2(s_slots)
   // partitioned input (keys / vcol point at the partitioned copies)
   const uint32_t* part_begin;
+  const uint32_t* part_end;
   uint32_t n_parts;
   // direct output (partitioned regime)
   OutSpec out;
@@ -642,7 +643,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_part_smem_kernel(GbParams p) {
     smem_table_clear(p, t);
     if (threadIdx.x == 0) { s_groups = 0; s_spill = 0; }
     __syncthreads();
-    const uint64_t begin = p.part_begin[part], end = p.part_begin[part + 1];
+    const uint64_t begin = p.part_begin[part], end = p.part_end[part];
     const uint32_t copy_base = (threadIdx.x & (p.s_copies - 1)) * t.slots1;
     uint64_t nkey[kGbRows], nv[kGbRows][NV];
     bool npass[kGbRows];
@@ -787,9 +788,10 @@ static unsigned capped_grid(uint64_t want, uint64_t cap) { return (unsigned)(wan
   }
 
 // join.cu: radix-partition (key, value columns) with the fused filter; returns the partition boundaries on the device
+uint64_t group_by_partition_capacity(uint64_t n, int bits);
 olap_status group_by_partition_rows(olap_ctx* ctx, const uint64_t* keys, uint64_t n, const TermPack& terms, int n_vcols,
                                     const uint64_t* const* vcols, int bits, uint64_t* out_keys, uint64_t* const* out_vcols,
-                                    uint32_t* part_begin, cudaStream_t s);
+                                    uint32_t* bounds, uint32_t* h_bounds, cudaStream_t s);
 
 // shared-memory budget per CTA for group tables
 static uint64_t slot_bytes(const GbParams& p) { return 8 + 4 + 8ULL * p.n_cells; }
@@ -799,18 +801,20 @@ static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups
   const uint32_t P = 1u << bits;
   uint64_t* pk = nullptr;
   uint64_t* pv[kMaxVcols] = {};
-  uint32_t* begin = nullptr;
-  OLAP_TRY(sc.get<uint64_t>(p.n, &pk));
-  for (int q = 0; q < p.n_vcols; q++) OLAP_TRY(sc.get<uint64_t>(p.n, &pv[q]));
-  OLAP_TRY(sc.get<uint32_t>(P + 1, &begin));
-  OLAP_TRY(group_by_partition_rows(ctx, p.keys, p.n, p.terms, p.n_vcols, p.vcol, bits, pk, pv, begin, s));
+  uint32_t* bounds = nullptr;  // rows of partition q are [bounds[q], bounds[P + q])
+  std::vector<uint32_t> h(2 * (size_t)P);
+  const uint64_t rows_cap = group_by_partition_capacity(p.n, bits);
+  OLAP_TRY(sc.get<uint64_t>(rows_cap + 4, &pk));
+  for (int q = 0; q < p.n_vcols; q++) OLAP_TRY(sc.get<uint64_t>(rows_cap + 4, &pv[q]));
+  OLAP_TRY(sc.get<uint32_t>(2 * (uint64_t)P, &bounds));
+  OLAP_TRY(group_by_partition_rows(ctx, p.keys, p.n, p.terms, p.n_vcols, p.vcol, bits, pk, pv, bounds, h.data(), s));
   phase_mark(ctx, s, "partition");
   GbParams q = p;  // aggregate the partitioned copies; the filter has been applied by the partition pass
   q.keys = pk;
   for (int i = 0; i < p.n_vcols; i++) q.vcol[i] = pv[i];
   q.terms.n = 0;
   q.vec = true;  // pool allocations are 256-byte aligned
-  q.part_begin = begin; q.n_parts = P;
+  q.part_begin = bounds; q.part_end = bounds + P; q.n_parts = P;
   const uint64_t per_part = (n_groups_hint + P - 1) / P;
   uint64_t need = pow2_at_least((per_part * 3 + 1) / 2);  // <= 67 % load even if the partitions are a little uneven
   if (need < 64) need = 64;
@@ -828,9 +832,6 @@ static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups
     count_launch(ctx);
   } else {
     // very high cardinality: every partition aggregates into an L2-resident slice-sized global table, reused in turn
-    std::vector<uint32_t> h(P + 1);
-    OLAP_CUDA(cudaMemcpyAsync(h.data(), begin, (P + 1) * 4, cudaMemcpyDeviceToHost, s));
-    OLAP_CUDA(cudaStreamSynchronize(s));
     GbParams t = q;
     t.g_cap = pow2_at_least(std::max<uint64_t>(2 * per_part + per_part / 2, 1024));
     const uint64_t n1 = t.g_cap + 1;
@@ -840,7 +841,7 @@ static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups
     const unsigned tgrid = capped_grid((n1 + 255) / 256, (uint64_t)ctx->sm_count * 8);
     const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
     for (uint32_t part = 0; part < P; part++) {
-      const uint64_t b0 = h[part], b1 = h[part + 1];
+      const uint64_t b0 = h[part], b1 = h[P + part];
       if (b1 == b0) continue;
       gb_init_kernel<<<tgrid, 256, 0, s>>>(t);
       GB_DISPATCH_NV(p.n_vcols, (gb_global_kernel<NV><<<capped_grid((b1 - b0 + tile - 1) / tile, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(t, b0, b1)));

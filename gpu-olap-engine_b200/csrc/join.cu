@@ -937,18 +937,56 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
 }
 
 // Partition pass of the partitioned group-by (groupby.cu): (key, up to 4 value columns) with the filter fused in.
+// Same two layouts as the join's sides: one pass into fixed-capacity regions, or -- when a region overflows (heavy hitters)
+// -- the exact histogram layout.  The outputs must hold group_by_partition_capacity(n, bits) rows; bounds: device [2P],
+// rows of partition p are [bounds[p], bounds[P + p]); h_bounds receives the same on the host.
+uint64_t group_by_partition_capacity(uint64_t n, int bits) { return side_rows_cap(n, bits); }
+
 olap_status group_by_partition_rows(olap_ctx* ctx, const uint64_t* keys, uint64_t n, const TermPack& terms, int n_vcols,
                                     const uint64_t* const* vcols, int bits, uint64_t* out_keys, uint64_t* const* out_vcols,
-                                    uint32_t* part_begin, cudaStream_t s) {
+                                    uint32_t* bounds, uint32_t* h_bounds, cudaStream_t s) {
   if (n_vcols > kMaxPay) { set_error("partitioned group-by carries at most %d value columns", kMaxPay); return OLAP_ERR_UNSUPPORTED; }
+  const uint32_t P = 1u << bits;
   Scratch sc(ctx, s);
-  uint32_t* hist = nullptr;
-  OLAP_TRY(sc.get<uint32_t>((uint64_t)(1u << bits) * ctx->sm_count * kPartCtasPerSm, &hist));
   PartArgs a;
   memset(&a, 0, sizeof(a));
-  a.bits = bits; a.keys = keys; a.n = n; a.hist = hist; a.out_keys = out_keys; a.terms = terms;
+  a.bits = bits; a.keys = keys; a.n = n; a.out_keys = out_keys; a.terms = terms;
   for (int q = 0; q < n_vcols; q++) { a.pay_in[q] = vcols[q]; a.pay_out[q] = out_vcols[q]; }
-  return run_partition(ctx, a, n_vcols, false, part_begin, s);
+  const uint64_t cap = alloc_capacity(n, P);
+  if (env_u64("OLAP_GB_ALLOC", 1) && (uint64_t)P * cap < 0xFFFFFFFFULL) {
+    uint32_t* cursor = nullptr;
+    OLAP_TRY(sc.get<uint32_t>(P, &cursor));
+    a.cursor = cursor; a.cap = (uint32_t)cap;
+    PartPlan pl = plan_partition(ctx, n);
+    a.chunk = pl.chunk; a.vec = aligned32(keys);
+    OLAP_CUDA(cudaMemsetAsync(cursor, 0, (size_t)P * 4, s));
+    switch (n_vcols) {
+      case 0: OLAP_TRY((launch_partition<0, false, true>(ctx, a, pl.grid, s))); break;
+      case 1: OLAP_TRY((launch_partition<1, false, true>(ctx, a, pl.grid, s))); break;
+      case 2: OLAP_TRY((launch_partition<2, false, true>(ctx, a, pl.grid, s))); break;
+      case 3: OLAP_TRY((launch_partition<3, false, true>(ctx, a, pl.grid, s))); break;
+      default: OLAP_TRY((launch_partition<4, false, true>(ctx, a, pl.grid, s))); break;
+    }
+    part_bounds_kernel<<<1, 256, 0, s>>>(nullptr, cursor, a.cap, P, bounds);
+    count_launch(ctx, 2);
+    std::vector<uint32_t> used(P);
+    OLAP_CUDA(cudaMemcpyAsync(used.data(), cursor, (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+    OLAP_CUDA(cudaMemcpyAsync(h_bounds, bounds, 2 * (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+    OLAP_CUDA(cudaStreamSynchronize(s));
+    bool overflow = false;
+    for (uint32_t p = 0; p < P; p++) overflow |= used[p] > a.cap;
+    if (!overflow) return OLAP_OK;
+  }
+  uint32_t *hist = nullptr, *beg = nullptr;
+  OLAP_TRY(sc.get<uint32_t>((uint64_t)P * ctx->sm_count * kPartCtasPerSm, &hist));
+  OLAP_TRY(sc.get<uint32_t>(P + 1, &beg));
+  a.cursor = nullptr; a.cap = 0; a.hist = hist;
+  OLAP_TRY(run_partition(ctx, a, n_vcols, false, beg, s));
+  part_bounds_kernel<<<1, 256, 0, s>>>(beg, nullptr, 0, P, bounds);
+  count_launch(ctx);
+  OLAP_CUDA(cudaMemcpyAsync(h_bounds, bounds, 2 * (size_t)P * 4, cudaMemcpyDeviceToHost, s));
+  OLAP_CUDA(cudaStreamSynchronize(s));
+  return OLAP_OK;
 }
 
 }  // namespace olap

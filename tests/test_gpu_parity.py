@@ -283,6 +283,16 @@ def test_group_by_partitioned_regime(ctx, G, hint):
     check_group_by(ctx, k, [v, v, v, v, v, f, f], ALL5 + [O.SUM, O.MIN], hint)
 
 
+def test_group_by_partitioned_skewed_keys_take_the_exact_layout(ctx):
+    # 60 % of the rows share one key: its fixed-capacity partition region overflows, the partition pass must fall back to
+    # the exact histogram layout and the aggregates must not change
+    n = (1 << 21) + 77
+    k = O.gen_uniform_i64(n, 4, 50000) * 31 + 5; v = O.gen_uniform_i64(n, 5, 1 << 20) - (1 << 19)
+    k[: int(n * 0.6)] = 123456789
+    np.random.default_rng(3).shuffle(k)
+    check_group_by(ctx, k, [v, v, v, v], [O.SUM, O.COUNT, O.MIN, O.MAX], 50000)
+
+
 def test_group_by_partitioned_with_fused_filter(ctx):
     import gpu_olap_engine_b200 as g
     n = 1 << 21
