@@ -56,6 +56,7 @@ struct GbParams {
   uint32_t s_copies;  // power of two
   int s_hskip;        // hash bits already used to choose the radix partition (0 in the shared regime)
   int s_hshift;       // 64 - log2(s_slots)
+  int s_sub_bits;     // partitioned regime: each partition is aggregated in 2^s_sub_bits passes over disjoint hash sub-ranges
   // partitioned input (keys / vcol point at the partitioned copies)
   const uint32_t* part_begin;
   const uint32_t* part_end;
@@ -463,7 +464,13 @@ __device__ __forceinline__ void smem_table_clear(const GbParams& p, const SmemTa
 // the ones that chose the radix partition (s_hskip = partition bits, 0 in the shared regime).
 __device__ __forceinline__ uint32_t smem_home(const GbParams& p, uint64_t key) {
   const uint64_t h = (key ^ (key >> 29)) * 0x9E3779B97F4A7C15ULL;
-  return (uint32_t)((h << p.s_hskip) >> p.s_hshift);  // the TOP remaining bits: a lower window of a multiplicative hash clusters
+  return (uint32_t)((h << (p.s_hskip + p.s_sub_bits)) >> p.s_hshift);  // the TOP remaining bits: a lower window of a multiplicative hash clusters
+}
+
+// hash sub-range of a key inside its partition (only called when s_sub_bits > 0)
+__device__ __forceinline__ uint32_t smem_sub(const GbParams& p, uint64_t key) {
+  const uint64_t h = (key ^ (key >> 29)) * 0x9E3779B97F4A7C15ULL;
+  return (uint32_t)((h << p.s_hskip) >> (64 - p.s_sub_bits));
 }
 
 // Aggregate this thread's kGbRows rows into the thread's copy of the table.  Every lane calls it (pass = false without a row).
@@ -639,7 +646,11 @@ __global__ void __launch_bounds__(kGbThreads) gb_part_smem_kernel(GbParams p) {
   __shared__ uint32_t s_groups, s_spill;
   const SmemTable t = smem_table(p, smem_raw);
   const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
-  for (uint32_t part = blockIdx.x; part < p.n_parts; part += gridDim.x) {
+  // work unit = (partition, hash sub-range): a partition whose groups do not fit one table is read 2^s_sub_bits times, each
+  // pass aggregating the keys of one sub-range -- still far cheaper than L2 atomics on a global table
+  const uint32_t n_units = p.n_parts << p.s_sub_bits;
+  for (uint32_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const uint32_t part = unit >> p.s_sub_bits, sub = unit & ((1u << p.s_sub_bits) - 1);
     smem_table_clear(p, t);
     if (threadIdx.x == 0) { s_groups = 0; s_spill = 0; }
     __syncthreads();
@@ -659,6 +670,10 @@ __global__ void __launch_bounds__(kGbThreads) gb_part_smem_kernel(GbParams p) {
         for (int q = 0; q < NV; q++) v[j][q] = nv[j][q];
       }
       if (base + tile < end) load_rows<NV, true>(p, base + tile + (uint64_t)threadIdx.x * kGbRows, begin, end, nkey, nv, npass);
+      if (p.s_sub_bits) {
+#pragma unroll
+        for (int j = 0; j < kGbRows; j++) pass[j] = pass[j] && smem_sub(p, key[j]) == sub;
+      }
       smem_update_rows<NV>(p, t, copy_base, key, v, pass, &s_spill);
     }
     __syncthreads();
@@ -818,16 +833,19 @@ static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups
   const uint64_t per_part = (n_groups_hint + P - 1) / P;
   uint64_t need = pow2_at_least((per_part * 3 + 1) / 2);  // <= 67 % load even if the partitions are a little uneven
   if (need < 64) need = 64;
+  // a partition whose table exceeds shared memory is aggregated in up to 4 passes over disjoint hash sub-ranges
+  int sub_bits = 0;
+  while (sub_bits < 2 && need > 64 && (need + 1) * slot_bytes(p) + 16 > 200 * 1024) { need >>= 1; sub_bits++; }
   const uint64_t bytes = (need + 1) * slot_bytes(p) + 16;
   if (bytes <= 200 * 1024) {
     uint64_t copies = 1;  // replicate small tables so that 512 threads do not hammer a few dozen slots (2 CTAs per SM: 100 KB each)
     while (copies < 16 && ((need + 1) * slot_bytes(p) * copies * 2 + 16) <= 100 * 1024) copies <<= 1;
-    q.s_slots = (uint32_t)need; q.s_copies = (uint32_t)copies; q.s_hskip = bits; q.s_hshift = 64 - ilog2_u64(need);
+    q.s_slots = (uint32_t)need; q.s_copies = (uint32_t)copies; q.s_hskip = bits; q.s_sub_bits = sub_bits; q.s_hshift = 64 - ilog2_u64(need);
     const uint64_t bytes = (need + 1) * slot_bytes(p) * copies + 16;
     const unsigned per_sm = bytes <= 100 * 1024 ? 2 : 1;
     GB_DISPATCH_NV(p.n_vcols, {
       OLAP_CUDA(cudaFuncSetAttribute(gb_part_smem_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-      gb_part_smem_kernel<NV><<<capped_grid(P, (uint64_t)ctx->sm_count * per_sm), kGbThreads, bytes, s>>>(q);
+      gb_part_smem_kernel<NV><<<capped_grid((uint64_t)P << sub_bits, (uint64_t)ctx->sm_count * per_sm), kGbThreads, bytes, s>>>(q);
     });
     count_launch(ctx);
   } else {
