@@ -201,6 +201,64 @@ class ShardedExchange:
         return outs, segs
 
 
+class PeerExchange:
+    """The shuffle's data movement over NVSwitch peer memory instead of NCCL point-to-point: every rank owns a symmetric
+    receive buffer per column (torch symmetric memory: the peers' buffers are mapped into this process), the W x W count
+    matrix is all-gathered (tiny), and each rank then stores its region for rank d directly at its final offset in d's
+    buffer -- a dense, contiguous receive buffer, no alignment rules, 766 GB/s per direction measured on B200 / NVLink 5
+    against 425 GB/s for NCCL send/recv (scratch/symm_probe.py).  A device-side barrier on the stream orders the stores
+    before the readers and the readers of the previous step before the stores."""
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.symm = symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.bufs = {}          # name -> (local tensor, handle, capacity rows)
+        self.bytes_sent = 0
+
+    def _buffer(self, name, rows, dtype, device):
+        ent = self.bufs.get(name)
+        if ent is None or ent[2] < rows:
+            cap = int(rows)
+            t = self.symm.empty(cap, dtype=dtype, device=device)
+            h = self.symm.rendezvous(t, self.group)
+            ent = (t, h, cap)
+            self.bufs[name] = ent
+        return ent
+
+    def exchange(self, cols, names, begin, count, capacity_rows):
+        """cols[i][begin[d] : begin[d] + count[d]] goes to rank d.  capacity_rows must be the same on every rank; returns
+        None (on every rank) when some rank would receive more than that -- the caller then takes the NCCL path."""
+        W, r = self.world, self.rank
+        dev = cols[0].device
+        mine = torch.tensor(count, dtype=torch.int64, device=dev)
+        allc = torch.empty(W * W, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=self.group)
+        Cm = allc.view(W, W).tolist()                       # Cm[s][d]: rows s sends to d (host waits: tiny)
+        recv_tot = [sum(Cm[s][d] for s in range(W)) for d in range(W)]
+        if max(recv_tot) > capacity_rows:
+            return None
+        outs = []
+        for col, name in zip(cols, names):
+            t, h, cap = self._buffer(name, capacity_rows, col.dtype, dev)
+            h.barrier()                                     # everyone is done reading what the previous step delivered
+            for k in range(W):
+                d = (r + k) % W                             # start with the own region, then round-robin over the peers
+                n = Cm[r][d]
+                if n == 0:
+                    continue
+                off = sum(Cm[s2][d] for s2 in range(r))
+                dst = t if d == r else h.get_buffer(d, (cap,), col.dtype)
+                dst[off:off + n].copy_(col[begin[d]:begin[d] + n])
+                if d != r:
+                    self.bytes_sent += n * col.element_size()
+            h.barrier()                                     # all stores have landed
+            outs.append(t[:recv_tot[r]])
+        return outs, [(s2, Cm[s2][r]) for s2 in range(W)]
+
+
 class ShardedJoin:
     """GpuHashJoin across ranks.  join() returns a dict describing this rank's shard of the result."""
 
@@ -208,8 +266,20 @@ class ShardedJoin:
         self.ops = ops
         self.x = ShardedExchange(group)
         self._comm = None   # side stream for the exchange, so it overlaps the next partition kernel
+        self.peer = None    # NVSwitch peer-memory exchange (CUDA + NCCL group only); OLAP_PEER_EXCHANGE=0 keeps NCCL send/recv
+        if self.x.nccl and self.x.world > 1 and os.environ.get("OLAP_PEER_EXCHANGE", "1") != "0":
+            try:
+                self.peer = PeerExchange(group)
+            except Exception as e:  # symmetric memory not available on this build / topology
+                print(f"[sharded] peer-memory exchange unavailable ({e}); using NCCL send/recv", file=sys.stderr)
 
-    def _exchange(self, pk, pid, begin, count, tag):
+    def _exchange(self, pk, pid, begin, count, tag, capacity_rows=None):
+        if self.peer is not None and capacity_rows:
+            got = self.peer.exchange([pk, pid], ["recv_k" + tag, "recv_i" + tag], begin, count, capacity_rows)
+            if got is not None:
+                (rk, ri), segs = got
+                self.x.bytes_sent += self.peer.bytes_sent; self.peer.bytes_sent = 0
+                return rk, ri, segs
         buf = getattr(self.ops, "buffer", None)
         bufs = None
         if buf and self.x.world > 1:   # cached receive buffers, sized once the counts are known
@@ -217,9 +287,14 @@ class ShardedJoin:
         (rk, ri), segs = self.x.exchange_regions([pk, pid], begin, count, bufs)
         return rk, ri, segs
 
+    @staticmethod
+    def _capacity(n_local):
+        """Rows a rank may receive for one side on the peer path (same formula on every rank): 30 % above an even split."""
+        return int(n_local * 1.3) + (1 << 16)
+
     def shuffle(self, keys, n, tag=""):
         pk, pid, begin, count = self.ops.shuffle_partition(keys, n, self.x.bits, tag)
-        return self._exchange(pk, pid, begin, count, tag)
+        return self._exchange(pk, pid, begin, count, tag, self._capacity(n))
 
     def shuffle_both(self, build_keys, n_build, probe_keys, n_probe):
         """Both sides; on CUDA the build-side exchange runs on a side stream while the probe side is being partitioned."""
@@ -234,15 +309,15 @@ class ShardedJoin:
         pk_s, pi_s, pmeta = self.ops.shuffle_partition_async(probe_keys, n_probe, self.x.bits, "_p")      # queued, not awaited
         with torch.cuda.stream(self._comm):
             self._comm.wait_event(done_b)
-            b = self._exchange(bk_s, bi_s, bbegin, bcount, "_b")
+            b = self._exchange(bk_s, bi_s, bbegin, bcount, "_b", self._capacity(n_build))
             ev = torch.cuda.Event(); ev.record(self._comm)
         m = pmeta.tolist()                              # host waits for the probe partition; the build exchange ran meanwhile
         main.wait_event(ev)
-        p = self._exchange(pk_s, pi_s, m[:P + 1], m[P + 1:], "_p")
+        p = self._exchange(pk_s, pi_s, m[:P + 1], m[P + 1:], "_p", self._capacity(n_probe))
         return b, p
 
     def join(self, build_keys, n_build, probe_keys, n_probe, max_matches=None, strategy=JOIN_AUTO):
-        if build_keys.is_cuda and self.x.world > 1 and hasattr(self.ops, "join_build"):
+        if build_keys.is_cuda and self.x.world > 1 and hasattr(self.ops, "join_build") and self.peer is None:
             return self._join_overlapped(build_keys, n_build, probe_keys, n_probe, max_matches, strategy)
         (bk, bi, bsegs), (pk, pi, psegs) = self.shuffle_both(build_keys, n_build, probe_keys, n_probe)
         nb, npb = int(bk.numel()), int(pk.numel())
