@@ -62,6 +62,9 @@ SIGNATURES = {
     "olap_partition_of": (u32, [i64, i32]),
     "olap_shuffle_partition_i64": (i32, [vp, vp, vp, u64, i32, vp, vp, vp, vp, vp]),
     "olap_shuffle_dest_of": (u32, [i64, i32]),
+    "olap_shuffle_scratch_words": (u64, [vp, i32]),
+    "olap_shuffle_count_i64": (i32, [vp, vp, u64, i32, vp, vp, vp]),
+    "olap_shuffle_scatter_i64": (i32, [vp, vp, u64, i32, vp, vp, vp, vp, vp]),
     "olap_group_by_i64": (i32, [vp, vp, C.POINTER(AggSpec), i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_agg_identity": (i64, [i32]),
     "olap_compute_launch_params": (None, [u64, C.POINTER(u32), C.POINTER(u32)]),

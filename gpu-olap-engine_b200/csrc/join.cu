@@ -27,6 +27,7 @@ constexpr int kPartTile = 4096;          // rows staged per CTA iteration (8 per
 constexpr int kPartCtasPerSm = 2;
 constexpr int kMaxPartBits = 8;          // <= 256 partitions per pass
 constexpr int kMaxPay = 4;
+constexpr int kMaxPeers = 8;
 constexpr uint64_t kShuffleSalt = 0x5bd1e9955bd1e995ULL;  // multi-GPU destination hash = mix64(key ^ salt)               // 8-byte payload columns carried along (group-by)
 
 struct PartArgs {
@@ -39,6 +40,12 @@ struct PartArgs {
   uint32_t* hist;                        // [P][gridDim.x]: counts, then exclusive offsets after the scan
   uint32_t* cursor;                      // ALLOC mode: rows handed out so far per partition (global atomics), [P]
   uint32_t cap;                          // ALLOC mode: partition p owns output rows [p * cap, (p + 1) * cap)
+  // PEER mode (multi-GPU shuffle fused with the exchange, <= kMaxPeers partitions): partition p is written straight into
+  // rank p's receive buffers (peer-mapped pointers), starting at row peer_off[p] there; exact per-CTA offsets from the histogram
+  uint64_t* peer_keys[8];
+  uint32_t* peer_ids[8];
+  uint32_t peer_off[8];
+  const uint32_t* part_begin;            // PEER mode: scanned partition starts (device, [P + 1])
   uint64_t* out_keys;
   uint32_t* out_ids;
   uint64_t* pay_out[kMaxPay];
@@ -142,8 +149,14 @@ __global__ void __launch_bounds__(1024) part_scan_kernel(uint32_t* hist, uint32_
 // ALLOC = true : no histogram pass; partition p owns a fixed-capacity region and every tile reserves its run in it with
 //                one global atomic per (tile, partition).  Saves a full read of the keys; a region that overflows (skewed
 //                keys) is reported through cursor[p] > cap and the caller falls back to the exact layout.
-template <int NPAY, bool IDS, bool ALLOC>
+// PEER  = true : exact offsets like ALLOC = false, but partition p (= destination rank p) has its own output arrays:
+//                the stores of the write-out phase go over NVLink into the peers' receive buffers -- the exchange of the
+//                multi-GPU shuffle happens inside this kernel, run by run, instead of in a collective after it.
+template <int NPAY, bool IDS, bool ALLOC, bool PEER = false>
 __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) partition_kernel(PartArgs a) {
+  constexpr bool BYPART = ALLOC || PEER;  // the staged row remembers its partition, the destination is formed at write-out
+  __shared__ uint64_t* s_kptr[kMaxPeers];
+  __shared__ uint32_t* s_iptr[kMaxPeers];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* s_key = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* s_pay = s_key + kPartTile;                               // [NPAY][kPartTile]
@@ -154,7 +167,14 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
 
   const int P = 1 << a.bits, sh = 64 - a.bits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < P; i += kPartThreads) { s_cnt[i] = 0; s_cursor[i] = ALLOC ? 0u : a.hist[(uint64_t)i * gridDim.x + blockIdx.x]; }
+  for (int i = tid; i < P; i += kPartThreads) {
+    s_cnt[i] = 0;
+    s_cursor[i] = ALLOC ? 0u : a.hist[(uint64_t)i * gridDim.x + blockIdx.x];
+    if (PEER) {
+      s_cursor[i] = s_cursor[i] - a.part_begin[i] + a.peer_off[i];
+      s_kptr[i] = a.peer_keys[i]; s_iptr[i] = a.peer_ids[i];
+    }
+  }
   static_assert(kPartTile <= 65536, "rank is packed into 16 bits");
   __syncthreads();
   const uint64_t begin = blockIdx.x * a.chunk, end = min(a.n, begin + a.chunk);
@@ -219,7 +239,7 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
           const uint64_t row = tile + (uint64_t)(j * kPartThreads + tid) * 4 + e;
           const uint32_t part = pr[j][e] >> 16, pos = s_off[part] + (pr[j][e] & 0xFFFFu);
           s_key[pos] = k[j][e];
-          s_dst[pos] = ALLOC ? part : s_gbase[part] + pos;
+          s_dst[pos] = BYPART ? part : s_gbase[part] + pos;
           if (IDS) s_id[pos] = a.ids_in ? ld_stream_u32(a.ids_in + row) : (uint32_t)row;
 #pragma unroll
           for (int q = 0; q < NPAY; q++) s_pay[(size_t)q * kPartTile + pos] = ld_stream_u64(a.pay_in[q] + row);
@@ -233,6 +253,13 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
     const uint32_t total = s_total;
     for (uint32_t i = tid; i < total; i += kPartThreads) {
       uint32_t dst = s_dst[i];
+      if (PEER) {
+        const uint32_t part = dst;
+        dst = s_gbase[part] + i;
+        s_kptr[part][dst] = s_key[i];
+        if (IDS) s_iptr[part][dst] = s_id[i];
+        continue;
+      }
       if (ALLOC) {
         if (!s_cursor[dst]) continue;
         dst = s_gbase[dst] + i;
@@ -257,11 +284,11 @@ static PartPlan plan_partition(olap_ctx* ctx, uint64_t n) {
   return {grid, chunk};
 }
 
-template <int NPAY, bool IDS, bool ALLOC = false>
+template <int NPAY, bool IDS, bool ALLOC = false, bool PEER = false>
 static olap_status launch_partition(olap_ctx* ctx, PartArgs& a, unsigned grid, cudaStream_t s) {
   const size_t smem = (size_t)kPartTile * (8 + 8 * NPAY + (IDS ? 4 : 0) + 4);
-  OLAP_CUDA((cudaFuncSetAttribute(partition_kernel<NPAY, IDS, ALLOC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-  partition_kernel<NPAY, IDS, ALLOC><<<grid, kPartThreads, smem, s>>>(a);
+  OLAP_CUDA((cudaFuncSetAttribute(partition_kernel<NPAY, IDS, ALLOC, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  partition_kernel<NPAY, IDS, ALLOC, PEER><<<grid, kPartThreads, smem, s>>>(a);
   count_launch(ctx);
   return OLAP_OK;
 }
@@ -1130,6 +1157,62 @@ olap_status olap_shuffle_partition_i64(olap_ctx* ctx, const int64_t* keys, const
                                        int64_t* out_keys, uint32_t* out_row_ids, uint32_t* out_part_begin, uint32_t* out_part_count,
                                        void* stream) {
   return partition_api(ctx, keys, row_ids, n_rows, bits, kShuffleSalt, out_keys, out_row_ids, out_part_begin, out_part_count, stream);
+}
+
+// Shuffle fused with the exchange.  scratch: olap_shuffle_scratch_words(bits) u32 = [P][grid] histogram, then [P + 1] starts.
+uint64_t olap_shuffle_scratch_words(olap_ctx* ctx, int32_t bits) {
+  if (!ctx || bits < 0 || bits > 3) return 0;
+  const uint64_t P = 1ULL << bits;
+  return P * (uint64_t)ctx->sm_count * kPartCtasPerSm + P + 1;
+}
+
+static olap_status shuffle_args(olap_ctx* ctx, const int64_t* keys, uint64_t n_rows, int32_t bits, uint32_t* scratch, PartArgs* a, PartPlan* pl) {
+  OLAP_REQUIRE(ctx && keys && scratch, "NULL argument");
+  OLAP_REQUIRE(bits >= 1 && bits <= 3, "the fused shuffle serves 2, 4 or 8 ranks");
+  OLAP_REQUIRE(n_rows > 0 && n_rows < 0xFFFFFFFFULL, "row ids are u32 and the fused shuffle needs at least one row");
+  memset(a, 0, sizeof(*a));
+  *pl = plan_partition(ctx, n_rows);
+  a->bits = bits; a->salt = kShuffleSalt; a->keys = (const uint64_t*)keys; a->n = n_rows; a->hist = scratch;
+  a->chunk = pl->chunk; a->vec = aligned32(keys);
+  a->part_begin = scratch + (1ULL << bits) * ctx->sm_count * kPartCtasPerSm;
+  return OLAP_OK;
+}
+
+olap_status olap_shuffle_count_i64(olap_ctx* ctx, const int64_t* keys, uint64_t n_rows, int32_t bits, uint32_t* scratch,
+                                   uint32_t* out_part_count, void* stream) {
+  PartArgs a; PartPlan pl;
+  OLAP_TRY(shuffle_args(ctx, keys, n_rows, bits, scratch, &a, &pl));
+  OLAP_REQUIRE(out_part_count, "out_part_count is NULL");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream_of(stream);
+  const uint32_t P = 1u << bits;
+  // the kernels index the histogram by the launched grid: clear the slots of a full-size grid first
+  OLAP_CUDA(cudaMemsetAsync(scratch, 0, olap_shuffle_scratch_words(ctx, bits) * 4, s));
+  part_hist_kernel<<<pl.grid, kPartThreads, 0, s>>>(a);
+  part_scan_kernel<<<1, 1024, 0, s>>>(a.hist, P * pl.grid, pl.grid, P, const_cast<uint32_t*>(a.part_begin), out_part_count, 0);
+  count_launch(ctx, 3);
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
+
+olap_status olap_shuffle_scatter_i64(olap_ctx* ctx, const int64_t* keys, uint64_t n_rows, int32_t bits, uint32_t* scratch,
+                                     int64_t* const* dest_keys, uint32_t* const* dest_row_ids, const uint64_t* dest_row_offset, void* stream) {
+  PartArgs a; PartPlan pl;
+  OLAP_TRY(shuffle_args(ctx, keys, n_rows, bits, scratch, &a, &pl));
+  OLAP_REQUIRE(dest_keys && dest_row_ids && dest_row_offset, "NULL destination table");
+  const uint32_t P = 1u << bits;
+  for (uint32_t p = 0; p < P; p++) {
+    OLAP_REQUIRE(dest_keys[p] && dest_row_ids[p], "NULL destination pointer");
+    OLAP_REQUIRE(dest_row_offset[p] + n_rows < 0xFFFFFFFFULL, "destination offsets are u32 rows");
+    a.peer_keys[p] = (uint64_t*)dest_keys[p]; a.peer_ids[p] = dest_row_ids[p]; a.peer_off[p] = (uint32_t)dest_row_offset[p];
+  }
+  std::lock_guard<std::mutex> g(ctx->mu);
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream_of(stream);
+  OLAP_TRY((launch_partition<0, true, false, true>(ctx, a, pl.grid, s)));
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
 }
 
 uint32_t olap_shuffle_dest_of(int64_t key, int32_t bits) {

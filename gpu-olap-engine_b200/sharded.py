@@ -259,6 +259,36 @@ class PeerExchange:
         return outs, [(s2, Cm[s2][r]) for s2 in range(W)]
 
 
+    def fused_shuffle(self, ops, keys, n, names, capacity_rows):
+        """Partition + exchange in one kernel: the partition kernel of every rank stores (key, source row id) of each row
+        straight into the destination rank's receive buffers at the final offset (olap_shuffle_scatter_i64).  Only the
+        W x W count matrix goes through a collective.  Returns like exchange(); None when a rank would overflow."""
+        W, r = self.world, self.rank
+        bits = _log2(W)
+        dev = keys.device
+        lib, ctx = ops.lib, ops.ctx
+        words = int(lib.olap_shuffle_scratch_words(ctx.handle, bits))
+        scratch = ops.buffer("shuffle_scratch_" + names[0], words, torch.int32)
+        cnt = ops.empty(W, torch.int32)
+        _lib.check(lib.olap_shuffle_count_i64(ctx.handle, keys.data_ptr(), n, bits, scratch.data_ptr(), cnt.data_ptr(), ops._stream()))
+        allc = torch.empty(W * W, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, cnt.to(torch.int64), group=self.group)
+        Cm = allc.view(W, W).tolist()                       # Cm[s][d]: rows s sends to d (host waits: tiny)
+        recv_tot = [sum(Cm[s][d] for s in range(W)) for d in range(W)]
+        if max(recv_tot) > capacity_rows:
+            return None
+        tk, hk, _ = self._buffer(names[0], capacity_rows, torch.int64, dev)
+        ti, hi, _ = self._buffer(names[1], capacity_rows, torch.int32, dev)
+        hk.barrier()                                        # everyone is done reading what the previous step delivered
+        dk = (C.c_void_p * W)(*[int(p) for p in hk.buffer_ptrs])
+        di = (C.c_void_p * W)(*[int(p) for p in hi.buffer_ptrs])
+        off = (C.c_uint64 * W)(*[sum(Cm[s2][d] for s2 in range(r)) for d in range(W)])
+        _lib.check(lib.olap_shuffle_scatter_i64(ctx.handle, keys.data_ptr(), n, bits, scratch.data_ptr(), dk, di, off, ops._stream()))
+        hk.barrier()                                        # every rank's stores have landed
+        self.bytes_sent += (n - Cm[r][r]) * 12
+        return [tk[:recv_tot[r]], ti[:recv_tot[r]]], [(s2, Cm[s2][r]) for s2 in range(W)]
+
+
 class ShardedJoin:
     """GpuHashJoin across ranks.  join() returns a dict describing this rank's shard of the result."""
 
@@ -266,6 +296,7 @@ class ShardedJoin:
         self.ops = ops
         self.x = ShardedExchange(group)
         self._comm = None   # side stream for the exchange, so it overlaps the next partition kernel
+        self.fuse = os.environ.get("OLAP_FUSED_SHUFFLE", "1") != "0"   # partition kernel stores straight into the peers' buffers
         self.peer = None    # NVSwitch peer-memory exchange (CUDA + NCCL group only); OLAP_PEER_EXCHANGE=0 keeps NCCL send/recv
         if self.x.nccl and self.x.world > 1 and os.environ.get("OLAP_PEER_EXCHANGE", "1") != "0":
             try:
@@ -292,13 +323,27 @@ class ShardedJoin:
         """Rows a rank may receive for one side on the peer path (same formula on every rank): 30 % above an even split."""
         return int(n_local * 1.3) + (1 << 16)
 
+    def _fused(self, keys, n, tag):
+        """Fused partition + peer-store shuffle of one side, or None when it is unavailable / would overflow."""
+        if self.peer is None or not self.fuse or n == 0 or self.x.world > 8 or not hasattr(self.ops, "lib"):
+            return None
+        got = self.peer.fused_shuffle(self.ops, keys, n, ["recv_k" + tag, "recv_i" + tag], self._capacity(n))
+        if got is None:
+            return None
+        (rk, ri), segs = got
+        self.x.bytes_sent += self.peer.bytes_sent; self.peer.bytes_sent = 0
+        return rk, ri, segs
+
     def shuffle(self, keys, n, tag=""):
+        got = self._fused(keys, n, tag)
+        if got is not None:
+            return got
         pk, pid, begin, count = self.ops.shuffle_partition(keys, n, self.x.bits, tag)
         return self._exchange(pk, pid, begin, count, tag, self._capacity(n))
 
     def shuffle_both(self, build_keys, n_build, probe_keys, n_probe):
         """Both sides; on CUDA the build-side exchange runs on a side stream while the probe side is being partitioned."""
-        if not (build_keys.is_cuda and self.x.world > 1 and hasattr(self.ops, "shuffle_partition_async")):
+        if not (build_keys.is_cuda and self.x.world > 1 and hasattr(self.ops, "shuffle_partition_async")) or (self.peer is not None and self.fuse):
             return self.shuffle(build_keys, n_build, "_b"), self.shuffle(probe_keys, n_probe, "_p")
         P = self.x.world
         main = torch.cuda.current_stream()

@@ -175,6 +175,22 @@ OLAP_API olap_status olap_shuffle_partition_i64(olap_ctx* ctx, const int64_t* ke
                                                 uint32_t* out_part_count, void* stream);
 OLAP_API uint32_t olap_shuffle_dest_of(int64_t key, int32_t bits);
 
+/* The same shuffle FUSED with the exchange over NVSwitch peer memory (2, 4 or 8 ranks: bits in [1, 3]).
+ *   1. olap_shuffle_count_i64: rows this rank holds for every destination -> out_part_count (dptr, 2^bits u32).
+ *   2. the caller all-gathers the count matrix and derives, for every destination p, the first row this rank owns in
+ *      rank p's receive buffers (sum of the counts of the lower ranks).
+ *   3. olap_shuffle_scatter_i64: the partition kernel stores (key, source row id) of every row directly at
+ *      dest_keys[p][dest_row_offset[p] + ...] / dest_row_ids[p][...]: pointers into the PEERS' memory (e.g. torch symmetric
+ *      memory buffer_ptrs), written run by run over NVLink -- no send buffer, no collective for the payload.
+ * scratch (dptr): olap_shuffle_scratch_words(ctx, bits) u32, the same buffer for both calls, untouched in between.
+ * The caller orders the stores against the readers (a barrier across ranks before and after step 3).            */
+OLAP_API uint64_t olap_shuffle_scratch_words(olap_ctx* ctx, int32_t bits);
+OLAP_API olap_status olap_shuffle_count_i64(olap_ctx* ctx, const int64_t* keys, uint64_t n_rows, int32_t bits, uint32_t* scratch,
+                                            uint32_t* out_part_count, void* stream);
+OLAP_API olap_status olap_shuffle_scatter_i64(olap_ctx* ctx, const int64_t* keys, uint64_t n_rows, int32_t bits, uint32_t* scratch,
+                                              int64_t* const* dest_keys, uint32_t* const* dest_row_ids,
+                                              const uint64_t* dest_row_offset, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Aggregation.  Replaces AggregateParams/AggregateSpec/AggregateKernel::aggregate
  * (gpu-kernel-compiler/src/aggregate_kernel.rs:37-125) and hash_aggregate_kernel (join_kernels.cuh:216-240).
