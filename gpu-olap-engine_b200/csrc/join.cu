@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(kJoinThreads, 4) probe_kernel(const uint64_t* 
 struct PipeArgs {
   const uint64_t* bkeys; const uint32_t* bids; const uint64_t* pkeys; const uint32_t* pids;
   const uint32_t* bb; const uint32_t* pb;          // device, [2P]: rows of partition p are [x[p], x[P + p])
-  uint32_t P; int bits; uint32_t R; uint32_t pid_base;
+  uint32_t P; int bits; uint32_t R; uint32_t pid_base; uint32_t load_pct;
   Bucket* arena; uint64_t stride;                  // ring slot r = arena + r * stride buckets
   uint32_t* sync;                                  // [0] ticket, then cleared[P], built[P], probed[P]; zeroed before the launch
   uint32_t grid_dbg;
@@ -627,9 +627,14 @@ __host__ __device__ __forceinline__ uint32_t tiles_of(uint32_t begin, uint32_t e
   return (uint32_t)(((uint64_t)end - (begin & ~3u) + tile - 1) / tile);
 }
 struct PartWork { uint32_t n_clear, n_build, n_probe, nbk; };
-__host__ __device__ __forceinline__ PartWork part_work(uint32_t b0, uint32_t b1, uint32_t p0, uint32_t p1) {
+// buckets of a table: load_pct / 100 two-slot buckets per build row (100 = load factor 0.5)
+__host__ __device__ __forceinline__ uint32_t table_buckets(uint32_t rows, uint32_t load_pct) {
+  const uint64_t b = ((uint64_t)rows * load_pct + 99) / 100;
+  return b > 64 ? (uint32_t)b : 64u;
+}
+__host__ __device__ __forceinline__ PartWork part_work(uint32_t b0, uint32_t b1, uint32_t p0, uint32_t p1, uint32_t load_pct) {
   PartWork w;
-  w.nbk = b1 - b0 > 64u ? b1 - b0 : 64u;           // one bucket per build row
+  w.nbk = table_buckets(b1 - b0, load_pct);
   const bool active = b1 > b0 && p1 > p0;          // inner join: an empty side yields nothing
   w.n_clear = active ? (w.nbk + kClearTile - 1) / kClearTile : 0;
   w.n_build = active ? tiles_of(b0, b1, kJoinTile) : 0;
@@ -678,21 +683,21 @@ __global__ void __launch_bounds__(kJoinThreads, 4) join_pipeline_kernel(const __
     int phase = 0;
     uint32_t p = s;
     if (s < P) {
-      const PartWork w = part_work(a.bb[s], a.bb[P + s], a.pb[s], a.pb[P + s]);
+      const PartWork w = part_work(a.bb[s], a.bb[P + s], a.pb[s], a.pb[P + s], a.load_pct);
       if (idx >= w.n_clear) { idx -= w.n_clear; phase = 1; }
     } else phase = 1;
     if (phase == 1) {
       p = s - 1;
       uint32_t nbd = 0;
-      if (s >= 1 && s <= P) nbd = part_work(a.bb[p], a.bb[P + p], a.pb[p], a.pb[P + p]).n_build;
+      if (s >= 1 && s <= P) nbd = part_work(a.bb[p], a.bb[P + p], a.pb[p], a.pb[P + p], a.load_pct).n_build;
       if (idx >= nbd) { idx -= nbd; phase = 2; p = s - 2; }
     }
     const uint32_t b0 = a.bb[p], b1 = a.bb[P + p], p0 = a.pb[p], p1 = a.pb[P + p];
-    const PartWork w = part_work(b0, b1, p0, p1);
+    const PartWork w = part_work(b0, b1, p0, p1, a.load_pct);
     Bucket* table = a.arena + (uint64_t)(p % a.R) * a.stride;
     if (phase == 0) {
       uint32_t need = 0;
-      if (p >= a.R) { const uint32_t q = p - a.R; need = part_work(a.bb[q], a.bb[P + q], a.pb[q], a.pb[P + q]).n_probe; }
+      if (p >= a.R) { const uint32_t q = p - a.R; need = part_work(a.bb[q], a.bb[P + q], a.pb[q], a.pb[P + q], a.load_pct).n_probe; }
       pipe_wait(probed + (p >= a.R ? p - a.R : 0), need, a.waited + 0);
       const uint32_t c0 = idx * kClearTile, c1 = min(w.nbk, c0 + kClearTile);
       const u64x4 z = {0, 0, 0, 0};
@@ -875,8 +880,9 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   std::vector<uint32_t> hp;
   OLAP_TRY(partition_side(ctx, pk, np, bits, pkp, pip, d_pb, hp, sc, s, "hist_probe", "partition_probe"));
   const uint32_t* hb = b.hb.data();
-  const uint64_t nbk = std::max<uint64_t>(b.max_part, 64);  // buckets per table: exactly 32 B per build row of the largest partition
-  auto work = [&](uint32_t p) { return part_work(hb[p], hb[P + p], hp[p], hp[P + p]); };
+  const uint32_t load_pct = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(env_u64("OLAP_JOIN_LOAD", 100), 50), 400);
+  const uint64_t nbk = table_buckets((uint32_t)b.max_part, load_pct);  // buckets per table slot, sized for the largest partition
+  auto work = [&](uint32_t p) { return part_work(hb[p], hb[P + p], hp[p], hp[P + p], load_pct); };
 
   if (env_u64("OLAP_JOIN_PIPE", 1)) {
     // the join pipeline: one persistent kernel over all partitions (see join_pipeline_kernel)
@@ -896,7 +902,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     OLAP_CUDA(cudaMemsetAsync(sync, 0, sync_words * 4, s));
     pa.waited = reinterpret_cast<unsigned long long*>(sync + ((1 + 3 * (uint64_t)P + 1) & ~1ULL));
     pa.bkeys = b.pkb; pa.bids = b.pib; pa.pkeys = pkp; pa.pids = pip; pa.bb = b.d_bounds; pa.pb = d_pb;
-    pa.P = P; pa.bits = bits; pa.R = (uint32_t)R; pa.pid_base = pid_base;
+    pa.P = P; pa.bits = bits; pa.R = (uint32_t)R; pa.pid_base = pid_base; pa.load_pct = load_pct;
     pa.arena = (Bucket*)ctx->table_arena; pa.stride = nbk; pa.sync = sync;
     pa.out = out; pa.max_matches = max_matches; pa.count = d_count;
     uint64_t items = 0;
@@ -943,7 +949,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     const int k = p % S;
     cudaStream_t st = (dbg & 4) ? s : ctx->streams[k];
     Bucket* table = (Bucket*)ctx->table_arena + (uint64_t)k * nbk;
-    const uint64_t tb = std::max<uint64_t>(b1 - b0, 64);  // this partition's table: one bucket per build row
+    const uint64_t tb = table_buckets((uint32_t)(b1 - b0), load_pct);  // this partition's table
     if (!(dbg & 2)) {
       OLAP_CUDA(cudaMemsetAsync(table, 0, tb * 32, st));
       count_launch(ctx);
