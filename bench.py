@@ -267,9 +267,9 @@ def run_ours(args):
     # ---- CPU baseline (oracle port of the reference CPU path) on a bounded sample, all host cores and single-thread
     cores = os.cpu_count() or 1
     cpu_rps, cpu_sec, _ = cpu_reference_join(args.cpu_log2_build, args.cpu_log2_probe, cores)
-    cpu1_rps, _, _ = cpu_reference_join(args.cpu_log2_build - 2, args.cpu_log2_probe - 2, 1)
+    cpu1_rps, _, _ = cpu_reference_join(args.cpu_log2_build - 3, args.cpu_log2_probe - 3, 1)
     sample = (f"2^{args.cpu_log2_build} unique-key build x 2^{args.cpu_log2_probe} FK probe (same generator), pairs materialised, "
-              f"{cores} threads, {cpu_sec:.2f} s; single-thread ref1 on a 4x smaller sample: {cpu1_rps / 1e6:.1f} M rows/s")
+              f"{cores} threads, {cpu_sec:.2f} s; single-thread ref1 on an 8x smaller sample: {cpu1_rps / 1e6:.1f} M rows/s")
 
     line = {
         "metric": "join rows/sec (|build|+|probe|)/time", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
@@ -310,8 +310,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-build", type=int, default=27)
     ap.add_argument("--log2-probe", type=int, default=29)
-    ap.add_argument("--cpu-log2-build", type=int, default=24)
-    ap.add_argument("--cpu-log2-probe", type=int, default=26)
+    ap.add_argument("--cpu-log2-build", type=int, default=26)
+    ap.add_argument("--cpu-log2-probe", type=int, default=28)
     ap.add_argument("--zipf", type=float, default=0.0)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: omit the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: omit the CPU baseline leg")
