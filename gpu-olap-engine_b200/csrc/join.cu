@@ -473,14 +473,17 @@ __device__ __forceinline__ void stage_or_spill(uint2* stage, uint32_t idx, uint3
 }
 
 // Probe one tile of kJoinTile rows starting at `tile` (a multiple of 4 rows) against one table.  Called by the whole CTA.
-template <bool VEC>
+// PIPE: called from the join pipeline, whose own barriers already cover the reset of sh.n before and the reuse of sh after.
+template <bool VEC, bool PIPE = false>
 __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Bucket* __restrict__ table, uint32_t nb, int bits, uint32_t pid_base,
                                            const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids, uint64_t begin, uint64_t end,
                                            uint64_t tile, olap_pair* __restrict__ out, uint64_t max_matches,
                                            unsigned long long* __restrict__ count) {
   const int tid = threadIdx.x, lane = tid & 31;
-  if (tid == 0) sh.n = 0;
-  __syncthreads();
+  if (!PIPE) {
+    if (tid == 0) sh.n = 0;
+    __syncthreads();
+  }
 #pragma unroll 1
   for (int sub = 0; sub < kJoinSub; sub++) {
     const uint64_t row0 = tile + (uint64_t)(sub * kJoinThreads + tid) * kJoinRows;
@@ -574,7 +577,7 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Bucket* __rest
       }
     }
   }
-  __syncthreads();
+  if (!PIPE) __syncthreads();
 }
 
 // one table, one relation: the single-table (broadcast) strategy and the per-partition fallback
@@ -671,8 +674,7 @@ __global__ void __launch_bounds__(kJoinThreads, 4) join_pipeline_kernel(const __
   if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
   __syncthreads();
   for (;;) {
-    const uint32_t t = s_ticket;
-    __syncthreads();
+    const uint32_t t = s_ticket;  // written before the barrier that ended the previous item; rewritten only after this item's barriers
     if (t >= total) break;
     uint32_t next = 0;
     if (tid == 0) next = atomicAdd(ticket, 1u);  // in flight while this item runs
@@ -708,8 +710,9 @@ __global__ void __launch_bounds__(kJoinThreads, 4) join_pipeline_kernel(const __
       build_tile<true>(table, w.nbk, a.bits, a.bkeys, a.bids, b0, b1, (b0 & ~3u) + (uint64_t)idx * kJoinTile);
       pipe_signal(built + p);
     } else {
+      if (tid == 0) sh.n = 0;  // ordered before the tile by pipe_wait's barrier
       pipe_wait(built + p, w.n_build, a.waited + 2);
-      probe_tile<true>(sh, table, w.nbk, a.bits, a.pid_base, a.pkeys, a.pids, p0, p1, (p0 & ~3u) + (uint64_t)idx * kJoinTile, a.out,
+      probe_tile<true, true>(sh, table, w.nbk, a.bits, a.pid_base, a.pkeys, a.pids, p0, p1, (p0 & ~3u) + (uint64_t)idx * kJoinTile, a.out,
                        a.max_matches, a.count);
       pipe_signal(probed + p);
     }
