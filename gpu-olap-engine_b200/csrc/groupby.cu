@@ -10,8 +10,9 @@
 //                tables are merged into the global table at the end
 //   partitioned  rows (key + distinct value columns, filter applied) are radix-partitioned by key hash with join.cu's
 //                write-combining partitioner, so that every partition's groups fit a shared-memory table (one CTA per
-//                partition, results written straight to the output) or, for very high cardinalities, an L2-resident
-//                global table reused partition after partition
+//                partition -- or per hash sub-range of a partition, up to 4 passes over its rows -- results written
+//                straight to the output) or, for very high cardinalities, an L2-resident global table reused
+//                partition after partition
 //   global       one global open-addressing table (native 64-bit L2 atomics, read-before-atomic MIN/MAX): the
 //                universal fallback (also the spill target of the other regimes)
 // Roofline: HBM; algorithmic bytes per row = 8 B key + 8 B per distinct value column (+ 8 B per predicate column).

@@ -1,20 +1,21 @@
-// Radix hash join on int64 keys: histogram -> scan -> shared-memory-staged, write-combining radix partition ->
-// per-partition open-addressing build/probe in an L2-resident table.  Replaces radix_partition_kernel,
-// build_hash_table_kernel and probe_hash_table_kernel (gpu-kernel-compiler/kernels/join_kernels.cuh:45-166) and the
-// stub JoinKernel::join (gpu-kernel-compiler/src/join_kernel.rs:39-68).
+// Radix hash join on int64 keys: shared-memory-staged, write-combining radix partition of both sides -> ONE persistent
+// pipeline kernel that clears, builds and probes the L2-resident bucket table of every partition.  Replaces
+// radix_partition_kernel, build_hash_table_kernel and probe_hash_table_kernel
+// (gpu-kernel-compiler/kernels/join_kernels.cuh:45-166) and the stub JoinKernel::join
+// (gpu-kernel-compiler/src/join_kernel.rs:39-68).  Also: the multi-GPU shuffle (same partition kernel, destination rank
+// instead of radix partition, optionally storing straight into the peers' receive buffers) and the partition pass of the
+// partitioned group-by.
 //
-// Why this shape (measured on B200, scratch/micro.cu -> profiles/r01_microbench.txt):
-//   * random 16-byte gathers run at ~260 G/s while the table is L2-resident (<= 64 MB) but 37 G/s once it spills
+// Why this shape (measured on B200, scratch/micro.cu -> profiles/r01_microbench_hw_facts.txt):
+//   * random 32-byte gathers run at ~260 G/s while the table is L2-resident (<= 64 MB) but 37 G/s once it spills
 //     to HBM (4 GB), and global atomics 110-165 G/s vs 20 G/s -> partition until one partition's table fits L2;
 //   * a per-row global atomic + scatter (the reference's partition kernel) does 18 G rows/s; shared-memory atomics
 //     are NOT a bottleneck (820 G rows/s histogram) -> rank rows with smem atomics, stage the tile in shared memory,
-//     write each partition's run with coalesced stores, and take the per-CTA output offsets from a histogram pass so
-//     that the partition kernel issues no global atomics at all;
+//     write each partition's run with coalesced stores; output positions come from one global atomic per (tile,
+//     partition) into fixed-capacity regions, or from a histogram pass when an exact contiguous layout is needed;
 //   * one global atomic per match (the reference's probe) serialises on one address (1.5 G/s) -> matches are staged
 //     per CTA tile in shared memory and reserved with one atomic per tile.
-// Table slots carry a generation tag, so the table arena is never cleared between partitions or joins.
 #include "common.cuh"
-
 
 #include <algorithm>
 #include <cstdlib>
