@@ -8,6 +8,7 @@
 #include <cfloat>
 #include <cstdlib>
 #include <memory>
+#include <cmath>
 #include <map>
 
 namespace {
@@ -33,7 +34,8 @@ struct Col {
   std::string name;
   int type = OLAP_I64;  // OLAP_I64 / OLAP_F64 (record_batch_convert.rs: everything is one of the two 8-byte layouts)
   BufPtr buf;
-  uint64_t* data() const { return (uint64_t*)buf->p; }
+  uint64_t off = 0;     // first row inside buf: the batches of a consolidated table are views into one allocation per column
+  uint64_t* data() const { return (uint64_t*)buf->p + off; }
 };
 struct Batch { std::vector<Col> cols; uint64_t n = 0; };
 using Batches = std::vector<Batch>;
@@ -56,6 +58,11 @@ __global__ void __launch_bounds__(256) gather_pairs_kernel(const uint64_t* __res
                                                            uint64_t n, uint64_t* __restrict__ out) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, st = (uint64_t)gridDim.x * blockDim.x;
   for (; i < n; i += st) out[i] = __ldg(col + ld_stream_u32(pairs + 2 * i + side));
+}
+// out[i] = col[i * stride]: an evenly spaced sample of a column
+__global__ void __launch_bounds__(256) sample_kernel(const uint64_t* __restrict__ col, uint64_t stride, uint64_t m, uint64_t* __restrict__ out) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, st = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < m; i += st) out[i] = col[i * stride];
 }
 static unsigned small_grid(olap_ctx* ctx, uint64_t n) {
   uint64_t g = (n + 255) / 256, cap = (uint64_t)ctx->sm_count * 8;
@@ -100,7 +107,7 @@ static std::string expr_name(const olap_expr* e) {
 }
 
 // value of an expression on one batch: a device column or a broadcast literal
-struct Value { bool is_lit = false; int type = OLAP_I64; uint64_t bits = 0; BufPtr buf; uint64_t* data() const { return (uint64_t*)buf->p; } };
+struct Value { bool is_lit = false; int type = OLAP_I64; uint64_t bits = 0; BufPtr buf; uint64_t off = 0; uint64_t* data() const { return (uint64_t*)buf->p + off; } };
 
 static bool parse_literal(const std::string& s, Value* v) {  // executor.rs:390-401: i64 first, then f64
   if (s.empty()) return false;
@@ -126,8 +133,8 @@ static olap_status materialise(olap_ctx* ctx, const Value& v, uint64_t n, Value*
 static olap_status eval_expr(olap_ctx* ctx, const olap_expr* e, const Batch& b, Value* out) {
   if (e->kind == EXPR_COLUMN) {  // by name first, then by index (executor.rs:381-387)
     for (const Col& c : b.cols)
-      if (c.name == e->text) { out->is_lit = false; out->type = c.type; out->buf = c.buf; return OLAP_OK; }
-    if (e->index < b.cols.size()) { const Col& c = b.cols[e->index]; out->is_lit = false; out->type = c.type; out->buf = c.buf; return OLAP_OK; }
+      if (c.name == e->text) { out->is_lit = false; out->type = c.type; out->buf = c.buf; out->off = c.off; return OLAP_OK; }
+    if (e->index < b.cols.size()) { const Col& c = b.cols[e->index]; out->is_lit = false; out->type = c.type; out->buf = c.buf; out->off = c.off; return OLAP_OK; }
     set_error("Column '%s' not found in batch", e->text.c_str());
     return OLAP_ERR_BAD_ARG;
   }
@@ -190,10 +197,46 @@ static olap_status collect_terms(olap_ctx* ctx, const olap_expr* e, const Batch&
 static olap_status exec(olap_ctx* ctx, const olap_plan* p, Batches* out);
 
 // execute_table_scan, executor.rs:110-155 -- wired to the in-memory catalog instead of returning nothing
+// A table registered batch by batch is moved, the first time it is scanned, into ONE allocation per column; its batches
+// become views (same boundaries, same order).  Operators that need all rows of a column at once (aggregate, join keys) then
+// take a zero-copy view instead of concatenating on every query.
+static olap_status consolidate(olap_ctx* ctx, Batches* t) {
+  if (t->size() < 2) return OLAP_OK;
+  const size_t nc = (*t)[0].cols.size();
+  uint64_t total = 0;
+  bool done = true;
+  for (const Batch& b : *t) {
+    if (b.cols.size() != nc) return OLAP_OK;  // ragged schemas stay as they are
+    for (size_t c = 0; c < nc; c++) done = done && b.cols[c].buf == (*t)[0].cols[c].buf && b.cols[c].off == total;
+    total += b.n;
+  }
+  if (done || total == 0) return OLAP_OK;
+  for (size_t c = 0; c < nc; c++) {
+    BufPtr arena;
+    OLAP_TRY(new_buf(ctx, total * 8, &arena));
+    uint64_t off = 0;
+    for (Batch& b : *t) {
+      if (b.n) OLAP_CUDA(cudaMemcpyAsync((uint64_t*)arena->p + off, b.cols[c].data(), b.n * 8, cudaMemcpyDeviceToDevice, ctx->streams[0]));
+      off += b.n;
+    }
+    OLAP_CUDA(cudaStreamSynchronize(ctx->streams[0]));  // the sources are released below
+    off = 0;
+    for (Batch& b : *t) { b.cols[c].buf = arena; b.cols[c].off = off; off += b.n; }
+  }
+  return OLAP_OK;
+}
+
 static olap_status exec_scan(olap_ctx* ctx, const olap_plan* p, Batches* out) {
   Catalog* cat = catalog_of(ctx);
   Batches src;
-  { std::lock_guard<std::mutex> g(cat->mu); auto it = cat->tables.find(p->table); if (it != cat->tables.end()) src = it->second; }
+  {
+    std::lock_guard<std::mutex> g(cat->mu);
+    auto it = cat->tables.find(p->table);
+    if (it != cat->tables.end()) {
+      OLAP_TRY(consolidate(ctx, &it->second));
+      src = it->second;
+    }
+  }
   auto project = [&](const Batch& b, Batch* o) -> olap_status {
     o->n = b.n;
     if (!p->has_proj) { o->cols = b.cols; return OLAP_OK; }
@@ -247,7 +290,7 @@ static olap_status exec_projection(olap_ctx* ctx, const olap_plan* p, Batches* o
       Value v, m;
       OLAP_TRY(eval_expr(ctx, e, b, &v));
       OLAP_TRY(materialise(ctx, v, b.n, &m));
-      Col c; c.name = expr_name(e); c.type = m.type; c.buf = m.buf;
+      Col c; c.name = expr_name(e); c.type = m.type; c.buf = m.buf; c.off = m.off;
       o.cols.push_back(c);
     }
     out->push_back(o);
@@ -349,14 +392,108 @@ static olap_status upload_scalar(olap_ctx* ctx, uint64_t bits, BufPtr* out) {
 // execute_aggregate, executor.rs:297-355.  No GROUP BY: exactly the reference's execution -- one row, every aggregate
 // emitted as Float64 (:347), identities for empty input (:310-311, :339-345).  GROUP BY: the completion rule of
 // key = first group_by expression as Int64, one row per distinct key, typed aggregates.
+// positions (in the input's column order) of the columns an expression reads, resolved like eval_expr does
+static void referenced_columns(const olap_expr* e, const Batch& b, std::vector<bool>* used) {
+  if (!e) return;
+  if (e->kind == EXPR_BINARY) { referenced_columns(e->l, b, used); referenced_columns(e->r, b, used); return; }
+  if (e->kind != EXPR_COLUMN) return;
+  for (size_t i = 0; i < b.cols.size(); i++)
+    if (b.cols[i].name == e->text) { (*used)[i] = true; return; }
+  if (e->index < b.cols.size()) (*used)[e->index] = true;
+}
+
+// One batch over all input rows holding (only) the columns in `used`; a single input batch is taken as is.
+static olap_status concat_columns(olap_ctx* ctx, const Batches& in, const std::vector<bool>& used, uint64_t total, Batch* all) {
+  if (in.size() == 1) { *all = in[0]; return OLAP_OK; }
+  all->n = total;
+  all->cols.resize(in[0].cols.size());
+  for (size_t c = 0; c < in[0].cols.size(); c++) {
+    all->cols[c].name = in[0].cols[c].name; all->cols[c].type = in[0].cols[c].type;
+    if (!used[c]) continue;
+    bool contiguous = true;  // consolidated catalog tables: consecutive views into one allocation
+    uint64_t next = in[0].cols[c].off;
+    for (const Batch& b : in) {
+      contiguous = contiguous && b.cols.size() == in[0].cols.size() && b.cols[c].buf == in[0].cols[c].buf && b.cols[c].off == next;
+      next += b.n;
+    }
+    if (contiguous) { all->cols[c].buf = in[0].cols[c].buf; all->cols[c].off = in[0].cols[c].off; continue; }
+    OLAP_TRY(new_buf(ctx, std::max<uint64_t>(total, 2) * 8, &all->cols[c].buf));
+    uint64_t off = 0;
+    for (const Batch& b : in) {
+      if (b.cols.size() != in[0].cols.size() || b.cols[c].type != in[0].cols[c].type) { set_error("batches of one input disagree on their schema"); return OLAP_ERR_BAD_ARG; }
+      if (b.n) OLAP_CUDA(cudaMemcpyAsync(all->cols[c].data() + off, b.cols[c].data(), b.n * 8, cudaMemcpyDeviceToDevice, ctx->streams[0]));
+      off += b.n;
+    }
+  }
+  return OLAP_OK;
+}
+
+// Number of groups of a key column, estimated from the distinct keys d among m evenly spaced rows: for G equally likely
+// groups E[d] = G (1 - exp(-m / G)).  The group-by kernels take it as a hint: too low or too high costs speed (a shared
+// table that spills, or L2 atomics where shared memory would do), never correctness.
+static olap_status estimate_groups(olap_ctx* ctx, const uint64_t* keys, uint64_t n, uint64_t* est) {
+  const uint64_t m = std::min<uint64_t>(n, 1u << 20), stride = n / m;
+  BufPtr sk, ok, oa;
+  OLAP_TRY(new_buf(ctx, m * 8, &sk));
+  OLAP_TRY(new_buf(ctx, m * 8, &ok));
+  OLAP_TRY(new_buf(ctx, m * 8, &oa));
+  sample_kernel<<<small_grid(ctx, m), 256, 0, ctx->streams[0]>>>(keys, stride, m, (uint64_t*)sk->p);
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  olap_agg_spec cnt; cnt.values = nullptr; cnt.func = OLAP_COUNT; cnt.value_type = OLAP_I64;
+  uint64_t d = 0;
+  OLAP_TRY(olap_group_by_i64(ctx, (const int64_t*)sk->p, &cnt, 1, m, std::min<uint64_t>(m, 1u << 16), nullptr, 0, (int64_t*)ok->p, oa->p, m, nullptr, &d, nullptr));
+  double g;
+  if (m == n) g = (double)d;                        // the sample is the column
+  else if ((double)d > 0.98 * (double)m) g = (double)n;  // (almost) every sampled key is new: no information beyond "very many"
+  else {
+    double lo = (double)d, hi = (double)n;          // d = G (1 - exp(-m / G)) is increasing in G
+    for (int it = 0; it < 60; it++) {
+      const double mid = 0.5 * (lo + hi), dd = mid * (1.0 - exp(-(double)m / mid));
+      if (dd < (double)d) lo = mid; else hi = mid;
+    }
+    g = hi;
+  }
+  g = g * 1.25 + 16;
+  *est = (uint64_t)std::min<double>((double)n, std::max<double>(g, 64.0));
+  return OLAP_OK;
+}
+
 static olap_status exec_aggregate(olap_ctx* ctx, const olap_plan* p, Batches* out) {
-  Batches in;
-  OLAP_TRY(exec(ctx, p->in, &in));
+  // Aggregate directly over a filter: the conjunction becomes fused filter terms of the group-by kernel, evaluated on the
+  // unfiltered input -- the filter's output columns are never materialised (same rows aggregated, so same result).
+  const olap_plan* src = p->in;
+  const olap_expr* fused = nullptr;
+  if (src->kind == PLAN_FILTER) { fused = src->pred; src = src->in; }
+  Batches raw;
+  OLAP_TRY(exec(ctx, src, &raw));
   uint64_t n = 0;
-  for (const Batch& b : in) n += b.n;
+  for (const Batch& b : raw) n += b.n;
   const int na = (int)p->agg_in.size();
+  std::vector<olap_filter_term> terms; std::vector<Value> keep;
+  Batches in;  // zero or one batch: every input row, only the columns this node reads
+  if (!raw.empty() && n > 0) {
+    std::vector<bool> used(raw[0].cols.size(), false);
+    referenced_columns(fused, raw[0], &used);
+    for (const olap_expr* e : p->agg_in) referenced_columns(e, raw[0], &used);
+    for (const olap_expr* e : p->group_by) referenced_columns(e, raw[0], &used);
+    Batch all;
+    OLAP_TRY(concat_columns(ctx, raw, used, n, &all));
+    if (fused) {
+      OLAP_TRY(collect_terms(ctx, fused, all, &terms, &keep));
+      if (terms.size() > 8) {  // more conjuncts than the kernels fuse: materialise the filter after all
+        terms.clear(); keep.clear(); raw.clear();
+        OLAP_TRY(exec(ctx, p->in, &raw));
+        n = 0;
+        for (const Batch& b : raw) n += b.n;
+        std::vector<bool> every(raw.empty() ? 0 : raw[0].cols.size(), true);
+        if (!raw.empty() && n > 0) { OLAP_TRY(concat_columns(ctx, raw, every, n, &all)); in.push_back(all); }
+      } else in.push_back(all);
+    } else in.push_back(all);
+  }
+  if (in.empty()) n = 0;
   std::vector<Value> vals(na);
-  std::vector<olap_agg_spec> specs(na);
+  std::vector<olap_agg_spec> specs(na + 1);
   std::map<std::string, int> seen;  // identical input expressions are evaluated once (SUM(x), AVG(x), MIN(x) share one column)
   for (int a = 0; a < na; a++) {
     const std::string ename = expr_name(p->agg_in[a]);
@@ -366,31 +503,39 @@ static olap_status exec_aggregate(olap_ctx* ctx, const olap_plan* p, Batches* ou
     else { vals[a].type = OLAP_I64; OLAP_TRY(new_buf(ctx, 16, &vals[a].buf)); }
     specs[a].values = vals[a].data(); specs[a].func = p->agg_funcs[a]; specs[a].value_type = vals[a].type;
   }
+  // one more COUNT: the number of rows that pass the fused filter (the reference's "empty input" cases depend on it)
+  specs[na].values = nullptr; specs[na].func = OLAP_COUNT; specs[na].value_type = OLAP_I64;
   const bool grouped = !p->group_by.empty();
   Value key;
   if (grouped) {
-    if (in.empty() || n == 0) { Batch o; o.n = 0; return OLAP_OK; }  // grouped aggregation of nothing: no rows
+    if (in.empty() || n == 0) return OLAP_OK;  // grouped aggregation of nothing: no rows
     OLAP_TRY(eval_over_batches(ctx, p->group_by[0], in, n, &key));
     if (key.type != OLAP_I64) { set_error("GROUP BY key must be Int64 (aggregate_kernel.rs:48-49)"); return OLAP_ERR_UNSUPPORTED; }
   }
-  uint64_t hint = grouped ? std::min<uint64_t>(n, 1u << 16) : 1, cap = hint, groups = 0;
+  const int ns = na < 16 ? na + 1 : na;  // the kernel seam takes at most 16 aggregates
+  uint64_t hint = 1;
+  if (grouped) OLAP_TRY(estimate_groups(ctx, key.data(), n, &hint));
+  uint64_t cap = hint, groups = 0;
   BufPtr ok, oa;
   for (int attempt = 0; attempt < 2; attempt++) {
     OLAP_TRY(new_buf(ctx, cap * 8, &ok));
-    OLAP_TRY(new_buf(ctx, std::max<uint64_t>(na, 1) * cap * 8, &oa));
-    olap_status st = olap_group_by_i64(ctx, grouped ? (const int64_t*)key.data() : nullptr, specs.data(), na, n, hint, nullptr, 0, (int64_t*)ok->p, oa->p, cap,
-                                       nullptr, &groups, nullptr);
+    OLAP_TRY(new_buf(ctx, (uint64_t)ns * cap * 8, &oa));
+    olap_status st = olap_group_by_i64(ctx, grouped ? (const int64_t*)key.data() : nullptr, specs.data(), ns, n, hint,
+                                       terms.empty() ? nullptr : terms.data(), (int32_t)terms.size(), (int64_t*)ok->p, oa->p, cap, nullptr, &groups, nullptr);
     if (st == OLAP_ERR_CAPACITY && attempt == 0) { cap = hint = groups; continue; }
     OLAP_TRY(st);
     break;
   }
+  if (grouped && groups == 0) return OLAP_OK;  // every row was filtered out: like a filter that drops all its batches
   Batch o; o.n = groups;
   if (grouped) { Col kc; kc.name = expr_name(p->group_by[0]); kc.type = OLAP_I64; kc.buf = ok; o.cols.push_back(kc); }
   std::vector<uint64_t> host;
+  uint64_t passing = n;
   if (!grouped) {
-    host.resize((size_t)std::max(na, 1) * cap);
+    host.resize((size_t)ns * cap);
     OLAP_CUDA(cudaMemcpyAsync(host.data(), oa->p, host.size() * 8, cudaMemcpyDeviceToHost, ctx->streams[0]));
     OLAP_CUDA(cudaStreamSynchronize(ctx->streams[0]));
+    if (ns > na) passing = host[(size_t)na * cap];
   }
   for (int a = 0; a < na; a++) {
     Col c; c.name = std::string(agg_name(p->agg_funcs[a])) + "(" + expr_name(p->agg_in[a]) + ")";
@@ -404,8 +549,8 @@ static olap_status exec_aggregate(olap_ctx* ctx, const olap_plan* p, Batches* ou
       uint64_t bits = host[(size_t)a * cap];
       double d;
       if (is_f) memcpy(&d, &bits, 8); else d = (double)(int64_t)bits;
-      if (n == 0 && f == OLAP_MIN) d = DBL_MAX;    // f64::MAX (executor.rs:310)
-      if (n == 0 && f == OLAP_MAX) d = -DBL_MAX;   // f64::MIN (executor.rs:311)
+      if (passing == 0 && f == OLAP_MIN) d = DBL_MAX;    // f64::MAX (executor.rs:310)
+      if (passing == 0 && f == OLAP_MAX) d = -DBL_MAX;   // f64::MIN (executor.rs:311)
       memcpy(&bits, &d, 8);
       c.type = OLAP_F64;
       OLAP_TRY(upload_scalar(ctx, bits, &c.buf));
