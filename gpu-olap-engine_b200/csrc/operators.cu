@@ -299,24 +299,6 @@ static olap_status exec_projection(olap_ctx* ctx, const olap_plan* p, Batches* o
 }
 
 // all batches of one side as single columns (global row offset across batches, executor.rs:239-253)
-static olap_status concat(olap_ctx* ctx, const Batches& in, Batch* out) {
-  if (in.size() == 1) { *out = in[0]; return OLAP_OK; }
-  uint64_t n = 0;
-  for (const Batch& b : in) n += b.n;
-  out->n = n;
-  if (in.empty()) return OLAP_OK;
-  for (size_t c = 0; c < in[0].cols.size(); c++) {
-    Col o; o.name = in[0].cols[c].name; o.type = in[0].cols[c].type;
-    OLAP_TRY(new_buf(ctx, n * 8, &o.buf));
-    uint64_t off = 0;
-    for (const Batch& b : in) {
-      if (b.n) OLAP_CUDA(cudaMemcpyAsync(o.data() + off, b.cols[c].data(), b.n * 8, cudaMemcpyDeviceToDevice, ctx->streams[0]));
-      off += b.n;
-    }
-    out->cols.push_back(o);
-  }
-  return OLAP_OK;
-}
 
 static olap_status eval_over_batches(olap_ctx* ctx, const olap_expr* e, const Batches& in, uint64_t total, Value* out) {
   if (in.size() == 1) { Value v; OLAP_TRY(eval_expr(ctx, e, in[0], &v)); return materialise(ctx, v, in[0].n, out); }
@@ -337,6 +319,42 @@ static olap_status eval_over_batches(olap_ctx* ctx, const olap_expr* e, const Ba
 }
 
 // execute_hash_join, executor.rs:220-265, with the probe and the output the reference leaves out
+// positions (in the input's column order) of the columns an expression reads, resolved like eval_expr does
+static void referenced_columns(const olap_expr* e, const Batch& b, std::vector<bool>* used) {
+  if (!e) return;
+  if (e->kind == EXPR_BINARY) { referenced_columns(e->l, b, used); referenced_columns(e->r, b, used); return; }
+  if (e->kind != EXPR_COLUMN) return;
+  for (size_t i = 0; i < b.cols.size(); i++)
+    if (b.cols[i].name == e->text) { (*used)[i] = true; return; }
+  if (e->index < b.cols.size()) (*used)[e->index] = true;
+}
+
+// One batch over all input rows holding (only) the columns in `used`; a single input batch is taken as is.
+static olap_status concat_columns(olap_ctx* ctx, const Batches& in, const std::vector<bool>& used, uint64_t total, Batch* all) {
+  if (in.size() == 1) { *all = in[0]; return OLAP_OK; }
+  all->n = total;
+  all->cols.resize(in[0].cols.size());
+  for (size_t c = 0; c < in[0].cols.size(); c++) {
+    all->cols[c].name = in[0].cols[c].name; all->cols[c].type = in[0].cols[c].type;
+    if (!used[c]) continue;
+    bool contiguous = true;  // consolidated catalog tables: consecutive views into one allocation
+    uint64_t next = in[0].cols[c].off;
+    for (const Batch& b : in) {
+      contiguous = contiguous && b.cols.size() == in[0].cols.size() && b.cols[c].buf == in[0].cols[c].buf && b.cols[c].off == next;
+      next += b.n;
+    }
+    if (contiguous) { all->cols[c].buf = in[0].cols[c].buf; all->cols[c].off = in[0].cols[c].off; continue; }
+    OLAP_TRY(new_buf(ctx, std::max<uint64_t>(total, 2) * 8, &all->cols[c].buf));
+    uint64_t off = 0;
+    for (const Batch& b : in) {
+      if (b.cols.size() != in[0].cols.size() || b.cols[c].type != in[0].cols[c].type) { set_error("batches of one input disagree on their schema"); return OLAP_ERR_BAD_ARG; }
+      if (b.n) OLAP_CUDA(cudaMemcpyAsync(all->cols[c].data() + off, b.cols[c].data(), b.n * 8, cudaMemcpyDeviceToDevice, ctx->streams[0]));
+      off += b.n;
+    }
+  }
+  return OLAP_OK;
+}
+
 static olap_status exec_hash_join(olap_ctx* ctx, const olap_plan* p, Batches* out) {
   Batches left, right;
   OLAP_TRY(exec(ctx, p->in, &left));
@@ -347,13 +365,14 @@ static olap_status exec_hash_join(olap_ctx* ctx, const olap_plan* p, Batches* ou
   uint64_t nl = 0, nr = 0;
   for (const Batch& b : left) nl += b.n;
   for (const Batch& b : right) nr += b.n;
+  Batch L, R;  // every column of both sides over all rows (views when the inputs are consolidated tables)
+  OLAP_TRY(concat_columns(ctx, left, std::vector<bool>(left[0].cols.size(), true), nl, &L));
+  OLAP_TRY(concat_columns(ctx, right, std::vector<bool>(right[0].cols.size(), true), nr, &R));
+  L.n = nl; R.n = nr;
   Value lk, rk;  // first key expression of each side only (executor.rs:245)
-  OLAP_TRY(eval_over_batches(ctx, p->lkeys[0], left, nl, &lk));
-  OLAP_TRY(eval_over_batches(ctx, p->rkeys[0], right, nr, &rk));
+  OLAP_TRY(eval_over_batches(ctx, p->lkeys[0], Batches{L}, nl, &lk));
+  OLAP_TRY(eval_over_batches(ctx, p->rkeys[0], Batches{R}, nr, &rk));
   if (lk.type != OLAP_I64 || rk.type != OLAP_I64) { set_error("hash join keys must be Int64 (executor.rs:246)"); return OLAP_ERR_UNSUPPORTED; }
-  Batch L, R;
-  OLAP_TRY(concat(ctx, left, &L));
-  OLAP_TRY(concat(ctx, right, &R));
   uint64_t cap = std::max<uint64_t>(nr, 1), count = 0;
   BufPtr pairs;
   for (int attempt = 0; attempt < 2; attempt++) {
@@ -392,42 +411,6 @@ static olap_status upload_scalar(olap_ctx* ctx, uint64_t bits, BufPtr* out) {
 // execute_aggregate, executor.rs:297-355.  No GROUP BY: exactly the reference's execution -- one row, every aggregate
 // emitted as Float64 (:347), identities for empty input (:310-311, :339-345).  GROUP BY: the completion rule of
 // key = first group_by expression as Int64, one row per distinct key, typed aggregates.
-// positions (in the input's column order) of the columns an expression reads, resolved like eval_expr does
-static void referenced_columns(const olap_expr* e, const Batch& b, std::vector<bool>* used) {
-  if (!e) return;
-  if (e->kind == EXPR_BINARY) { referenced_columns(e->l, b, used); referenced_columns(e->r, b, used); return; }
-  if (e->kind != EXPR_COLUMN) return;
-  for (size_t i = 0; i < b.cols.size(); i++)
-    if (b.cols[i].name == e->text) { (*used)[i] = true; return; }
-  if (e->index < b.cols.size()) (*used)[e->index] = true;
-}
-
-// One batch over all input rows holding (only) the columns in `used`; a single input batch is taken as is.
-static olap_status concat_columns(olap_ctx* ctx, const Batches& in, const std::vector<bool>& used, uint64_t total, Batch* all) {
-  if (in.size() == 1) { *all = in[0]; return OLAP_OK; }
-  all->n = total;
-  all->cols.resize(in[0].cols.size());
-  for (size_t c = 0; c < in[0].cols.size(); c++) {
-    all->cols[c].name = in[0].cols[c].name; all->cols[c].type = in[0].cols[c].type;
-    if (!used[c]) continue;
-    bool contiguous = true;  // consolidated catalog tables: consecutive views into one allocation
-    uint64_t next = in[0].cols[c].off;
-    for (const Batch& b : in) {
-      contiguous = contiguous && b.cols.size() == in[0].cols.size() && b.cols[c].buf == in[0].cols[c].buf && b.cols[c].off == next;
-      next += b.n;
-    }
-    if (contiguous) { all->cols[c].buf = in[0].cols[c].buf; all->cols[c].off = in[0].cols[c].off; continue; }
-    OLAP_TRY(new_buf(ctx, std::max<uint64_t>(total, 2) * 8, &all->cols[c].buf));
-    uint64_t off = 0;
-    for (const Batch& b : in) {
-      if (b.cols.size() != in[0].cols.size() || b.cols[c].type != in[0].cols[c].type) { set_error("batches of one input disagree on their schema"); return OLAP_ERR_BAD_ARG; }
-      if (b.n) OLAP_CUDA(cudaMemcpyAsync(all->cols[c].data() + off, b.cols[c].data(), b.n * 8, cudaMemcpyDeviceToDevice, ctx->streams[0]));
-      off += b.n;
-    }
-  }
-  return OLAP_OK;
-}
-
 // Number of groups of a key column, estimated from the distinct keys d among m evenly spaced rows: for G equally likely
 // groups E[d] = G (1 - exp(-m / G)).  The group-by kernels take it as a hint: too low or too high costs speed (a shared
 // table that spills, or L2 atomics where shared memory would do), never correctness.
