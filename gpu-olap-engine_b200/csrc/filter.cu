@@ -22,75 +22,6 @@ struct CompactCols {
   int n;
 };
 
-// The comparison operator is dispatched once per 4 (or 8) rows, not per row: the switch sits outside the row loop.
-template <class T, int N>
-__device__ __forceinline__ void and_cmp(int op, const T (&l)[N], const T (&r)[N], bool (&f)[N]) {
-  switch (op) {
-    case OLAP_EQ:
-#pragma unroll
-      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] == r[i];
-      break;
-    case OLAP_NE:
-#pragma unroll
-      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] != r[i];
-      break;
-    case OLAP_LT:
-#pragma unroll
-      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] < r[i];
-      break;
-    case OLAP_LE:
-#pragma unroll
-      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] <= r[i];
-      break;
-    case OLAP_GT:
-#pragma unroll
-      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] > r[i];
-      break;
-    case OLAP_GE:
-#pragma unroll
-      for (int i = 0; i < N; i++) f[i] = f[i] && l[i] >= r[i];
-      break;
-    default:  // executor.rs:464: an unknown operator matches no row
-#pragma unroll
-      for (int i = 0; i < N; i++) f[i] = false;
-  }
-}
-
-// evaluates the conjunction on the 4 consecutive rows starting at row0 (a multiple of 4); rows >= n never pass
-template <bool VEC>
-__device__ __forceinline__ void eval_quad(const TermPack& terms, uint64_t row0, uint64_t n, bool (&f)[4]) {
-#pragma unroll
-  for (int e = 0; e < 4; e++) f[e] = row0 + e < n;
-#pragma unroll 1
-  for (int k = 0; k < terms.n; k++) {
-    uint64_t l[4], r[4];
-    if (VEC && row0 + 3 < n) {
-      const u64x4 a = ld_stream_u64x4(terms.lhs[k] + row0);
-      l[0] = a.a; l[1] = a.b; l[2] = a.c; l[3] = a.d;
-      if (terms.rhs[k]) { const u64x4 b = ld_stream_u64x4(terms.rhs[k] + row0); r[0] = b.a; r[1] = b.b; r[2] = b.c; r[3] = b.d; }
-      else { r[0] = r[1] = r[2] = r[3] = (uint64_t)terms.lit[k]; }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const bool in = row0 + e < n;
-        l[e] = in ? ld_stream_u64(terms.lhs[k] + row0 + e) : 0;
-        r[e] = (in && terms.rhs[k]) ? ld_stream_u64(terms.rhs[k] + row0 + e) : (uint64_t)terms.lit[k];
-      }
-    }
-    if (terms.type[k] == OLAP_F64) {
-      double dl[4], dr[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) { dl[e] = __longlong_as_double((long long)l[e]); dr[e] = __longlong_as_double((long long)r[e]); }
-      and_cmp<double, 4>(terms.op[k], dl, dr, f);
-    } else {
-      long long il[4], ir[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) { il[e] = (long long)l[e]; ir[e] = (long long)r[e]; }
-      and_cmp<long long, 4>(terms.op[k], il, ir, f);
-    }
-  }
-}
-
 __device__ __forceinline__ void store_mask4(uint8_t* out_mask, uint64_t row0, uint64_t n, const bool (&f)[4]) {
   if (row0 + 3 < n && ((uintptr_t)(out_mask + row0) & 3) == 0)
     *reinterpret_cast<uint32_t*>(out_mask + row0) = (uint32_t)f[0] | ((uint32_t)f[1] << 8) | ((uint32_t)f[2] << 16) | ((uint32_t)f[3] << 24);

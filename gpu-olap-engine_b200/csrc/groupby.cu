@@ -52,6 +52,7 @@ struct GbParams {
   uint64_t g_cap;     // power of two
   uint32_t* g_overflow;
   bool vec;           // keys and value columns are 32-byte aligned: 256-bit loads
+  bool terms_vec;     // so are the fused filter's columns
   // shared-memory tables
   uint32_t s_slots;   // power of two, per copy
   uint32_t s_copies;  // power of two
@@ -324,10 +325,11 @@ __device__ __forceinline__ void load_rows(const GbParams& p, uint64_t row0, uint
       for (int q = 0; q < NV; q++) v[j][q] = (pass[j] && q < p.n_vcols) ? ld_stream_u64(p.vcol[q] + row) : 0;
     }
   }
-  if (p.terms.n) {
+  if (p.terms.n) {  // the fused filter: 256-bit loads of the predicate columns, operator switch once per four rows
+    bool f[4];
+    if (p.terms_vec) eval_quad<true>(p.terms, row0, end, f); else eval_quad<false>(p.terms, row0, end, f);
 #pragma unroll
-    for (int j = 0; j < kGbRows; j++)
-      if (pass[j]) pass[j] = eval_terms_row(p.terms, row0 + j);
+    for (int j = 0; j < kGbRows; j++) pass[j] = pass[j] && f[j];
   }
 }
 
@@ -896,6 +898,9 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
   p.n = n_rows;
   p.vec = (((uintptr_t)keys) & 31) == 0;
   for (int q = 0; q < p.n_vcols; q++) p.vec = p.vec && (((uintptr_t)p.vcol[q]) & 31) == 0;
+  p.terms_vec = true;
+  for (int k = 0; k < p.terms.n; k++)
+    p.terms_vec = p.terms_vec && (((uintptr_t)p.terms.lhs[k]) & 31) == 0 && (!p.terms.rhs[k] || (((uintptr_t)p.terms.rhs[k]) & 31) == 0);
   if (!keys) n_groups_hint = 1;
   if (n_groups_hint < 1) n_groups_hint = 1;
 

@@ -52,6 +52,7 @@ struct PartArgs {
   uint64_t* pay_out[kMaxPay];
   TermPack terms;                        // rows failing the conjunction are dropped (fused filter for group-by)
   bool vec;                              // keys are 32-byte aligned: 256-bit loads
+  bool terms_vec;                        // so are the fused filter's columns
 };
 
 // Partition hash: one multiply (Fibonacci hashing of the folded key) for the local radix pass -- the full mix64 cost ~20 of
@@ -70,9 +71,11 @@ __device__ __forceinline__ void load_keys4(const PartArgs& a, uint64_t i, uint64
 #pragma unroll
     for (int e = 0; e < 4; e++) { ok[e] = i + e < end; k[e] = ok[e] ? ld_stream_u64(a.keys + i + e) : 0; }
   }
-  if (a.terms.n) {
+  if (a.terms.n) {  // fused filter of the partitioned group-by
+    bool f[4];
+    if (a.terms_vec) eval_quad<true>(a.terms, i, end, f); else eval_quad<false>(a.terms, i, end, f);
 #pragma unroll
-    for (int e = 0; e < 4; e++) if (ok[e]) ok[e] = eval_terms_row(a.terms, i + e);
+    for (int e = 0; e < 4; e++) ok[e] = ok[e] && f[e];
   }
 }
 
@@ -988,6 +991,8 @@ olap_status group_by_partition_rows(olap_ctx* ctx, const uint64_t* keys, uint64_
   PartArgs a;
   memset(&a, 0, sizeof(a));
   a.bits = bits; a.keys = keys; a.n = n; a.out_keys = out_keys; a.terms = terms;
+  a.terms_vec = true;
+  for (int k = 0; k < terms.n; k++) a.terms_vec = a.terms_vec && aligned32(terms.lhs[k]) && (!terms.rhs[k] || aligned32(terms.rhs[k]));
   for (int q = 0; q < n_vcols; q++) { a.pay_in[q] = vcols[q]; a.pay_out[q] = out_vcols[q]; }
   const uint64_t cap = alloc_capacity(n, P);
   if (env_u64("OLAP_GB_ALLOC", 1) && (uint64_t)P * cap < 0xFFFFFFFFULL) {
