@@ -26,7 +26,7 @@ def main():
         gb = O.gen_uniform_i64(nb * world, 11, dom); gp = O.gen_uniform_i64(npb * world, 12, dom)
         sj = sharded.ShardedJoin(ops)
         res = sj.join(torch.from_numpy(gb[rank * nb:(rank + 1) * nb].copy()).to(dev), nb,
-                      torch.from_numpy(gp[rank * npb:(rank + 1) * npb].copy()).to(dev), npb, max_matches=max(4 * npb, 16))
+                      torch.from_numpy(gp[rank * npb:(rank + 1) * npb].copy()).to(dev), npb, max_matches=max(4 * npb * world, 16))   # matches per probe row grow with the world size (fixed key domain)
         pairs = sharded.ShardedJoin.global_pairs(res, [r * nb for r in range(world)], [r * npb for r in range(world)]).cpu().numpy()
         gathered = [None] * world
         dist.all_gather_object(gathered, pairs)
