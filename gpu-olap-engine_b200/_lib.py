@@ -66,6 +66,7 @@ SIGNATURES = {
     "olap_shuffle_count_i64": (i32, [vp, vp, u64, i32, vp, vp, vp]),
     "olap_shuffle_scatter_i64": (i32, [vp, vp, u64, i32, vp, vp, vp, vp, vp]),
     "olap_group_by_i64": (i32, [vp, vp, C.POINTER(AggSpec), i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
+    "olap_group_by_prog_i64": (i32, [vp, vp, C.POINTER(AggSpec), vp, i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_agg_identity": (i64, [i32]),
     "olap_compute_launch_params": (None, [u64, C.POINTER(u32), C.POINTER(u32)]),
     "olap_expr_column": (vp, [u64, C.c_char_p]),

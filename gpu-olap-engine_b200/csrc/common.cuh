@@ -260,4 +260,73 @@ __device__ __forceinline__ void eval_quad(const TermPack& terms, uint64_t row0, 
 
 olap_status pack_terms(const olap_filter_term* terms, int32_t n_terms, TermPack* out);
 
+
+// eval_binary_expr (gpu-olap-core/src/executor.rs:411-441): i64 arithmetic wraps, x / 0 = 0, any other operator yields 0;
+// f64 is this core's extension (IEEE)
+__device__ __forceinline__ int64_t binop_i64(int64_t a, int64_t b, char op) {
+  switch (op) {
+    case '+': return (int64_t)((uint64_t)a + (uint64_t)b);
+    case '-': return (int64_t)((uint64_t)a - (uint64_t)b);
+    case '*': return (int64_t)((uint64_t)a * (uint64_t)b);
+    case '/': return b == 0 ? 0 : ((a == INT64_MIN && b == -1) ? INT64_MIN : a / b);
+    default: return 0;
+  }
+}
+__device__ __forceinline__ double binop_f64(double a, double b, char op) {
+  switch (op) {
+    case '+': return a + b;
+    case '-': return a - b;
+    case '*': return a * b;
+    case '/': return a / b;
+    default: return 0.0;
+  }
+}
+
+
+// A value column computed on the fly: arithmetic over 8-byte columns and literals of ONE type in reverse Polish notation,
+// stack depth <= 3 (olap_expr_prog).  Lets the group-by kernels aggregate SUM(price * (1 - discount)) without the
+// projection passes that would materialise every temporary as a column.
+constexpr int kMaxProgOps = OLAP_PROG_MAX_OPS;
+struct ExprProg {
+  int8_t n;                        // 0: the value column is read from memory
+  int8_t f64;
+  int8_t op[kMaxProgOps];          // 'c' push column, 'l' push literal, '+' '-' '*' '/'
+  const uint64_t* col[kMaxProgOps];
+  uint64_t lit[kMaxProgOps];
+};
+
+// the program's value for the four consecutive rows starting at row0 (dead rows get an unspecified value)
+template <bool VEC>
+__device__ __forceinline__ void eval_prog4(const ExprProg& g, uint64_t row0, uint64_t begin, uint64_t end, uint64_t (&out)[4]) {
+  uint64_t s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  const bool whole = VEC && row0 >= begin && row0 + 3 < end;
+#pragma unroll 1
+  for (int k = 0; k < g.n; k++) {
+    const int op = g.op[k];
+    if (op == 'c' || op == 'l') {
+#pragma unroll
+      for (int e = 0; e < 4; e++) { s2[e] = s1[e]; s1[e] = s0[e]; }
+      if (op == 'l') { s0[0] = s0[1] = s0[2] = s0[3] = g.lit[k]; }
+      else if (whole) { const u64x4 v = ld_stream_u64x4(g.col[k] + row0); s0[0] = v.a; s0[1] = v.b; s0[2] = v.c; s0[3] = v.d; }
+      else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) s0[e] = (row0 + e >= begin && row0 + e < end) ? ld_stream_u64(g.col[k] + row0 + e) : 0;
+      }
+    } else {
+      if (g.f64) {
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+          s0[e] = (uint64_t)__double_as_longlong(binop_f64(__longlong_as_double((long long)s1[e]), __longlong_as_double((long long)s0[e]), (char)op));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) s0[e] = (uint64_t)binop_i64((int64_t)s1[e], (int64_t)s0[e], (char)op);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) s1[e] = s2[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; e++) out[e] = s0[e];
+}
+
 }  // namespace olap

@@ -212,25 +212,6 @@ __global__ void __launch_bounds__(256) gather_kernel(const uint64_t* __restrict_
   for (; i < n; i += stride) out[i] = __ldg(col + ld_stream_u32(sel + i));
 }
 
-__device__ __forceinline__ int64_t binop_i64(int64_t a, int64_t b, char op) {
-  switch (op) {
-    case '+': return (int64_t)((uint64_t)a + (uint64_t)b);
-    case '-': return (int64_t)((uint64_t)a - (uint64_t)b);
-    case '*': return (int64_t)((uint64_t)a * (uint64_t)b);
-    case '/': return b == 0 ? 0 : ((a == INT64_MIN && b == -1) ? INT64_MIN : a / b);
-    default: return 0;
-  }
-}
-__device__ __forceinline__ double binop_f64(double a, double b, char op) {
-  switch (op) {
-    case '+': return a + b;
-    case '-': return a - b;
-    case '*': return a * b;
-    case '/': return a / b;
-    default: return 0.0;
-  }
-}
-
 template <bool F64>
 __global__ void __launch_bounds__(256) project_kernel(const uint64_t* __restrict__ lhs, const uint64_t* __restrict__ rhs, uint64_t lit,
                                                       char op, uint64_t n, uint64_t* __restrict__ out, bool vec) {

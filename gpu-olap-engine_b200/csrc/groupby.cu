@@ -42,6 +42,8 @@ struct GbParams {
   TermPack terms;
   int n_vcols;                             // distinct value columns, each loaded once per row
   const uint64_t* vcol[kMaxVcols];
+  ExprProg prog[kMaxVcols];                // prog[q].n > 0: value column q is computed, not loaded
+  bool prog_vec;                           // the programs' columns are 32-byte aligned
   int n_cells;
   int8_t cell_op[kMaxCells];
   int8_t cell_vcol[kMaxCells];
@@ -303,14 +305,14 @@ constexpr int kGbRows = 4;  // rows per thread per iteration: all of their loads
 // loads the keys and the distinct value columns of this thread's kGbRows CONSECUTIVE rows (row0 is a multiple of 4, so
 // one 256-bit evict-first load per column when the columns are 32-byte aligned), masks rows outside [begin, end), applies
 // the filter
-template <int NV, bool KEYED>
+template <int NV, bool KEYED, bool PROG = false>
 __device__ __forceinline__ void load_rows(const GbParams& p, uint64_t row0, uint64_t begin, uint64_t end, uint64_t (&key)[kGbRows],
                                           uint64_t (&v)[kGbRows][NV], bool (&pass)[kGbRows]) {
   if (p.vec && row0 >= begin && row0 + 3 < end) {
     if (KEYED) { const u64x4 k = ld_stream_u64x4(p.keys + row0); key[0] = k.a; key[1] = k.b; key[2] = k.c; key[3] = k.d; }
 #pragma unroll
     for (int q = 0; q < NV; q++) {
-      if (q < p.n_vcols) { const u64x4 x = ld_stream_u64x4(p.vcol[q] + row0); v[0][q] = x.a; v[1][q] = x.b; v[2][q] = x.c; v[3][q] = x.d; }
+      if (q < p.n_vcols && (!PROG || p.prog[q].n == 0)) { const u64x4 x = ld_stream_u64x4(p.vcol[q] + row0); v[0][q] = x.a; v[1][q] = x.b; v[2][q] = x.c; v[3][q] = x.d; }
       else { v[0][q] = v[1][q] = v[2][q] = v[3][q] = 0; }
     }
 #pragma unroll
@@ -322,9 +324,17 @@ __device__ __forceinline__ void load_rows(const GbParams& p, uint64_t row0, uint
       pass[j] = row >= begin && row < end;
       key[j] = (KEYED && pass[j]) ? ld_stream_u64(p.keys + row) : 0;
 #pragma unroll
-      for (int q = 0; q < NV; q++) v[j][q] = (pass[j] && q < p.n_vcols) ? ld_stream_u64(p.vcol[q] + row) : 0;
+      for (int q = 0; q < NV; q++) v[j][q] = (pass[j] && q < p.n_vcols && (!PROG || p.prog[q].n == 0)) ? ld_stream_u64(p.vcol[q] + row) : 0;
     }
   }
+#pragma unroll
+  for (int q = 0; q < NV; q++)
+    if (PROG && q < p.n_vcols && p.prog[q].n) {  // computed value column: evaluate its program on these four rows
+      uint64_t r[4];
+      if (p.prog_vec) eval_prog4<true>(p.prog[q], row0, begin, end, r); else eval_prog4<false>(p.prog[q], row0, begin, end, r);
+#pragma unroll
+      for (int j = 0; j < kGbRows; j++) v[j][q] = r[j];
+    }
   if (p.terms.n) {  // the fused filter: 256-bit loads of the predicate columns, operator switch once per four rows
     bool f[4];
     if (p.terms_vec) eval_quad<true>(p.terms, row0, end, f); else eval_quad<false>(p.terms, row0, end, f);
@@ -342,7 +352,7 @@ struct AllAcc {
   uint64_t add_i[NV]; double add_f[NV]; long long min_i[NV], max_i[NV], min_f[NV], max_f[NV];
 };
 
-template <int NV>
+template <int NV, bool PROG = false>
 __global__ void __launch_bounds__(kGbThreads) gb_nokey_kernel(GbParams p) {
   AllAcc<NV> a;
 #pragma unroll
@@ -358,7 +368,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_nokey_kernel(GbParams p) {
     uint64_t key[U][kGbRows], v[U][kGbRows][NV];
     bool pass[U][kGbRows];
 #pragma unroll
-    for (int u = 0; u < U; u++) load_rows<NV, false>(p, base + u * tile + (uint64_t)threadIdx.x * kGbRows, 0, p.n, key[u], v[u], pass[u]);
+    for (int u = 0; u < U; u++) load_rows<NV, false, PROG>(p, base + u * tile + (uint64_t)threadIdx.x * kGbRows, 0, p.n, key[u], v[u], pass[u]);
 #pragma unroll
     for (int u = 0; u < U; u++)
 #pragma unroll
@@ -431,13 +441,13 @@ __global__ void __launch_bounds__(kGbThreads) gb_nokey_kernel(GbParams p) {
 
 // ------------------------------------------------------------------------------------------- global regime
 // begin/end: row range (whole input, or one partition of the partitioned copies)
-template <int NV>
+template <int NV, bool PROG = false>
 __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(GbParams p, uint64_t begin, uint64_t end) {
   const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
   for (uint64_t base = (begin & ~3ULL) + blockIdx.x * tile; base < end; base += (uint64_t)gridDim.x * tile) {
     uint64_t key[kGbRows], v[kGbRows][NV];
     bool pass[kGbRows];
-    load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, begin, end, key, v, pass);
+    load_rows<NV, true, PROG>(p, base + (uint64_t)threadIdx.x * kGbRows, begin, end, key, v, pass);
     global_update_rows<NV>(p, key, v, pass);
   }
 }
@@ -605,7 +615,7 @@ __device__ __forceinline__ void smem_merge_slot(const GbParams& p, const SmemTab
   for (int c = 0; c < p.n_cells; c++) cell_atomic_shared(p.cell_op[c], t.cells + (uint64_t)c * t.total + slot, t.cells[(uint64_t)c * t.total + src]);
 }
 
-template <int NV>
+template <int NV, bool PROG = false>
 __global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SmemTable t = smem_table(p, smem_raw);
@@ -617,7 +627,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
   uint64_t nkey[kGbRows], nv[kGbRows][NV];
   bool npass[kGbRows];
   uint64_t base = blockIdx.x * tile;
-  if (base < p.n) load_rows<NV, true>(p, base + (uint64_t)threadIdx.x * kGbRows, 0, p.n, nkey, nv, npass);
+  if (base < p.n) load_rows<NV, true, PROG>(p, base + (uint64_t)threadIdx.x * kGbRows, 0, p.n, nkey, nv, npass);
   for (; base < p.n; base += stride) {
     uint64_t key[kGbRows], v[kGbRows][NV];
     bool pass[kGbRows];
@@ -627,7 +637,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_shared_kernel(GbParams p) {
 #pragma unroll
       for (int q = 0; q < NV; q++) v[j][q] = nv[j][q];
     }
-    if (base + stride < p.n) load_rows<NV, true>(p, base + stride + (uint64_t)threadIdx.x * kGbRows, 0, p.n, nkey, nv, npass);
+    if (base + stride < p.n) load_rows<NV, true, PROG>(p, base + stride + (uint64_t)threadIdx.x * kGbRows, 0, p.n, nkey, nv, npass);
     smem_update_rows<NV>(p, t, copy_base, key, v, pass, nullptr);
   }
   __syncthreads();
@@ -757,7 +767,7 @@ __global__ void __launch_bounds__(256) gb_extract_kernel(GbParams p, bool emit_e
 }
 
 // ------------------------------------------------------------------------------------------- host driver
-static olap_status build_cells(const olap_agg_spec* specs, int n_aggs, GbParams* p) {
+static olap_status build_cells(const olap_agg_spec* specs, const olap_expr_prog* const* progs, int n_aggs, GbParams* p) {
   OLAP_REQUIRE(n_aggs >= 0 && n_aggs <= 16, "n_aggs must be in [0, 16]");
   OutSpec* o = &p->out;
   p->n_cells = 0; p->n_vcols = 0;
@@ -768,13 +778,31 @@ static olap_status build_cells(const olap_agg_spec* specs, int n_aggs, GbParams*
     OLAP_REQUIRE(t == OLAP_I64 || t == OLAP_F64, "value_type must be OLAP_I64 or OLAP_F64");
     o->func[a] = (int8_t)f; o->type[a] = (int8_t)t; o->cell[a] = -1;
     if (f == OLAP_COUNT) continue;
-    OLAP_REQUIRE(specs[a].values, "aggregate value column is NULL");
+    const olap_expr_prog* g = progs ? progs[a] : nullptr;
+    // a value column is identified by its buffer, or by its program object when it is computed
+    const uint64_t* id = g ? (const uint64_t*)g : (const uint64_t*)specs[a].values;
+    OLAP_REQUIRE(id, "aggregate value column is NULL");
     int vc = -1;
-    for (int q = 0; q < p->n_vcols; q++) if (p->vcol[q] == (const uint64_t*)specs[a].values) vc = q;
+    for (int q = 0; q < p->n_vcols; q++) if (p->vcol[q] == id) vc = q;
     if (vc < 0) {
       OLAP_REQUIRE(p->n_vcols < kMaxVcols, "more than 6 distinct value columns in one aggregation");
       vc = p->n_vcols++;
-      p->vcol[vc] = (const uint64_t*)specs[a].values;
+      p->vcol[vc] = id;
+      if (g) {
+        OLAP_REQUIRE(g->n_ops >= 1 && g->n_ops <= kMaxProgOps, "expression program: 1..OLAP_PROG_MAX_OPS entries");
+        ExprProg& e = p->prog[vc];
+        e.n = (int8_t)g->n_ops; e.f64 = t == OLAP_F64;
+        int depth = 0;
+        for (int k = 0; k < g->n_ops; k++) {
+          const int op = g->op[k];
+          e.op[k] = (int8_t)op; e.col[k] = (const uint64_t*)g->column[k]; e.lit[k] = (uint64_t)g->literal_bits[k];
+          if (op == 'c') { OLAP_REQUIRE(g->column[k], "expression program: NULL column"); depth++; }
+          else if (op == 'l') depth++;
+          else { OLAP_REQUIRE(op == '+' || op == '-' || op == '*' || op == '/', "expression program: unknown op"); OLAP_REQUIRE(depth >= 2, "expression program: stack underflow"); depth--; }
+          OLAP_REQUIRE(depth <= 3, "expression program: stack depth > 3");
+        }
+        OLAP_REQUIRE(depth == 1, "expression program must leave exactly one value");
+      }
     }
     const int8_t op = (f == OLAP_SUM || f == OLAP_AVG) ? (t == OLAP_F64 ? ADD_F64 : ADD_I64)
                       : f == OLAP_MIN ? (t == OLAP_F64 ? MIN_F64 : MIN_I64) : (t == OLAP_F64 ? MAX_F64 : MAX_I64);
@@ -878,10 +906,9 @@ static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups
 
 using namespace olap;
 
-extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, const olap_agg_spec* specs, int32_t n_aggs, uint64_t n_rows,
-                                         uint64_t n_groups_hint, const olap_filter_term* terms, int32_t n_terms, int64_t* out_keys,
-                                         void* out_aggs, uint64_t out_capacity, uint64_t* out_n_groups_dptr, uint64_t* host_n_groups,
-                                         void* stream) {
+static olap_status group_by_impl(olap_ctx* ctx, const int64_t* keys, const olap_agg_spec* specs, const olap_expr_prog* const* progs, int32_t n_aggs,
+                                 uint64_t n_rows, uint64_t n_groups_hint, const olap_filter_term* terms, int32_t n_terms, int64_t* out_keys,
+                                 void* out_aggs, uint64_t out_capacity, uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream) {
   OLAP_REQUIRE(ctx, "ctx is NULL");
   OLAP_REQUIRE(n_aggs == 0 || specs, "specs is NULL");
   OLAP_REQUIRE(out_capacity == 0 || (out_keys && (n_aggs == 0 || out_aggs)), "output pointer is NULL");
@@ -892,12 +919,19 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
 
   GbParams p;
   memset(&p, 0, sizeof(p));
-  OLAP_TRY(build_cells(specs, n_aggs, &p));
+  OLAP_TRY(build_cells(specs, progs, n_aggs, &p));
   OLAP_TRY(pack_terms(terms, n_terms, &p.terms));
   p.keys = (const uint64_t*)keys;
   p.n = n_rows;
   p.vec = (((uintptr_t)keys) & 31) == 0;
-  for (int q = 0; q < p.n_vcols; q++) p.vec = p.vec && (((uintptr_t)p.vcol[q]) & 31) == 0;
+  bool any_prog = false;
+  p.prog_vec = true;
+  for (int q = 0; q < p.n_vcols; q++) {
+    if (p.prog[q].n == 0) { p.vec = p.vec && (((uintptr_t)p.vcol[q]) & 31) == 0; continue; }
+    any_prog = true;
+    for (int k = 0; k < p.prog[q].n; k++)
+      if (p.prog[q].op[k] == 'c') p.prog_vec = p.prog_vec && (((uintptr_t)p.prog[q].col[k]) & 31) == 0;
+  }
   p.terms_vec = true;
   for (int k = 0; k < p.terms.n; k++)
     p.terms_vec = p.terms_vec && (((uintptr_t)p.terms.lhs[k]) & 31) == 0 && (!p.terms.rhs[k] || (((uintptr_t)p.terms.rhs[k]) & 31) == 0);
@@ -924,6 +958,11 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
     if (need < 16) need = 16;
     const bool shared = keys && attempt == 0 && (need + 1) * sbytes + 16 <= budget;
     const bool partitioned = keys && attempt == 0 && !shared && n_rows >= (1u << 20) && p.n_vcols <= 4;  // the partitioner carries <= 4 payload columns
+    if (any_prog && partitioned) {
+      set_error("computed aggregate inputs are fused in the no-key / shared / global regimes only; materialise them for %llu groups",
+                (unsigned long long)n_groups_hint);
+      return OLAP_ERR_UNSUPPORTED;
+    }
     // global table: the spill target of the shared/partitioned regimes (small), or the whole table
     uint64_t gh = (shared || partitioned) ? std::min<uint64_t>(n_groups_hint, 4096) : n_groups_hint;
     p.g_cap = keys ? pow2_at_least(std::max<uint64_t>(2 * gh, 1024)) : 1;
@@ -939,22 +978,31 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
     phase_mark(ctx, s, "init");
     if (n_rows > 0) {
       if (!keys) {
-        GB_DISPATCH_NV(p.n_vcols, (gb_nokey_kernel<NV><<<capped_grid((tiles + 1) / 2, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p)));
+        if (any_prog) { GB_DISPATCH_NV(p.n_vcols, (gb_nokey_kernel<NV, true><<<capped_grid((tiles + 1) / 2, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p))); }
+        else { GB_DISPATCH_NV(p.n_vcols, (gb_nokey_kernel<NV><<<capped_grid((tiles + 1) / 2, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p))); }
         count_launch(ctx);
       } else if (shared) {
         uint64_t copies = 1;
         while (copies < 64 && (need + 1) * sbytes * copies * 2 + 16 <= budget) copies <<= 1;
         p.s_slots = (uint32_t)need; p.s_copies = (uint32_t)copies; p.s_hskip = 0; p.s_hshift = 64 - ilog2_u64(need);
         const size_t smem = (size_t)((need + 1) * copies * sbytes + 16);
-        GB_DISPATCH_NV(p.n_vcols, {
-          OLAP_CUDA(cudaFuncSetAttribute(gb_shared_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          gb_shared_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 2), kGbThreads, smem, s>>>(p);
-        });
+        if (any_prog) {
+          GB_DISPATCH_NV(p.n_vcols, {
+            OLAP_CUDA((cudaFuncSetAttribute(gb_shared_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+            gb_shared_kernel<NV, true><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 2), kGbThreads, smem, s>>>(p);
+          });
+        } else {
+          GB_DISPATCH_NV(p.n_vcols, {
+            OLAP_CUDA(cudaFuncSetAttribute(gb_shared_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gb_shared_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 2), kGbThreads, smem, s>>>(p);
+          });
+        }
         count_launch(ctx);
       } else if (partitioned) {
         OLAP_TRY(run_partitioned(ctx, p, n_groups_hint, tsc, s));
       } else {
-        GB_DISPATCH_NV(p.n_vcols, (gb_global_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p, 0, n_rows)));
+        if (any_prog) { GB_DISPATCH_NV(p.n_vcols, (gb_global_kernel<NV, true><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p, 0, n_rows))); }
+        else { GB_DISPATCH_NV(p.n_vcols, (gb_global_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 4), kGbThreads, 0, s>>>(p, 0, n_rows))); }
         count_launch(ctx);
       }
       OLAP_CUDA(cudaGetLastError());
@@ -982,4 +1030,20 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
     return OLAP_ERR_CAPACITY;
   }
   return OLAP_OK;
+}
+
+extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, const olap_agg_spec* specs, int32_t n_aggs, uint64_t n_rows,
+                                         uint64_t n_groups_hint, const olap_filter_term* terms, int32_t n_terms, int64_t* out_keys,
+                                         void* out_aggs, uint64_t out_capacity, uint64_t* out_n_groups_dptr, uint64_t* host_n_groups,
+                                         void* stream) {
+  return group_by_impl(ctx, keys, specs, nullptr, n_aggs, n_rows, n_groups_hint, terms, n_terms, out_keys, out_aggs, out_capacity,
+                       out_n_groups_dptr, host_n_groups, stream);
+}
+
+extern "C" olap_status olap_group_by_prog_i64(olap_ctx* ctx, const int64_t* keys, const olap_agg_spec* specs, const olap_expr_prog* const* progs,
+                                              int32_t n_aggs, uint64_t n_rows, uint64_t n_groups_hint, const olap_filter_term* terms,
+                                              int32_t n_terms, int64_t* out_keys, void* out_aggs, uint64_t out_capacity,
+                                              uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream) {
+  return group_by_impl(ctx, keys, specs, progs, n_aggs, n_rows, n_groups_hint, terms, n_terms, out_keys, out_aggs, out_capacity,
+                       out_n_groups_dptr, host_n_groups, stream);
 }

@@ -7,6 +7,7 @@
 #include <cerrno>
 #include <cfloat>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <cmath>
 #include <map>
@@ -411,6 +412,58 @@ static olap_status upload_scalar(olap_ctx* ctx, uint64_t bits, BufPtr* out) {
 // execute_aggregate, executor.rs:297-355.  No GROUP BY: exactly the reference's execution -- one row, every aggregate
 // emitted as Float64 (:347), identities for empty input (:310-311, :339-345).  GROUP BY: the completion rule of
 // key = first group_by expression as Int64, one row per distinct key, typed aggregates.
+// PhysicalExpr tree -> olap_expr_prog over the columns of batch b (reverse Polish, depth <= 3, one value type).
+// false: the tree does not fit a program (mixed types, too long / deep, a bare column or literal) -- evaluate it with
+// the projection kernels instead.
+static bool compile_prog_rec(const olap_expr* e, const Batch& b, olap_expr_prog* g, int* type, int* depth, int* max_depth) {
+  if (g->n_ops >= OLAP_PROG_MAX_OPS) return false;
+  if (e->kind == EXPR_COLUMN) {
+    const Col* c = nullptr;
+    for (const Col& x : b.cols) if (x.name == e->text) { c = &x; break; }
+    if (!c && e->index < b.cols.size()) c = &b.cols[e->index];
+    if (!c || !c->buf) return false;
+    if (*type >= 0 && *type != c->type) return false;
+    *type = c->type;
+    g->op[g->n_ops] = 'c'; g->column[g->n_ops] = c->data(); g->literal_bits[g->n_ops] = 0; g->n_ops++;
+    *max_depth = std::max(*max_depth, ++*depth);
+    return true;
+  }
+  if (e->kind == EXPR_LITERAL) {
+    Value v;
+    if (!parse_literal(e->text, &v)) return false;
+    if (*type >= 0 && *type != v.type) return false;
+    *type = v.type;
+    g->op[g->n_ops] = 'l'; g->column[g->n_ops] = nullptr; g->literal_bits[g->n_ops] = (int64_t)v.bits; g->n_ops++;
+    *max_depth = std::max(*max_depth, ++*depth);
+    return true;
+  }
+  if (e->text.size() != 1 || !strchr("+-*/", e->text[0])) return false;
+  if (!compile_prog_rec(e->l, b, g, type, depth, max_depth)) return false;
+  if (!compile_prog_rec(e->r, b, g, type, depth, max_depth)) return false;
+  if (g->n_ops >= OLAP_PROG_MAX_OPS) return false;
+  g->op[g->n_ops] = (int8_t)e->text[0]; g->column[g->n_ops] = nullptr; g->literal_bits[g->n_ops] = 0; g->n_ops++;
+  --*depth;
+  return true;
+}
+// The literal's type must be known before the column it is combined with is seen ("1.0 - l_discount"): find the tree's type first.
+static int expr_type(const olap_expr* e, const Batch& b) {
+  if (e->kind == EXPR_COLUMN) {
+    for (const Col& x : b.cols) if (x.name == e->text) return x.type;
+    return e->index < b.cols.size() ? b.cols[e->index].type : -1;
+  }
+  if (e->kind == EXPR_LITERAL) { Value v; return parse_literal(e->text, &v) ? v.type : -1; }
+  const int l = expr_type(e->l, b), r = expr_type(e->r, b);
+  return l == r ? l : -1;  // eval_binary_expr refuses mixed operands; the materialising path reports that error
+}
+static bool compile_prog(const olap_expr* e, const Batch& b, olap_expr_prog* g, int* type) {
+  if (e->kind != EXPR_BINARY) return false;
+  memset(g, 0, sizeof(*g));
+  *type = expr_type(e, b);
+  if (*type < 0) return false;
+  int depth = 0, max_depth = 0;
+  return compile_prog_rec(e, b, g, type, &depth, &max_depth) && depth == 1 && max_depth <= 3;
+}
+
 // Number of groups of a key column, estimated from the distinct keys d among m evenly spaced rows: for G equally likely
 // groups E[d] = G (1 - exp(-m / G)).  The group-by kernels take it as a hint: too low or too high costs speed (a shared
 // table that spills, or L2 atomics where shared memory would do), never correctness.
@@ -477,15 +530,32 @@ static olap_status exec_aggregate(olap_ctx* ctx, const olap_plan* p, Batches* ou
   if (in.empty()) n = 0;
   std::vector<Value> vals(na);
   std::vector<olap_agg_spec> specs(na + 1);
+  std::vector<olap_expr_prog> prog_store(na);
+  std::vector<const olap_expr_prog*> progs(na + 1, nullptr);
   std::map<std::string, int> seen;  // identical input expressions are evaluated once (SUM(x), AVG(x), MIN(x) share one column)
-  for (int a = 0; a < na; a++) {
-    const std::string ename = expr_name(p->agg_in[a]);
-    auto it = seen.find(ename);
-    if (it != seen.end()) vals[a] = vals[it->second];
-    else if (!in.empty()) { OLAP_TRY(eval_over_batches(ctx, p->agg_in[a], in, n, &vals[a])); seen[ename] = a; }
-    else { vals[a].type = OLAP_I64; OLAP_TRY(new_buf(ctx, 16, &vals[a].buf)); }
-    specs[a].values = vals[a].data(); specs[a].func = p->agg_funcs[a]; specs[a].value_type = vals[a].type;
-  }
+  // Arithmetic inputs are handed to the aggregation kernel as small programs over the input columns (no projection passes);
+  // fuse_exprs = false materialises them with the projection kernels, as the reference's executor would.
+  auto bind_inputs = [&](bool fuse_exprs) -> olap_status {
+    seen.clear();
+    for (int a = 0; a < na; a++) {
+      progs[a] = nullptr;
+      const std::string ename = expr_name(p->agg_in[a]);
+      auto it = seen.find(ename);
+      if (it != seen.end()) { vals[a] = vals[it->second]; progs[a] = progs[it->second]; }
+      else if (!in.empty()) {
+        int type = -1;
+        if (fuse_exprs && p->agg_funcs[a] != OLAP_COUNT && compile_prog(p->agg_in[a], in[0], &prog_store[a], &type)) {
+          progs[a] = &prog_store[a]; vals[a] = Value(); vals[a].type = type;
+        } else OLAP_TRY(eval_over_batches(ctx, p->agg_in[a], in, n, &vals[a]));
+        seen[ename] = a;
+      } else { vals[a].type = OLAP_I64; OLAP_TRY(new_buf(ctx, 16, &vals[a].buf)); }
+      specs[a].values = progs[a] ? nullptr : vals[a].data(); specs[a].func = p->agg_funcs[a]; specs[a].value_type = vals[a].type;
+    }
+    return OLAP_OK;
+  };
+  // grouped aggregation is bound by its table updates, so the extra arithmetic is free; the no-key kernel is a pure stream
+  // and measured faster on a materialised column (Q6 shape: 0.78 ms vs 0.96 ms fused)
+  OLAP_TRY(bind_inputs(!p->group_by.empty()));
   // one more COUNT: the number of rows that pass the fused filter (the reference's "empty input" cases depend on it)
   specs[na].values = nullptr; specs[na].func = OLAP_COUNT; specs[na].value_type = OLAP_I64;
   const bool grouped = !p->group_by.empty();
@@ -500,11 +570,19 @@ static olap_status exec_aggregate(olap_ctx* ctx, const olap_plan* p, Batches* ou
   if (grouped) OLAP_TRY(estimate_groups(ctx, key.data(), n, &hint));
   uint64_t cap = hint, groups = 0;
   BufPtr ok, oa;
+  bool refused = false;  // at most one UNSUPPORTED retry
   for (int attempt = 0; attempt < 2; attempt++) {
     OLAP_TRY(new_buf(ctx, cap * 8, &ok));
     OLAP_TRY(new_buf(ctx, (uint64_t)ns * cap * 8, &oa));
-    olap_status st = olap_group_by_i64(ctx, grouped ? (const int64_t*)key.data() : nullptr, specs.data(), ns, n, hint,
-                                       terms.empty() ? nullptr : terms.data(), (int32_t)terms.size(), (int64_t*)ok->p, oa->p, cap, nullptr, &groups, nullptr);
+    olap_status st = olap_group_by_prog_i64(ctx, grouped ? (const int64_t*)key.data() : nullptr, specs.data(), progs.data(), ns, n, hint,
+                                            terms.empty() ? nullptr : terms.data(), (int32_t)terms.size(), (int64_t*)ok->p, oa->p, cap, nullptr, &groups,
+                                            nullptr);
+    if (st == OLAP_ERR_UNSUPPORTED && !refused) {  // too many groups for the regimes that fuse expressions: materialise them
+      refused = true;
+      OLAP_TRY(bind_inputs(false));
+      attempt = -1;
+      continue;
+    }
     if (st == OLAP_ERR_CAPACITY && attempt == 0) { cap = hint = groups; continue; }
     OLAP_TRY(st);
     break;

@@ -210,6 +210,26 @@ OLAP_API olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, const
                                        uint64_t n_rows, uint64_t n_groups_hint, const olap_filter_term* terms,
                                        int32_t n_terms, int64_t* out_keys, void* out_aggs, uint64_t out_capacity,
                                        uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream);
+/* Aggregate inputs computed on the fly (no reference analogue: the reference materialises every projection first,
+ * executor.rs:184-214).  progs[i] == NULL: aggregate i reads specs[i].values as before.  Otherwise specs[i].values is
+ * ignored and the value is the result of a small arithmetic program in reverse Polish notation over 8-byte device columns
+ * and literals, all of type specs[i].value_type, evaluated inside the aggregation kernel with eval_binary_expr's semantics
+ * (i64 wraps, x / 0 = 0; f64 IEEE):  op 'c' pushes column[k], 'l' pushes literal_bits[k], '+' '-' '*' '/' replace the two
+ * topmost entries (second-from-top OP top).  At most OLAP_PROG_MAX_OPS entries, stack depth <= 3.  Aggregates that share
+ * one program pointer share one evaluation.  Returns OLAP_ERR_UNSUPPORTED when the cardinality hint needs the partitioned
+ * regime (which carries plain columns only): materialise the expression and call olap_group_by_i64 instead.          */
+#define OLAP_PROG_MAX_OPS 10
+typedef struct {
+  int32_t n_ops;
+  int8_t op[OLAP_PROG_MAX_OPS];
+  const void* column[OLAP_PROG_MAX_OPS];
+  int64_t literal_bits[OLAP_PROG_MAX_OPS];
+} olap_expr_prog;
+OLAP_API olap_status olap_group_by_prog_i64(olap_ctx* ctx, const int64_t* keys, const olap_agg_spec* specs,
+                                            const olap_expr_prog* const* progs, int32_t n_aggs, uint64_t n_rows,
+                                            uint64_t n_groups_hint, const olap_filter_term* terms, int32_t n_terms,
+                                            int64_t* out_keys, void* out_aggs, uint64_t out_capacity,
+                                            uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream);
 /* AggFunc::identity_value (aggregate_kernel.rs:27-33) */
 OLAP_API int64_t olap_agg_identity(int32_t func);
 /* compute_launch_params (filter_kernel.rs:75-79, aggregate_kernel.rs:127-131), without the u32 truncation bug */

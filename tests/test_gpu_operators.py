@@ -209,3 +209,21 @@ def test_tpch_q1_shape(ex):
     plan = g.GpuAggregate(g.GpuFilter(g.GpuTableScan("lineitem"), g.BinaryExpr(col("l_shipdate"), "<=", lit(10471))), [key], aggs)
     got = run_both(ex, plan, tables, sort_by=["((l_returnflag * lit(2)) + l_linestatus)"], exact=False)
     assert got[0].num_rows == 6
+
+
+def test_aggregate_expression_inputs_fused_and_materialised(ex):
+    # SUM / MIN / AVG over arithmetic expressions: with few groups the expression is evaluated inside the aggregation
+    # kernel (olap_group_by_prog_i64); with 300 K groups over 2^21 rows the kernel refuses (partitioned regime) and the
+    # operator layer materialises the expression instead -- same answers either way
+    import gpu_olap_engine_b200 as g
+    n = (1 << 21) + 123
+    a = O.gen_uniform_i64(n, 71, 1 << 20) - (1 << 19); b = O.gen_uniform_i64(n, 72, 1000) + 1
+    f = O.gen_dyadic_f64(n, 73, 1 << 16)
+    for groups in (7, 300000):
+        t = pa.table({"k": O.gen_uniform_i64(n, 70, groups), "a": a, "b": b, "f": f})
+        tables = {"t": t.to_batches(max_chunksize=700000)}
+        e1 = g.BinaryExpr(g.BinaryExpr(col("a"), "*", lit(3)), "-", g.BinaryExpr(col("a"), "/", col("b")))
+        e2 = g.BinaryExpr(col("f"), "*", g.BinaryExpr(lit("0.5"), "+", col("f")))
+        plan = g.GpuAggregate(g.GpuTableScan("t"), [col("k")], [g.Sum(e1), g.Min(e1), g.Avg(e1), g.Sum(e2), g.Max(e2), g.Count(col("a"))])
+        run_both(ex, plan, tables, sort_by=["k"], exact=True)
+
