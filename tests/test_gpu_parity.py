@@ -220,6 +220,21 @@ def test_join_large_skewed_partition_keeps_three_ring_slots(ctx):
     assert (O.sort_pairs(pairs.to_numpy(2 * cnt).reshape(-1, 2)) == O.sort_pairs(exp_pairs)).all()
 
 
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("part_rows", ["524288", "1024"])   # 2 partitions / up to 256 tiny partitions (ring reuse, dependency counters)
+@pytest.mark.parametrize("alloc", ["1", "0"])   # one-pass fixed-capacity regions / exact histogram layout (unaligned partition starts)
+def test_join_tile_boundaries_in_both_partition_layouts(ctx, alloc, part_rows, monkeypatch):
+    # radix strategy on sizes that straddle the 2048-row work items, the 4096-row partition tiles and the 4-row vector
+    # loads; every size is checked against the oracle's match set
+    monkeypatch.setenv("OLAP_JOIN_ALLOC", alloc)
+    monkeypatch.setenv("OLAP_JOIN_PART_ROWS", part_rows)
+    rng = np.random.default_rng(int(alloc) + 17)
+    for nb, npb in [(2048, 4096), (2049, 4095), (4097, 8191), (8190, 3), (3, 8190), (65537, 131071), (131073, 70001), (1 << 18, (1 << 19) + 5)]:
+        dom = max(nb // 2, 2)
+        b = rng.integers(-dom, dom, nb).astype(np.int64); p = rng.integers(-dom, dom, npb).astype(np.int64)
+        check_join(ctx, b, p, 0)
+
+
 @pytest.mark.parametrize("bits", [1, 4, 8])
 def test_radix_partition_unit(ctx, bits):
     import gpu_olap_engine_b200 as g
