@@ -113,7 +113,10 @@ def run_reference(args):
         "impl": "reference", "metric": "join rows/sec (|build|+|probe|)/time", "value": rps, "unit": "rows/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"single-GPU radix hash join 2^{args.log2_build} unique-key build x 2^{args.log2_probe} FK probe, int64 keys, uniform",
+        "config": {"workload": (f"single-GPU radix hash join 2^{args.log2_build} unique-key build x 2^{args.log2_probe} FK probe, int64 keys, uniform"
+                                if args.gpus <= 1 else
+                                f"{args.gpus}-GPU key-sharded radix hash join, per GPU 2^{args.log2_build} unique-key build x 2^{args.log2_probe} FK probe "
+                                f"(global 2^{args.log2_build}*{args.gpus} x 2^{args.log2_probe}*{args.gpus}), int64 keys, uniform, rows contiguous-sharded"),
                    "sample": sample},
         "cpu_baseline": {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rps, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
