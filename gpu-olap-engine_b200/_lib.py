@@ -28,6 +28,15 @@ class AggSpec(C.Structure):
     _fields_ = [("values", C.c_void_p), ("func", C.c_int32), ("value_type", C.c_int32)]
 
 
+PROG_MAX_OPS = 10
+
+
+class ExprProg(C.Structure):
+    """olap_expr_prog: reverse-Polish arithmetic over device columns / literals, evaluated inside the aggregation kernel."""
+    _fields_ = [("n_ops", C.c_int32), ("op", C.c_int8 * PROG_MAX_OPS), ("column", C.c_void_p * PROG_MAX_OPS),
+                ("literal_bits", C.c_int64 * PROG_MAX_OPS)]
+
+
 # name -> (restype, argtypes); the test-suite checks that every OLAP_API symbol of the header is listed here
 vp, u64, i64, i32, u32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32
 pu64, pvp = C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)

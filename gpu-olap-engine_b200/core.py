@@ -241,7 +241,7 @@ class Context:
 
     # ------------------------------------------------------------------ aggregate
     def group_by_i64(self, keys, n_rows: int, aggs: Sequence[tuple], n_groups_hint: int, out_capacity: Optional[int] = None,
-                     terms: Optional[Sequence[Term]] = None, stream=None):
+                     terms: Optional[Sequence[Term]] = None, stream=None, progs=None):
         """AggregateKernel::aggregate analogue.  aggs: [(func, values, value_type)].
 
         Returns (n_groups, out_keys DeviceBuffer, out_aggs DeviceBuffer [n_aggs * out_capacity], out_capacity)."""
@@ -252,8 +252,14 @@ class Context:
         oa = self.alloc(max(na, 1) * cap, np.uint64)
         arr, nt = _terms(terms)
         g = C.c_uint64()
-        check(self.lib.olap_group_by_i64(self.handle, _ptr(keys), specs, na, n_rows, n_groups_hint, arr, nt, ok.ptr, oa.ptr, cap,
-                                         None, C.byref(g), stream))
+        if progs is None:
+            check(self.lib.olap_group_by_i64(self.handle, _ptr(keys), specs, na, n_rows, n_groups_hint, arr, nt, ok.ptr, oa.ptr, cap,
+                                             None, C.byref(g), stream))
+        else:  # progs[i]: None, or [("c", column) | ("l", literal) | "+" | "-" | "*" | "/", ...] in reverse Polish notation
+            built = [None if pr is None else make_prog(pr, aggs[i][2]) for i, pr in enumerate(progs)]
+            ptrs = (C.c_void_p * max(na, 1))(*[None if b is None else C.addressof(b) for b in built])
+            check(self.lib.olap_group_by_prog_i64(self.handle, _ptr(keys), specs, ptrs, na, n_rows, n_groups_hint, arr, nt, ok.ptr, oa.ptr, cap,
+                                                  None, C.byref(g), stream))
         return g.value, ok, oa, cap
 
     # ------------------------------------------------------------------ profiling
@@ -310,6 +316,24 @@ class JoinBuild:
             self.close()
         except Exception:
             pass
+
+
+def make_prog(items, value_type) -> "_lib.ExprProg":
+    """[("c", DeviceBuffer) | ("l", number) | "+" | "-" | "*" | "/"] -> olap_expr_prog (literals take the aggregate's value type)."""
+    from ._lib import ExprProg, PROG_MAX_OPS
+    if not 1 <= len(items) <= PROG_MAX_OPS:
+        raise ValueError("an expression program has 1..%d entries" % PROG_MAX_OPS)
+    g = ExprProg()
+    g.n_ops = len(items)
+    for k, it in enumerate(items):
+        if isinstance(it, str):
+            g.op[k] = ord(it)
+        elif it[0] == "c":
+            g.op[k] = ord("c"); g.column[k] = _ptr(it[1])
+        else:
+            g.op[k] = ord("l")
+            g.literal_bits[k] = int(np.float64(it[1]).view(np.int64)) if value_type == F64 else int(it[1])
+    return g
 
 
 def typed_agg_results(out_aggs: np.ndarray, cap: int, n_groups: int, aggs: Sequence[tuple]):

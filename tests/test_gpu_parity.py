@@ -388,3 +388,32 @@ def test_pool_alloc_free_and_cap():
         assert ei.value.status == 2
         a.free()
         assert c.pool_stats()["used"] == 0 and c.pool_stats()["high_water"] >= 8000
+
+
+def test_group_by_expression_programs_at_the_kernel_seam(ctx):
+    # olap_group_by_prog_i64: SUM / MIN / MAX over a*3 - a/b (i64: wrapping, truncating division, x/0 = 0) and f*(0.5+f) (f64),
+    # evaluated inside the aggregation kernel, against the oracle's projection + group-by; shared, no-key and global regimes
+    import gpu_olap_engine_b200 as g
+    n = 400003
+    k = O.gen_uniform_i64(n, 80, 700) - 350
+    a = O.gen_uniform_i64(n, 81, 1 << 30) - (1 << 29); b = O.gen_uniform_i64(n, 82, 7) - 3   # b hits 0: x / 0 = 0
+    f = O.gen_dyadic_f64(n, 83, 1 << 12)
+    e1 = O.project_i64(O.project_i64(a, "*", literal=3), "-", r=O.project_i64(a, "/", r=b))
+    e2 = f * (0.5 + f)
+    dk, da, db, df = dev(ctx, k), dev(ctx, a), dev(ctx, b), dev(ctx, f)
+    p1 = [("c", da), ("l", 3), "*", ("c", da), ("c", db), "/", "-"]
+    p2 = [("c", df), ("l", 0.5), ("c", df), "+", "*"]
+    aggs = [(g.SUM, None, g.I64), (g.MIN, None, g.I64), (g.MAX, None, g.I64), (g.SUM, None, g.F64), (g.COUNT, None, g.I64)]
+    progs = [p1, p1, p1, p2, None]
+    for keys, hint in ((dk, 700), (None, 1), (dk, 70000)):
+        exp = O.group_by_i64(k if keys is not None else None, [e1, e1, e1, e2, e1], [O.SUM, O.MIN, O.MAX, O.SUM, O.COUNT])
+        ng, ok, oa, cap = ctx.group_by_i64(keys, n, aggs, hint, progs=progs)
+        assert ng == len(exp[0])
+        gk = ok.to_numpy(ng); order = np.argsort(gk, kind="stable")
+        res = g.typed_agg_results(oa.to_numpy(), cap, ng, aggs)
+        eo = np.argsort(exp[0], kind="stable")
+        if keys is not None:
+            assert (gk[order] == np.asarray(exp[0])[eo]).all()
+        for got, want in zip(res, exp[1]):
+            assert (np.asarray(got)[order] == np.asarray(want)[eo]).all()
+
