@@ -956,7 +956,8 @@ static olap_status group_by_impl(olap_ctx* ctx, const int64_t* keys, const olap_
     const uint64_t sbytes = slot_bytes(p), budget = 96 * 1024;  // shared regime: two CTAs per SM (a 50 KB budget / 4 CTAs measured no faster)
     uint64_t need = pow2_at_least((n_groups_hint * 4 + 2) / 3);
     if (need < 16) need = 16;
-    const bool shared = keys && attempt == 0 && (need + 1) * sbytes + 16 <= budget;
+    // up to 96 KB: two CTAs per SM; up to 200 KB: one CTA per SM, still ahead of the partitioned regime's extra pass
+    const bool shared = keys && attempt == 0 && (need + 1) * sbytes + 16 <= 200 * 1024;
     const bool partitioned = keys && attempt == 0 && !shared && n_rows >= (1u << 20) && p.n_vcols <= 4;  // the partitioner carries <= 4 payload columns
     if (any_prog && partitioned) {
       set_error("computed aggregate inputs are fused in the no-key / shared / global regimes only; materialise them for %llu groups",
@@ -989,12 +990,12 @@ static olap_status group_by_impl(olap_ctx* ctx, const int64_t* keys, const olap_
         if (any_prog) {
           GB_DISPATCH_NV(p.n_vcols, {
             OLAP_CUDA((cudaFuncSetAttribute(gb_shared_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-            gb_shared_kernel<NV, true><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 2), kGbThreads, smem, s>>>(p);
+            gb_shared_kernel<NV, true><<<capped_grid(tiles, (uint64_t)ctx->sm_count * (smem <= budget ? 2 : 1)), kGbThreads, smem, s>>>(p);
           });
         } else {
           GB_DISPATCH_NV(p.n_vcols, {
             OLAP_CUDA(cudaFuncSetAttribute(gb_shared_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gb_shared_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * 2), kGbThreads, smem, s>>>(p);
+            gb_shared_kernel<NV><<<capped_grid(tiles, (uint64_t)ctx->sm_count * (smem <= budget ? 2 : 1)), kGbThreads, smem, s>>>(p);
           });
         }
         count_launch(ctx);
