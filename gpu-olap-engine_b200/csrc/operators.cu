@@ -464,11 +464,11 @@ static bool compile_prog(const olap_expr* e, const Batch& b, olap_expr_prog* g, 
   return compile_prog_rec(e, b, g, type, &depth, &max_depth) && depth == 1 && max_depth <= 3;
 }
 
-// Number of groups of a key column, estimated from the distinct keys d among m evenly spaced rows: for G equally likely
+// Number of groups of a key column, estimated from the distinct keys d among m <= 2^17 evenly spaced rows: for G equally likely
 // groups E[d] = G (1 - exp(-m / G)).  The group-by kernels take it as a hint: too low or too high costs speed (a shared
 // table that spills, or L2 atomics where shared memory would do), never correctness.
 static olap_status estimate_groups(olap_ctx* ctx, const uint64_t* keys, uint64_t n, uint64_t* est) {
-  const uint64_t m = std::min<uint64_t>(n, 1u << 20), stride = n / m;
+  const uint64_t m = std::min<uint64_t>(n, 1u << 17), stride = n / m;  // 2^17 rows resolve cardinalities up to ~10^6 (d/m = 0.94 there) and cost ~50 us
   BufPtr sk, ok, oa;
   OLAP_TRY(new_buf(ctx, m * 8, &sk));
   OLAP_TRY(new_buf(ctx, m * 8, &ok));
