@@ -47,6 +47,9 @@ struct PartArgs {
   uint32_t* peer_ids[8];
   uint32_t peer_off[8];
   const uint32_t* part_begin;            // PEER mode: scanned partition starts (device, [P + 1])
+  // RANGE mode (direct-address join on a dense key domain): partition = (key - rmin) >> rshift; keys outside
+  // [rmin, rmin + rrange) cannot match and are dropped
+  int64_t rmin; uint64_t rrange; int rshift;
   uint64_t* out_keys;
   uint32_t* out_ids;
   uint64_t* pay_out[kMaxPay];
@@ -153,6 +156,19 @@ __global__ void __launch_bounds__(1024) part_scan_kernel(uint32_t* hist, uint32_
   }
 }
 
+// signed min / max of a key column -> out[0], out[1] (initialised to INT64_MAX / INT64_MIN by the caller)
+__global__ void __launch_bounds__(256) key_minmax_kernel(const uint64_t* __restrict__ keys, uint64_t n, long long* __restrict__ out) {
+  long long lo = INT64_MAX, hi = INT64_MIN;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const long long k = (long long)ld_stream_u64(keys + i);
+    lo = min(lo, k); hi = max(hi, k);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMin(out, lo); atomicMax(out + 1, hi); }
+}
+
 // ALLOC = false: exact layout; every CTA's output offsets come from the histogram pass (contiguous partitions, no atomics).
 // ALLOC = true : no histogram pass; partition p owns a fixed-capacity region and every tile reserves its run in it with
 //                one global atomic per (tile, partition).  Saves a full read of the keys; a region that overflows (skewed
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(1024) part_scan_kernel(uint32_t* hist, uint32_
 //                multi-GPU shuffle happens inside this kernel, run by run, instead of in a collective after it.
 // TERMS = true : a fused filter conjunction drops rows before they are ranked (partitioned group-by with a predicate); a
 //                template parameter because even dead filter code cost the join's instantiations registers and 8 % of speed.
-template <int NPAY, bool IDS, bool ALLOC, bool PEER = false, bool TERMS = false>
+template <int NPAY, bool IDS, bool ALLOC, bool PEER = false, bool TERMS = false, bool RANGE = false>
 __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) partition_kernel(PartArgs a) {
   constexpr bool BYPART = ALLOC || PEER;  // the staged row remembers its partition, the destination is formed at write-out
   __shared__ uint64_t* s_kptr[kMaxPeers];
@@ -216,7 +232,12 @@ __global__ void __launch_bounds__(kPartThreads, NPAY > 1 ? 1 : kPartCtasPerSm) p
 #pragma unroll
       for (int e = 0; e < 4; e++)
         if (pr[j][e] == 0) {
-          const uint32_t part = (uint32_t)(part_hash(k[j][e], a.salt) >> sh);
+          uint32_t part;
+          if (RANGE) {
+            const uint64_t d = k[j][e] - (uint64_t)a.rmin;
+            if (d >= a.rrange) { pr[j][e] = 0xFFFFFFFFu; continue; }  // outside the build side's key range: no match possible
+            part = (uint32_t)(d >> a.rshift);
+          } else part = (uint32_t)(part_hash(k[j][e], a.salt) >> sh);
           pr[j][e] = (part << 16) | atomicAdd(&s_cnt[part], 1u);
         }
     __syncthreads();
@@ -302,11 +323,11 @@ static PartPlan plan_partition(olap_ctx* ctx, uint64_t n) {
   return {grid, chunk};
 }
 
-template <int NPAY, bool IDS, bool ALLOC = false, bool PEER = false, bool TERMS = false>
+template <int NPAY, bool IDS, bool ALLOC = false, bool PEER = false, bool TERMS = false, bool RANGE = false>
 static olap_status launch_partition(olap_ctx* ctx, PartArgs& a, unsigned grid, cudaStream_t s) {
   const size_t smem = (size_t)kPartTile * (8 + 8 * NPAY + (IDS ? 4 : 0) + 4);
-  OLAP_CUDA((cudaFuncSetAttribute(partition_kernel<NPAY, IDS, ALLOC, PEER, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
-  partition_kernel<NPAY, IDS, ALLOC, PEER, TERMS><<<grid, kPartThreads, smem, s>>>(a);
+  OLAP_CUDA((cudaFuncSetAttribute(partition_kernel<NPAY, IDS, ALLOC, PEER, TERMS, RANGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+  partition_kernel<NPAY, IDS, ALLOC, PEER, TERMS, RANGE><<<grid, kPartThreads, smem, s>>>(a);
   count_launch(ctx);
   return OLAP_OK;
 }
@@ -346,7 +367,8 @@ static olap_status run_partition_alloc(olap_ctx* ctx, PartArgs& a, cudaStream_t 
   a.chunk = pl.chunk;
   a.vec = aligned32(a.keys);
   OLAP_CUDA(cudaMemsetAsync(a.cursor, 0, (size_t)(1u << a.bits) * 4, s));
-  OLAP_TRY((launch_partition<0, true, true>(ctx, a, pl.grid, s)));
+  if (a.rrange) OLAP_TRY((launch_partition<0, true, true, false, false, true>(ctx, a, pl.grid, s)));
+  else OLAP_TRY((launch_partition<0, true, true>(ctx, a, pl.grid, s)));
   count_launch(ctx);
   OLAP_CUDA(cudaGetLastError());
   if (part_mark) phase_mark(ctx, s, part_mark);
@@ -606,6 +628,100 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Bucket* __rest
   if (!PIPE) __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------- direct-address tables
+// When the build keys are dense (max - min + 1 <= 4 x rows) and unique -- surrogate keys of a dimension table, the
+// benchmark's permutation of 0..n-1 -- a partition's table is just row_id[key - min]: 4 bytes per key of the partition's key
+// range (2 MB instead of 16 MB at C2), ONE atomicExch per build row (it also detects a duplicate key, which sends the whole
+// join back to the bucket tables), no hash, no key compare, no continuation on the probe side.  Partitions are key RANGES
+// ((key - min) >> shift) so that every table covers a contiguous slice of the domain.
+constexpr uint32_t kDirectEmpty = 0xFFFFFFFFu;
+
+template <bool VEC>
+__device__ __forceinline__ void build_tile_direct(uint32_t* __restrict__ table, uint64_t rmin, uint32_t mask, const uint64_t* __restrict__ keys,
+                                                  const uint32_t* __restrict__ ids, uint64_t begin, uint64_t end, uint64_t tile,
+                                                  uint32_t* __restrict__ dup_flag) {
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int sub = 0; sub < kJoinSub; sub++) {
+    const uint64_t row0 = tile + (uint64_t)(sub * kJoinThreads + tid) * kJoinRows;
+    uint64_t key[kJoinRows];
+    uint32_t id[kJoinRows];
+    bool live[kJoinRows];
+    load_rows4<VEC>(keys, ids, begin, end, row0, key, id, live);
+    uint32_t old[kJoinRows];
+#pragma unroll
+    for (int j = 0; j < kJoinRows; j++) old[j] = live[j] ? atomicExch(&table[(uint32_t)(key[j] - rmin) & mask], id[j]) : kDirectEmpty;
+    bool dup = false;
+#pragma unroll
+    for (int j = 0; j < kJoinRows; j++) dup = dup || old[j] != kDirectEmpty;
+    if (dup) *dup_flag = 1;  // a second row with the same key: this representation cannot hold it
+  }
+}
+
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool VEC>
+__device__ __forceinline__ void probe_tile_direct(ProbeShared& sh, const uint32_t* __restrict__ table, uint64_t rmin, uint32_t mask,
+                                                  uint32_t pid_base, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
+                                                  uint64_t begin, uint64_t end, uint64_t tile, olap_pair* __restrict__ out,
+                                                  uint64_t max_matches, unsigned long long* __restrict__ count) {
+  const int tid = threadIdx.x, lane = tid & 31;
+#pragma unroll 1
+  for (int sub = 0; sub < kJoinSub; sub++) {
+    const uint64_t row0 = tile + (uint64_t)(sub * kJoinThreads + tid) * kJoinRows;
+    uint64_t key[kJoinRows];
+    uint32_t pid[kJoinRows], row[kJoinRows];
+    bool live[kJoinRows];
+    load_rows4<VEC>(keys, ids, begin, end, row0, key, pid, live);
+#pragma unroll
+    for (int j = 0; j < kJoinRows; j++) row[j] = live[j] ? ld_cg_u32(table + ((uint32_t)(key[j] - rmin) & mask)) : kDirectEmpty;  // four gathers in flight
+    uint32_t nh = 0;
+#pragma unroll
+    for (int j = 0; j < kJoinRows; j++) nh += row[j] != kDirectEmpty;
+    uint32_t inc = nh;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total) {
+      uint32_t base = 0;
+      if (lane == 31) base = atomicAdd(&sh.n, total);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      uint32_t pos = base + inc - nh;  // a tile never yields more pairs than rows here: the stage (>= kJoinTile pairs) cannot overflow
+#pragma unroll
+      for (int j = 0; j < kJoinRows; j++) {
+        if (row[j] != kDirectEmpty) sh.stage[pos] = make_uint2(row[j], pid[j] + pid_base);
+        pos += row[j] != kDirectEmpty;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n = sh.n;
+  if (tid == 0 && n) sh.base = atomicAdd(count, (unsigned long long)n);  // one global atomic per tile
+  __syncthreads();
+  if (out && n) {
+    const unsigned long long base = sh.base;
+    if (base + n <= max_matches) {
+      const uint32_t lead = (uint32_t)((reinterpret_cast<uintptr_t>(out + base) >> 3) & 1);
+      if (tid == 0 && lead) st_stream_u64(out + base, (uint64_t)sh.stage[0].x | ((uint64_t)sh.stage[0].y << 32));
+      uint32_t i = lead + 2 * tid;
+      for (; i + 1 < n; i += 2 * kJoinThreads) {
+        const uint2 a = sh.stage[i], b = sh.stage[i + 1];
+        st_stream_u64x2(out + base + i, make_ulonglong2((uint64_t)a.x | ((uint64_t)a.y << 32), (uint64_t)b.x | ((uint64_t)b.y << 32)));
+      }
+      if (i < n) st_stream_u64(out + base + i, (uint64_t)sh.stage[i].x | ((uint64_t)sh.stage[i].y << 32));
+    } else {
+      for (uint32_t i = tid; i < n; i += kJoinThreads) {
+        const unsigned long long pos = base + i;
+        if (pos < max_matches) st_stream_u64(out + pos, (uint64_t)sh.stage[i].x | ((uint64_t)sh.stage[i].y << 32));
+      }
+    }
+  }
+}
+
 // one table, one relation: the single-table (broadcast) strategy and the per-partition fallback
 template <bool VEC>
 __global__ void __launch_bounds__(kJoinThreads) build_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ ids,
@@ -642,6 +758,8 @@ struct PipeArgs {
   const uint64_t* bkeys; const uint32_t* bids; const uint64_t* pkeys; const uint32_t* pids;
   const uint32_t* bb; const uint32_t* pb;          // device, [2P]: rows of partition p are [x[p], x[P + p])
   uint32_t P; int bits; uint32_t R; uint32_t pid_base; uint32_t load_pct;
+  uint32_t direct_entries;                         // DIRECT: keys per partition (2^rshift); tables hold 4-byte row ids
+  uint64_t rmin; uint32_t* dup;                    // DIRECT: smallest build key; set to 1 when a build key repeats
   Bucket* arena; uint64_t stride;                  // ring slot r = arena + r * stride buckets
   uint32_t* sync;                                  // [0] ticket, then cleared[P], built[P], probed[P]; zeroed before the launch
   uint32_t grid_dbg;
@@ -661,9 +779,9 @@ __host__ __device__ __forceinline__ uint32_t table_buckets(uint32_t rows, uint32
   const uint64_t b = ((uint64_t)rows * load_pct + 99) / 100;
   return b > 64 ? (uint32_t)b : 64u;
 }
-__host__ __device__ __forceinline__ PartWork part_work(uint32_t b0, uint32_t b1, uint32_t p0, uint32_t p1, uint32_t load_pct) {
+__host__ __device__ __forceinline__ PartWork part_work(uint32_t b0, uint32_t b1, uint32_t p0, uint32_t p1, uint32_t load_pct, uint32_t direct_entries = 0) {
   PartWork w;
-  w.nbk = table_buckets(b1 - b0, load_pct);
+  w.nbk = direct_entries ? direct_entries / 8 : table_buckets(b1 - b0, load_pct);  // direct tables: size in 32-byte units (for the clear items)
   const bool active = b1 > b0 && p1 > p0;          // inner join: an empty side yields nothing
   w.n_clear = active ? (w.nbk + kClearTile - 1) / kClearTile : 0;
   w.n_build = active ? tiles_of(b0, b1, kJoinTile) : 0;
@@ -690,7 +808,8 @@ __device__ __forceinline__ void pipe_signal(uint32_t* counter) {
   if (threadIdx.x == 0) { __threadfence(); atomicAdd(counter, 1u); }
 }
 
-__global__ void __launch_bounds__(kJoinThreads, 4) join_pipeline_kernel(const __grid_constant__ PipeArgs a) {
+template <bool DIRECT>
+__global__ void __launch_bounds__(kJoinThreads, DIRECT ? 5 : 4) join_pipeline_kernel(const __grid_constant__ PipeArgs a) {
   __shared__ ProbeShared sh;
   __shared__ uint32_t s_ticket;
   const int tid = threadIdx.x;
@@ -711,35 +830,40 @@ __global__ void __launch_bounds__(kJoinThreads, 4) join_pipeline_kernel(const __
     int phase = 0;
     uint32_t p = s;
     if (s < P) {
-      const PartWork w = part_work(a.bb[s], a.bb[P + s], a.pb[s], a.pb[P + s], a.load_pct);
+      const PartWork w = part_work(a.bb[s], a.bb[P + s], a.pb[s], a.pb[P + s], a.load_pct, a.direct_entries);
       if (idx >= w.n_clear) { idx -= w.n_clear; phase = 1; }
     } else phase = 1;
     if (phase == 1) {
       p = s - 1;
       uint32_t nbd = 0;
-      if (s >= 1 && s <= P) nbd = part_work(a.bb[p], a.bb[P + p], a.pb[p], a.pb[P + p], a.load_pct).n_build;
+      if (s >= 1 && s <= P) nbd = part_work(a.bb[p], a.bb[P + p], a.pb[p], a.pb[P + p], a.load_pct, a.direct_entries).n_build;
       if (idx >= nbd) { idx -= nbd; phase = 2; p = s - 2; }
     }
     const uint32_t b0 = a.bb[p], b1 = a.bb[P + p], p0 = a.pb[p], p1 = a.pb[P + p];
-    const PartWork w = part_work(b0, b1, p0, p1, a.load_pct);
+    const PartWork w = part_work(b0, b1, p0, p1, a.load_pct, a.direct_entries);
     Bucket* table = a.arena + (uint64_t)(p % a.R) * a.stride;
     if (phase == 0) {
       uint32_t need = 0;
-      if (p >= a.R) { const uint32_t q = p - a.R; need = part_work(a.bb[q], a.bb[P + q], a.pb[q], a.pb[P + q], a.load_pct).n_probe; }
+      if (p >= a.R) { const uint32_t q = p - a.R; need = part_work(a.bb[q], a.bb[P + q], a.pb[q], a.pb[P + q], a.load_pct, a.direct_entries).n_probe; }
       pipe_wait(probed + (p >= a.R ? p - a.R : 0), need, a.waited + 0);
       const uint32_t c0 = idx * kClearTile, c1 = min(w.nbk, c0 + kClearTile);
-      const u64x4 z = {0, 0, 0, 0};
+      const uint64_t fill = DIRECT ? ~0ULL : 0ULL;  // direct tables: every entry = kDirectEmpty
+      const u64x4 z = {fill, fill, fill, fill};
       for (uint32_t i = c0 + tid; i < c1; i += kJoinThreads) st_stream_u64x4(table + i, z);
       pipe_signal(cleared + p);
     } else if (phase == 1) {
       pipe_wait(cleared + p, w.n_clear, a.waited + 1);
-      build_tile<true>(table, w.nbk, a.bits, a.bkeys, a.bids, b0, b1, (b0 & ~3u) + (uint64_t)idx * kJoinTile);
+      if (DIRECT) build_tile_direct<true>(reinterpret_cast<uint32_t*>(table), a.rmin, a.direct_entries - 1, a.bkeys, a.bids, b0, b1,
+                                          (b0 & ~3u) + (uint64_t)idx * kJoinTile, a.dup);
+      else build_tile<true>(table, w.nbk, a.bits, a.bkeys, a.bids, b0, b1, (b0 & ~3u) + (uint64_t)idx * kJoinTile);
       pipe_signal(built + p);
     } else {
       if (tid == 0) sh.n = 0;  // ordered before the tile by pipe_wait's barrier
       pipe_wait(built + p, w.n_build, a.waited + 2);
-      probe_tile<true, true>(sh, table, w.nbk, a.bits, a.pid_base, a.pkeys, a.pids, p0, p1, (p0 & ~3u) + (uint64_t)idx * kJoinTile, a.out,
-                       a.max_matches, a.count);
+      if (DIRECT) probe_tile_direct<true>(sh, reinterpret_cast<const uint32_t*>(table), a.rmin, a.direct_entries - 1, a.pid_base, a.pkeys, a.pids, p0,
+                                          p1, (p0 & ~3u) + (uint64_t)idx * kJoinTile, a.out, a.max_matches, a.count);
+      else probe_tile<true, true>(sh, table, w.nbk, a.bits, a.pid_base, a.pkeys, a.pids, p0, p1, (p0 & ~3u) + (uint64_t)idx * kJoinTile, a.out,
+                                  a.max_matches, a.count);
       pipe_signal(probed + p);
     }
     if (tid == 0) s_ticket = next;
@@ -799,16 +923,19 @@ static uint64_t side_rows_cap(uint64_t n, int bits) {
   return std::max<uint64_t>(n, (uint64_t)P * cap);
 }
 
+struct KeyRange { int64_t rmin = 0; uint64_t rrange = 0; int rshift = 0; };  // rrange > 0: partition by key range (direct-address join)
+
 static olap_status partition_side(olap_ctx* ctx, const uint64_t* keys, uint64_t n, int bits, uint64_t* out_keys, uint32_t* out_ids,
                                   uint32_t* d_bounds, std::vector<uint32_t>& h_bounds, Scratch& sc, cudaStream_t s, const char* hist_mark,
-                                  const char* part_mark) {
+                                  const char* part_mark, const KeyRange* range = nullptr, bool* range_overflow = nullptr) {
   const uint32_t P = 1u << bits;
   h_bounds.resize(2 * (size_t)P);
   PartArgs a;
   memset(&a, 0, sizeof(a));
   a.bits = bits; a.keys = keys; a.n = n; a.out_keys = out_keys; a.out_ids = out_ids;
+  if (range) { a.rmin = range->rmin; a.rrange = range->rrange; a.rshift = range->rshift; }
   const uint64_t cap = alloc_capacity(n, P);
-  if (env_u64("OLAP_JOIN_ALLOC", 1) && (uint64_t)P * cap < 0xFFFFFFFFULL) {
+  if ((range || env_u64("OLAP_JOIN_ALLOC", 1)) && (uint64_t)P * cap < 0xFFFFFFFFULL) {
     uint32_t* cursor = nullptr;
     OLAP_TRY(sc.get<uint32_t>(P, &cursor));
     a.cursor = cursor; a.cap = (uint32_t)cap;
@@ -823,6 +950,10 @@ static olap_status partition_side(olap_ctx* ctx, const uint64_t* keys, uint64_t 
     for (uint32_t p = 0; p < P; p++) overflow |= used[p] > a.cap;
     if (!overflow) return OLAP_OK;
   }
+  if (range) {  // key ranges of very different sizes (skewed probe side): the caller goes back to hash partitions
+    if (range_overflow) *range_overflow = true;
+    return OLAP_OK;
+  }
   uint32_t *hist = nullptr, *beg = nullptr;
   OLAP_TRY(sc.get<uint32_t>((uint64_t)P * ctx->sm_count * kPartCtasPerSm, &hist));
   OLAP_TRY(sc.get<uint32_t>(P + 1, &beg));
@@ -832,6 +963,29 @@ static olap_status partition_side(olap_ctx* ctx, const uint64_t* keys, uint64_t 
   count_launch(ctx);
   OLAP_CUDA(cudaMemcpyAsync(h_bounds.data(), d_bounds, 2 * (size_t)P * 4, cudaMemcpyDeviceToHost, s));
   OLAP_CUDA(cudaStreamSynchronize(s));
+  return OLAP_OK;
+}
+
+constexpr olap_status OLAP_ERR_INTERNAL_RETRY = (olap_status)1000;  // never leaves this file
+
+// min / max of the build keys; r->rrange > 0 when they are dense enough for direct-address tables: the key range is at most
+// 4 x the rows (a direct table then takes <= 16 bytes per build row, half of the bucket table) and fits 32-bit offsets
+static olap_status detect_dense_keys(olap_ctx* ctx, const uint64_t* keys, uint64_t n, cudaStream_t s, KeyRange* r) {
+  Scratch sc(ctx, s);
+  long long* d = nullptr;
+  OLAP_TRY(sc.get<long long>(2, &d));
+  const long long init[2] = {INT64_MAX, INT64_MIN};
+  long long mm[2];
+  OLAP_CUDA(cudaMemcpyAsync(d, init, 16, cudaMemcpyHostToDevice, s));
+  key_minmax_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(keys, n, d);
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  OLAP_CUDA(cudaMemcpyAsync(mm, d, 16, cudaMemcpyDeviceToHost, s));
+  OLAP_CUDA(cudaStreamSynchronize(s));
+  phase_mark(ctx, s, "minmax");
+  const uint64_t span = (uint64_t)mm[1] - (uint64_t)mm[0];  // max - min, exact in unsigned arithmetic
+  *r = KeyRange();
+  if (mm[1] >= mm[0] && span < 0xFFFFFFF0ULL && span + 1 <= 4 * n) { r->rmin = mm[0]; r->rrange = span + 1; }
   return OLAP_OK;
 }
 
@@ -845,6 +999,7 @@ struct BuildSide {
   Bucket* table = nullptr; uint64_t nbk = 0;
   // radix: the partitioned build side
   uint64_t* pkb = nullptr; uint32_t* pib = nullptr; int bits = 0; uint32_t P = 0;
+  KeyRange range;                // range.rrange > 0: direct-address tables over key ranges instead of bucket tables over hash partitions
   uint32_t* d_bounds = nullptr;  // partition bounds on the device, [2P]
   std::vector<uint32_t> hb;      // ... and on the host
   uint64_t max_part = 0;
@@ -875,13 +1030,24 @@ static olap_status build_side_prepare(olap_ctx* ctx, const uint64_t* bk, uint64_
   const uint64_t target = env_u64("OLAP_JOIN_PART_ROWS", 512 * 1024);
   int bits = 1;
   while (bits < kMaxPartBits && ((nb + target - 1) / target) > (1ULL << bits)) bits++;
+  if (b->range.rrange) {  // direct-address join: <= 256 key ranges of 2^rshift keys (>= 64 Ki keys = 256 KB tables)
+    int sh = 16;
+    while (((b->range.rrange + (1ULL << sh) - 1) >> sh) > (1ULL << kMaxPartBits)) sh++;
+    b->range.rshift = sh;
+    const uint64_t used = (b->range.rrange + (1ULL << sh) - 1) >> sh;
+    bits = 1;
+    while ((1ULL << bits) < used) bits++;
+  }
   b->bits = bits; b->P = 1u << bits;
   Scratch sc(ctx, s);
   const uint64_t rows = side_rows_cap(nb, bits);
   OLAP_TRY(pool_alloc(ctx, rows * 8 + 32, s, (void**)&b->pkb));
   OLAP_TRY(pool_alloc(ctx, rows * 4 + 32, s, (void**)&b->pib));
   OLAP_TRY(pool_alloc(ctx, 2 * (size_t)b->P * 4, s, (void**)&b->d_bounds));
-  OLAP_TRY(partition_side(ctx, bk, nb, bits, b->pkb, b->pib, b->d_bounds, b->hb, sc, s, "hist_build", "partition_build"));
+  bool range_overflow = false;
+  OLAP_TRY(partition_side(ctx, bk, nb, bits, b->pkb, b->pib, b->d_bounds, b->hb, sc, s, "hist_build", "partition_build",
+                          b->range.rrange ? &b->range : nullptr, &range_overflow));
+  if (range_overflow) return OLAP_ERR_INTERNAL_RETRY;
   b->max_part = 0;
   for (uint32_t p = 0; p < b->P; p++) b->max_part = std::max<uint64_t>(b->max_part, b->hb[b->P + p] - b->hb[p]);
   return OLAP_OK;
@@ -907,13 +1073,17 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   OLAP_TRY(sc.get<uint32_t>(rows + 8, &pip));
   OLAP_TRY(sc.get<uint32_t>(2 * (uint64_t)P, &d_pb));
   std::vector<uint32_t> hp;
-  OLAP_TRY(partition_side(ctx, pk, np, bits, pkp, pip, d_pb, hp, sc, s, "hist_probe", "partition_probe"));
+  const bool direct = b.range.rrange != 0;
+  bool range_overflow = false;
+  OLAP_TRY(partition_side(ctx, pk, np, bits, pkp, pip, d_pb, hp, sc, s, "hist_probe", "partition_probe", direct ? &b.range : nullptr, &range_overflow));
+  if (range_overflow) return OLAP_ERR_INTERNAL_RETRY;
   const uint32_t* hb = b.hb.data();
   const uint32_t load_pct = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(env_u64("OLAP_JOIN_LOAD", 100), 50), 400);
-  const uint64_t nbk = table_buckets((uint32_t)b.max_part, load_pct);  // buckets per table slot, sized for the largest partition
-  auto work = [&](uint32_t p) { return part_work(hb[p], hb[P + p], hp[p], hp[P + p], load_pct); };
+  const uint32_t direct_entries = direct ? (1u << b.range.rshift) : 0;  // direct tables: one 4-byte row id per key of the range
+  const uint64_t nbk = direct ? direct_entries / 8 : table_buckets((uint32_t)b.max_part, load_pct);  // 32-byte units per table slot
+  auto work = [&](uint32_t p) { return part_work(hb[p], hb[P + p], hp[p], hp[P + p], load_pct, direct_entries); };
 
-  if (env_u64("OLAP_JOIN_PIPE", 1)) {
+  if (direct || env_u64("OLAP_JOIN_PIPE", 1)) {
     // the join pipeline: one persistent kernel over all partitions (see join_pipeline_kernel)
     PipeArgs pa;
     memset(&pa, 0, sizeof(pa));
@@ -932,6 +1102,12 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     pa.waited = reinterpret_cast<unsigned long long*>(sync + ((1 + 3 * (uint64_t)P + 1) & ~1ULL));
     pa.bkeys = b.pkb; pa.bids = b.pib; pa.pkeys = pkp; pa.pids = pip; pa.bb = b.d_bounds; pa.pb = d_pb;
     pa.P = P; pa.bits = bits; pa.R = (uint32_t)R; pa.pid_base = pid_base; pa.load_pct = load_pct;
+    uint32_t* d_dup = nullptr;
+    if (direct) {
+      OLAP_TRY(sc.get<uint32_t>(1, &d_dup));
+      OLAP_CUDA(cudaMemsetAsync(d_dup, 0, 4, s));
+      pa.direct_entries = direct_entries; pa.rmin = (uint64_t)b.range.rmin; pa.dup = d_dup;
+    }
     pa.arena = (Bucket*)ctx->table_arena; pa.stride = nbk; pa.sync = sync;
     pa.out = out; pa.max_matches = max_matches; pa.count = d_count;
     uint64_t items = 0;
@@ -944,15 +1120,23 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     pa.step_start[P + 2] = (uint32_t)items;
     if (items) {
       int occ = 0;
-      OLAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, join_pipeline_kernel, kJoinThreads, 0));
+      if (direct) OLAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, join_pipeline_kernel<true>, kJoinThreads, 0));
+      else OLAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, join_pipeline_kernel<false>, kJoinThreads, 0));
       if (occ < 1) { set_error("join_pipeline_kernel does not fit on an SM"); return OLAP_ERR_CUDA; }
       const uint64_t grid = std::min<uint64_t>((uint64_t)occ * ctx->sm_count, items);
       pa.grid_dbg = (uint32_t)grid;
-      join_pipeline_kernel<<<(unsigned)grid, kJoinThreads, 0, s>>>(pa);
+      if (direct) join_pipeline_kernel<true><<<(unsigned)grid, kJoinThreads, 0, s>>>(pa);
+      else join_pipeline_kernel<false><<<(unsigned)grid, kJoinThreads, 0, s>>>(pa);
       count_launch(ctx, 2);
     }
     phase_mark(ctx, s, "build_probe");
     OLAP_CUDA(cudaGetLastError());
+    if (direct) {  // a repeated build key cannot live in a direct table: the caller redoes the join with bucket tables
+      uint32_t dup = 0;
+      OLAP_CUDA(cudaMemcpyAsync(&dup, d_dup, 4, cudaMemcpyDeviceToHost, s));
+      OLAP_CUDA(cudaStreamSynchronize(s));
+      if (dup) return OLAP_ERR_INTERNAL_RETRY;
+    }
     if (env_u64("OLAP_JOIN_DEBUG", 0) & 8) {
       unsigned long long w[6];
       OLAP_CUDA(cudaMemcpyAsync(w, pa.waited, sizeof(w), cudaMemcpyDeviceToHost, s));
@@ -1092,9 +1276,26 @@ olap_status olap_hash_join_i64(olap_ctx* ctx, const int64_t* build_keys, uint64_
   BuildSide b;
   olap_status st = OLAP_OK;
   if (n_build && n_probe) {  // executor.rs:231-233: an empty side yields no rows
-    st = build_side_prepare(ctx, (const uint64_t*)build_keys, n_build, strategy, s, &b);
-    if (st == OLAP_OK) st = build_side_probe(b, (const uint64_t*)probe_keys, n_probe, 0, out_pairs, max_matches, d_count, s);
-    build_side_free(b, s);
+    bool done = false;
+    if (strategy == OLAP_JOIN_RADIX && n_build >= (1u << 20) && env_u64("OLAP_JOIN_DIRECT", 1)) {
+      // dense build keys?  (a 1 GB read at C2: 0.2 ms)  Then try direct-address tables; a duplicate key or very uneven key
+      // ranges send the join back to the general path below.
+      KeyRange r;
+      st = detect_dense_keys(ctx, (const uint64_t*)build_keys, n_build, s, &r);
+      if (st == OLAP_OK && r.rrange) {
+        b.range = r;
+        st = build_side_prepare(ctx, (const uint64_t*)build_keys, n_build, strategy, s, &b);
+        if (st == OLAP_OK) st = build_side_probe(b, (const uint64_t*)probe_keys, n_probe, 0, out_pairs, max_matches, d_count, s);
+        build_side_free(b, s);
+        if (st == OLAP_ERR_INTERNAL_RETRY) { st = OLAP_OK; b = BuildSide(); OLAP_CUDA(cudaMemsetAsync(d_count, 0, 8, s)); }
+        else done = true;
+      }
+    }
+    if (!done && st == OLAP_OK) {
+      st = build_side_prepare(ctx, (const uint64_t*)build_keys, n_build, strategy, s, &b);
+      if (st == OLAP_OK) st = build_side_probe(b, (const uint64_t*)probe_keys, n_probe, 0, out_pairs, max_matches, d_count, s);
+      build_side_free(b, s);
+    }
   }
   phase_end(ctx, s);
   OLAP_TRY(st);

@@ -235,6 +235,27 @@ def test_join_tile_boundaries_in_both_partition_layouts(ctx, alloc, part_rows, m
         check_join(ctx, b, p, 0)
 
 
+@pytest.mark.timeout(300)
+def test_join_direct_address_tables_and_their_fallbacks(ctx):
+    # >= 2^20 build rows with a dense key range take the direct-address path (row_id[key - min] per key range); a repeated
+    # build key, or a probe side whose key ranges are very uneven, sends the join back to the bucket tables.  Same match set.
+    rng = np.random.default_rng(23)
+    nb, npb = (1 << 20) + 321, (1 << 21) + 77
+    perm = rng.permutation(nb).astype(np.int64)
+    cases = {
+        "dense unique, negative minimum": (perm - 500_000, rng.integers(-600_000, nb - 400_000, npb).astype(np.int64)),
+        "unique with holes (range = 3 x rows), probes in the holes and outside": (perm * 3 + 7, rng.integers(-50, 3 * nb + 100, npb).astype(np.int64)),
+        "dense with duplicates -> bucket tables": (rng.integers(0, nb, nb).astype(np.int64), rng.integers(0, nb, npb // 2).astype(np.int64)),
+        "one hot probe key -> uneven key ranges -> bucket tables": (perm, np.where(rng.random(npb) < 0.7, 12345, rng.integers(0, nb, npb)).astype(np.int64)),
+    }
+    for name, (b, p) in cases.items():
+        db, dp = dev(ctx, b), dev(ctx, p)
+        exp_c, exp_pairs = O.hash_join_i64(b, p, threads=8)
+        cnt, pairs = ctx.hash_join_i64(db, len(b), dp, len(p), max_matches=max(exp_c, 1), strategy=0)
+        assert cnt == exp_c, name
+        assert (O.sort_pairs(pairs.to_numpy(2 * cnt).reshape(-1, 2)) == O.sort_pairs(exp_pairs)).all(), name
+
+
 @pytest.mark.parametrize("bits", [1, 4, 8])
 def test_radix_partition_unit(ctx, bits):
     import gpu_olap_engine_b200 as g
