@@ -809,7 +809,7 @@ __device__ __forceinline__ void pipe_signal(uint32_t* counter) {
 }
 
 template <bool DIRECT>
-__global__ void __launch_bounds__(kJoinThreads, DIRECT ? 5 : 4) join_pipeline_kernel(const __grid_constant__ PipeArgs a) {
+__global__ void __launch_bounds__(kJoinThreads, DIRECT ? 6 : 4) join_pipeline_kernel(const __grid_constant__ PipeArgs a) {
   __shared__ ProbeShared sh;
   __shared__ uint32_t s_ticket;
   const int tid = threadIdx.x;
