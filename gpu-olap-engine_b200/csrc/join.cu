@@ -1129,7 +1129,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
       else join_pipeline_kernel<false><<<(unsigned)grid, kJoinThreads, 0, s>>>(pa);
       count_launch(ctx, 2);
     }
-    phase_mark(ctx, s, "build_probe");
+    phase_mark(ctx, s, direct ? "build_probe_direct" : "build_probe");
     OLAP_CUDA(cudaGetLastError());
     if (direct) {  // a repeated build key cannot live in a direct table: the caller redoes the join with bucket tables
       uint32_t dup = 0;

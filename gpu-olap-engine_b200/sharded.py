@@ -570,7 +570,7 @@ def bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, Cloc
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
-        bp_ms = phases.get("build_probe")      # rank 0's local join_pipeline_kernel (last step)
+        bp_ms = phases.get("build_probe_direct") or phases.get("build_probe")      # rank 0's local join_pipeline_kernel (last step)
         bp_bytes = 12.0 * (res["n_build_local"] + res["n_probe_local"]) + 8.0 * res["count"]
         achieved = bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms else None
         line = {
