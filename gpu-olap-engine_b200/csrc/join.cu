@@ -917,13 +917,13 @@ static void launch_probe(olap_ctx* ctx, const uint64_t* keys, const uint32_t* id
 // Radix-partition (key, row id) of one side of the join.  out_keys / out_ids must hold side_rows_cap(n, bits) rows.  First choice
 // is the one-pass ALLOC layout; if a region overflows (heavy hitters) the exact histogram layout is used instead.
 // d_bounds / h_bounds: [2P], rows of partition p are [x[p], x[P + p]).
-static uint64_t side_rows_cap(uint64_t n, int bits) {
+static uint64_t side_rows_cap(uint64_t n, int bits, uint32_t used_parts = 0) {
   const uint32_t P = 1u << bits;
-  const uint64_t cap = alloc_capacity(n, P);
+  const uint64_t cap = alloc_capacity(n, used_parts ? used_parts : P);  // key ranges: only `used_parts` of the P regions receive rows
   return std::max<uint64_t>(n, (uint64_t)P * cap);
 }
 
-struct KeyRange { int64_t rmin = 0; uint64_t rrange = 0; int rshift = 0; };  // rrange > 0: partition by key range (direct-address join)
+struct KeyRange { int64_t rmin = 0; uint64_t rrange = 0; int rshift = 0; uint32_t used = 0; };  // rrange > 0: partition by key range (direct-address join); used = ranges that can hold rows (<= P, P is rounded up to a power of two)
 
 static olap_status partition_side(olap_ctx* ctx, const uint64_t* keys, uint64_t n, int bits, uint64_t* out_keys, uint32_t* out_ids,
                                   uint32_t* d_bounds, std::vector<uint32_t>& h_bounds, Scratch& sc, cudaStream_t s, const char* hist_mark,
@@ -934,7 +934,7 @@ static olap_status partition_side(olap_ctx* ctx, const uint64_t* keys, uint64_t 
   memset(&a, 0, sizeof(a));
   a.bits = bits; a.keys = keys; a.n = n; a.out_keys = out_keys; a.out_ids = out_ids;
   if (range) { a.rmin = range->rmin; a.rrange = range->rrange; a.rshift = range->rshift; }
-  const uint64_t cap = alloc_capacity(n, P);
+  const uint64_t cap = alloc_capacity(n, range ? range->used : P);
   if ((range || env_u64("OLAP_JOIN_ALLOC", 1)) && (uint64_t)P * cap < 0xFFFFFFFFULL) {
     uint32_t* cursor = nullptr;
     OLAP_TRY(sc.get<uint32_t>(P, &cursor));
@@ -1035,12 +1035,13 @@ static olap_status build_side_prepare(olap_ctx* ctx, const uint64_t* bk, uint64_
     while (((b->range.rrange + (1ULL << sh) - 1) >> sh) > (1ULL << kMaxPartBits)) sh++;
     b->range.rshift = sh;
     const uint64_t used = (b->range.rrange + (1ULL << sh) - 1) >> sh;
+    b->range.used = (uint32_t)used;
     bits = 1;
     while ((1ULL << bits) < used) bits++;
   }
   b->bits = bits; b->P = 1u << bits;
   Scratch sc(ctx, s);
-  const uint64_t rows = side_rows_cap(nb, bits);
+  const uint64_t rows = side_rows_cap(nb, bits, b->range.used);
   OLAP_TRY(pool_alloc(ctx, rows * 8 + 32, s, (void**)&b->pkb));
   OLAP_TRY(pool_alloc(ctx, rows * 4 + 32, s, (void**)&b->pib));
   OLAP_TRY(pool_alloc(ctx, 2 * (size_t)b->P * 4, s, (void**)&b->d_bounds));
@@ -1068,7 +1069,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   Scratch sc(ctx, s);
   uint64_t* pkp = nullptr;
   uint32_t *pip = nullptr, *d_pb = nullptr;
-  const uint64_t rows = side_rows_cap(np, bits);
+  const uint64_t rows = side_rows_cap(np, bits, b.range.used);
   OLAP_TRY(sc.get<uint64_t>(rows + 4, &pkp));
   OLAP_TRY(sc.get<uint32_t>(rows + 8, &pip));
   OLAP_TRY(sc.get<uint32_t>(2 * (uint64_t)P, &d_pb));
