@@ -77,3 +77,37 @@ def test_oracle_is_not_imported_by_the_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    # the POD structs that cross the C ABI: sizes and field offsets as gcc sees them in include/olap_b200.h must equal the
+    # ctypes mirrors the tests and the bench use
+    import ctypes as C
+    import subprocess
+    from gpu_olap_engine_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text(r"""
+#include <stddef.h>
+#include <stdio.h>
+#include "olap_b200.h"
+int main(void) {
+  printf("olap_filter_term %zu %zu %zu %zu %zu %zu\n", sizeof(olap_filter_term), offsetof(olap_filter_term, lhs), offsetof(olap_filter_term, rhs),
+         offsetof(olap_filter_term, literal_bits), offsetof(olap_filter_term, op), offsetof(olap_filter_term, type));
+  printf("olap_agg_spec %zu %zu %zu %zu\n", sizeof(olap_agg_spec), offsetof(olap_agg_spec, values), offsetof(olap_agg_spec, func),
+         offsetof(olap_agg_spec, value_type));
+  printf("olap_expr_prog %zu %zu %zu %zu %zu\n", sizeof(olap_expr_prog), offsetof(olap_expr_prog, n_ops), offsetof(olap_expr_prog, op),
+         offsetof(olap_expr_prog, column), offsetof(olap_expr_prog, literal_bits));
+  printf("olap_pair %zu %d\n", sizeof(olap_pair), OLAP_PROG_MAX_OPS);
+  return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = {ln.split()[0]: [int(x) for x in ln.split()[1:]] for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()}
+    ft, ag, pr = _lib.FilterTerm, _lib.AggSpec, _lib.ExprProg
+    assert got["olap_filter_term"] == [C.sizeof(ft), ft.lhs.offset, ft.rhs.offset, ft.literal_bits.offset, ft.op.offset, ft.type.offset]
+    assert got["olap_agg_spec"] == [C.sizeof(ag), ag.values.offset, ag.func.offset, ag.value_type.offset]
+    assert got["olap_expr_prog"] == [C.sizeof(pr), pr.n_ops.offset, pr.op.offset, pr.column.offset, pr.literal_bits.offset]
+    assert got["olap_pair"] == [8, _lib.PROG_MAX_OPS]
+
