@@ -9,6 +9,8 @@ import oracle as O
 def test_reference_filter_vector():
     # gpu-olap-core/src/executor.rs:553-570: [5, 15, 25] > 10 -> [false, true, true]
     assert O.filter_mask_i64([5, 15, 25], O.GT, literal=10).tolist() == [0, 1, 1]
+    f = _golden("reference_test_vectors.json")["filter"]
+    assert O.filter_mask_i64(f["values"], O.GT, literal=f["literal"]).tolist() == f["mask"]
 
 
 def test_filter_ops_and_unknown_op():
@@ -35,11 +37,17 @@ def test_identity_values():
     assert L.orc_identity_value(O.MIN) == 2**63 - 1 and L.orc_identity_value(O.MAX) == -2**63
 
 
-HASH32 = [(0, 0x00000000), (1, 0x514e28b7), (2, 0x30f4c306), (42, 0x087fcd5c), (-1, 0x81f16f39), (0x7fffffff, 0xf9cc0ea8),
-          (-2**31, 0x6d3c65a0), (123456789, 0xba60d89a)]
-HASH64 = [(0, 0x00000000), (1, 0x514e28b7), (2, 0x30f4c306), (42, 0x087fcd5c), (-1, 0x00000000), (2**32, 0x514e28b7),
-          (2**32 + 1, 0x00000000), (0x0123456789abcdef, 0x1d6ef8ae), (-2**63, 0x6d3c65a0), (2**63 - 1, 0x6d3c65a0),
-          (1000000, 0x02409889)]
+def _golden(name):
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)) as f:
+        return json.load(f)
+
+
+# tests/golden/reference_test_vectors.json: the known-answer vectors of the reference (file:line cited inside)
+_REF = _golden("reference_test_vectors.json")
+HASH32 = [tuple(v) for v in _REF["hash_int32"]["vectors"]]
+HASH64 = [tuple(v) for v in _REF["hash_int64"]["vectors"]]
 
 
 def test_reference_hash_vectors():
@@ -48,7 +56,7 @@ def test_reference_hash_vectors():
         assert O.hash_int32(k) == e
     for k, e in HASH64:
         assert O.hash_int64(k) == e
-    assert (O.partition_id(1), O.partition_id(2), O.partition_id(42)) == (183, 6, 92)
+    assert [[k, O.partition_id(k)] for k, _ in _REF["partition_ids"]["vectors"]] == _REF["partition_ids"]["vectors"]
 
 
 def test_reference_partition_skew_on_dense_keys():
@@ -176,3 +184,46 @@ def test_generators_are_counter_based_and_bijective():
         assert (np.sort(p) == np.arange(dom)).all()
     d = O.gen_dyadic_f64(1000, 6, 1 << 20)
     assert (d * 1024 == np.round(d * 1024)).all()
+
+
+# ------------------------------------------------------------------------------------------------- fixtures from the reference itself
+def _ref_fixtures():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_kernels.json")) as f:
+        return json.load(f)
+
+
+def test_oracle_matches_the_reference_kernels_own_outputs():
+    """tests/golden/ref_kernels.json holds what the reference's CUDA kernels (join_kernels.cuh, built unmodified into
+    oracle/_ref) produced on a B200 for seeded inputs (tests/golden/make_ref_fixtures.py).  The oracle must reproduce every
+    one of them on the CPU: hashes, partition sizes and membership, join counts and pair sets, direct-address sums."""
+    fx = _ref_fixtures()
+    assert [O.hash_int64(k) for k in fx["hash_int64"]["keys"]] == fx["hash_int64"]["hashes"]
+    assert [O.hash_int32(k) for k in fx["hash_int32"]["keys"]] == fx["hash_int32"]["hashes"]
+    begin, _, _ = O.radix_partition_i64(np.arange(1 << 20, dtype=np.int64))
+    assert begin.tolist() == fx["partition_dense_2p20"]["begin"]
+    sizes = np.diff(np.asarray(fx["partition_dense_2p20"]["begin"]))
+    assert (sizes.min(), sizes.max()) == (3935, 4279)            # SURVEY.md 8(c): +-4 % skew of the reference hash on dense keys
+    pr = fx["partition_random"]
+    keys = O.gen_uniform_i64(pr["n"], pr["seed"], pr["domain"])
+    begin, _, ids = O.radix_partition_i64(keys)
+    assert begin.tolist() == pr["begin"]
+    part_of_row = np.empty(pr["n"], np.int32)
+    for p in range(256):
+        part_of_row[ids[begin[p]:begin[p + 1]]] = p
+    assert part_of_row[:200].tolist() == pr["partition_of_first_200_rows"]
+    for j in fx["joins"]:
+        b = O.gen_uniform_i64(j["nb"], j["seed_build"], j["domain"]); p = O.gen_uniform_i64(j["np"], j["seed_probe"], j["domain"])
+        c, pairs = O.hash_join_i64(b, p)
+        assert c == j["count"]
+        sp = O.sort_pairs(pairs)
+        chk = [int(sp[:, 0].astype(np.uint64).sum()), int(sp[:, 1].astype(np.uint64).sum()),
+               int((sp[:, 0].astype(np.uint64) * 1000003 + sp[:, 1].astype(np.uint64)).sum() % (1 << 61))]
+        assert chk == j["pairs_checksum"] and sp[:20].tolist() == j["first_pairs"]
+    assert fx["join_truncation"] == {"count": 1000, "pairs_written": 10}   # join_kernels.cuh:155-160: exact count, silent truncation
+    ha = fx["hash_aggregate_sum"]
+    gk = O.gen_uniform_i64(ha["n"], ha["seed_keys"], ha["groups"]).astype(np.uint32)
+    v = O.gen_uniform_i64(ha["n"], ha["seed_values"], 1 << 20).astype(np.uint64)
+    assert O.ref_hash_aggregate_u64(gk, v, ha["groups"]).tolist() == ha["sums"]
+
