@@ -629,7 +629,7 @@ __device__ __forceinline__ void probe_tile(ProbeShared& sh, const Bucket* __rest
 }
 
 // ------------------------------------------------------------------------------------------- direct-address tables
-// When the build keys are dense (max - min + 1 <= 4 x rows) and unique -- surrogate keys of a dimension table, the
+// When the build keys are dense (max - min + 1 <= 5 x rows) and unique -- surrogate keys of a dimension table, the
 // benchmark's permutation of 0..n-1 -- a partition's table is just row_id[key - min]: 4 bytes per key of the partition's key
 // range (2 MB instead of 16 MB at C2), ONE atomicExch per build row (it also detects a duplicate key, which sends the whole
 // join back to the bucket tables), no hash, no key compare, no continuation on the probe side.  Partitions are key RANGES
@@ -969,7 +969,8 @@ static olap_status partition_side(olap_ctx* ctx, const uint64_t* keys, uint64_t 
 constexpr olap_status OLAP_ERR_INTERNAL_RETRY = (olap_status)1000;  // never leaves this file
 
 // min / max of the build keys; r->rrange > 0 when they are dense enough for direct-address tables: the key range is at most
-// 4 x the rows (a direct table then takes <= 16 bytes per build row, half of the bucket table) and fits 32-bit offsets
+// 5 x the rows (a direct table then takes <= 20 bytes per build row against 32 for the bucket table; 5 rather than 4 so that a
+// rank holding a quarter of a dense global domain qualifies whatever its exact row count) and fits 32-bit offsets
 static olap_status detect_dense_keys(olap_ctx* ctx, const uint64_t* keys, uint64_t n, cudaStream_t s, KeyRange* r) {
   Scratch sc(ctx, s);
   long long* d = nullptr;
@@ -985,7 +986,7 @@ static olap_status detect_dense_keys(olap_ctx* ctx, const uint64_t* keys, uint64
   phase_mark(ctx, s, "minmax");
   const uint64_t span = (uint64_t)mm[1] - (uint64_t)mm[0];  // max - min, exact in unsigned arithmetic
   *r = KeyRange();
-  if (mm[1] >= mm[0] && span < 0xFFFFFFF0ULL && span + 1 <= 4 * n) { r->rmin = mm[0]; r->rrange = span + 1; }
+  if (mm[1] >= mm[0] && span < 0xFFFFFFF0ULL && span + 1 <= 5 * n) { r->rmin = mm[0]; r->rrange = span + 1; }
   return OLAP_OK;
 }
 

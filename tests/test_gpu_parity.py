@@ -245,6 +245,7 @@ def test_join_direct_address_tables_and_their_fallbacks(ctx):
     cases = {
         "dense unique, negative minimum": (perm - 500_000, rng.integers(-600_000, nb - 400_000, npb).astype(np.int64)),
         "unique with holes (range = 3 x rows), probes in the holes and outside": (perm * 3 + 7, rng.integers(-50, 3 * nb + 100, npb).astype(np.int64)),
+        "a quarter of a dense domain (range = 4 x rows), as a rank of a 4-GPU join sees it": (perm * 4 + 1, rng.integers(0, 4 * nb + 8, npb).astype(np.int64)),
         "dense with duplicates -> bucket tables": (rng.integers(0, nb, nb).astype(np.int64), rng.integers(0, nb, npb // 2).astype(np.int64)),
         "one hot probe key -> uneven key ranges -> bucket tables": (perm, np.where(rng.random(npb) < 0.7, 12345, rng.integers(0, nb, npb)).astype(np.int64)),
     }
