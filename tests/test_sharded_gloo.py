@@ -74,6 +74,21 @@ def _worker(rank, world, port, q):
         assert dest <= {rank}
         gathered = [None] * world
         dist.all_gather_object(gathered, pairs)
+        # ---- exchange_regions(skip_self, prefix): the own region stays in place, the received rows of every column start at the
+        # same 4-row-aligned base, column 1 carries the own ids in front (what the overlapped join indexes its pairs against)
+        pk, pid, begin, count = ops.shuffle_partition(torch.from_numpy(gp[rank * npb:(rank + 1) * npb].copy()), npb, sj.x.bits)
+        own = pid[begin[rank]:begin[rank] + count[rank]]
+        (rk, ri), segs = sj.x.exchange_regions([pk, pid], begin, count, skip_self=True, prefix=[None, own])
+        base = (count[rank] + 3) & ~3
+        assert segs[0] == (rank, base) and sum(c for _, c in segs[1:]) == rk.numel() - base == ri.numel() - base
+        assert (ri[:count[rank]] == own).all()
+        peer = 1 - rank
+        peer_rows = gp[peer * npb:(peer + 1) * npb]
+        got_keys = rk[base:].numpy(); got_ids = ri[base:].numpy()
+        assert all(src != rank or c == 0 for src, c in segs[1:])                 # nothing was sent to oneself
+        assert (peer_rows[got_ids] == got_keys).all()                            # every received (key, id) is a row of the peer
+        assert all(ops.lib.olap_shuffle_dest_of(int(k), sj.x.bits) == rank for k in got_keys)
+        assert len(got_keys) == sum(1 for k in peer_rows if ops.lib.olap_shuffle_dest_of(int(k), sj.x.bits) == rank)
         # ---- group-by with AVG / MIN / MAX / COUNT over sharded rows
         n = 5000
         k = O.gen_uniform_i64(n * world, 4, 300); v = O.gen_uniform_i64(n * world, 5, 1 << 20); f = O.gen_dyadic_f64(n * world, 6, 1 << 20)
