@@ -292,7 +292,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "join_pipeline_kernel<%s> (one persistent launch per step: clear + build + probe of all partitions' L2-resident tables)" % ("direct" if direct else "buckets"),
                      "achieved": bp_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": (bp_gbs / peak) if bp_gbs else None,
-                     "traffic": traffic.get("join_pipeline_dram_bytes_per_launch"), "algorithmic_bytes_per_launch": bp_bytes, "ms_per_launch": bp_ms,
+                     "traffic": traffic.get("join_pipeline_dram_bytes_per_launch" if direct else "join_pipeline_buckets_dram_bytes_per_launch"), "algorithmic_bytes_per_launch": bp_bytes, "ms_per_launch": bp_ms,
                      "note": "bound by L2 sector requests (one table gather per probe row, one atomic per build row), not by HBM: DESIGN.md section 4"},
         "roofline_partition": {"bound": "hbm", "kernel": "partition_kernel<0,true,true> (probe side; second largest launch)",
                                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
