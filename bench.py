@@ -152,47 +152,209 @@ def run_ours(args):
         from gpu_olap_engine_b200 import sharded
         return sharded.bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, ClockSampler)
 
-    nb, npb = 1 << args.log2_build, 1 << args.log2_probe
-    rows = nb + npb
-    # build keys = permutation of [0, 2^27) (unique), probe = uniform FK over the build domain, seed 3
-    dbuild = ctx.generate(nb, 1, 3, nb)
-    dprobe = ctx.generate(npb, 0, 33, nb)
-    pairs = ctx.alloc(2 * npb, np.uint32)
-    ctx.synchronize()
+    return bench_single(ctx, g, args, local_rank, peak, peak_kind)
 
+
+# Algorithmic bytes per row of every phase the join can run: what the kernel must read + write once.
+#   smem direct path: rows travel as one packed 8-byte word {key - min, row id}
+#   bucket / L2-direct path: 8-byte key + 4-byte id
+PHASE_BYTES = {
+    "minmax": ("key_minmax_kernel", lambda nb, npb, c: 8.0 * nb),
+    "partition_build_coarse": ("rpart_kernel<raw> (build side, 64-range coarse regions)", lambda nb, npb, c: 16.0 * nb),
+    "partition_build": ("rpart_kernel<regions> (build side, ranges of 2^15 keys)", lambda nb, npb, c: 16.0 * nb),
+    "partition_probe_coarse": ("rpart_kernel<raw> (probe side, 64-range coarse regions)", lambda nb, npb, c: 16.0 * npb),
+    "partition_probe": ("rpart_kernel<regions> (probe side, ranges of 2^15 keys)", lambda nb, npb, c: 16.0 * npb),
+    "build_probe_smem": ("djoin_kernel (build + probe of every key range in a 128 KB shared-memory table)", lambda nb, npb, c: 8.0 * (nb + npb) + 8.0 * c),
+    "build_probe_direct": ("join_pipeline_kernel<direct> (L2-resident row-id tables)", lambda nb, npb, c: 12.0 * (nb + npb) + 8.0 * c),
+    "build_probe": ("join_pipeline_kernel<buckets> (L2-resident two-slot bucket tables)", lambda nb, npb, c: 12.0 * (nb + npb) + 8.0 * c),
+}
+GENERAL_PHASE_BYTES = {
+    "partition_build": ("partition_kernel (build side, 256 hash partitions)", lambda nb, npb, c: 20.0 * nb),
+    "partition_probe": ("partition_kernel (probe side, 256 hash partitions)", lambda nb, npb, c: 20.0 * npb),
+}
+
+
+def load_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def kernel_rooflines(phases, table, nb, npb, count, peak, traffic):
+    out = []
+    for name, ms in phases.items():
+        ent = table.get(name) or PHASE_BYTES.get(name)
+        if not ent or not ms:
+            continue
+        by = ent[1](nb, npb, count)
+        gbs = by / (ms * 1e-3) / 1e9
+        out.append({"phase": name, "kernel": ent[0], "ms_per_launch": ms, "algorithmic_bytes_per_launch": by, "achieved": gbs, "frac": gbs / peak,
+                    "traffic": traffic.get(name)})
+    out.sort(key=lambda r: -r["ms_per_launch"])
+    return out
+
+
+def timed_join(ctx, g, torch, stream, dbuild, nb, dprobe, npb, pairs, steps, warmup, expect=None):
     def step():
         c, _ = ctx.hash_join_i64(dbuild, nb, dprobe, npb, max_matches=npb, strategy=g.JOIN_RADIX, out_pairs=pairs)
         return c
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         cnt = step()
-    assert cnt == npb or os.environ.get("OLAP_JOIN_DEBUG"), f"join count {cnt} != {npb}"
-    sampler = ClockSampler(local_rank)
-    stream = torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 0))  # the stream the kernels launch on
+    assert expect is None or cnt == expect, f"join count {cnt} != {expect}"
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase_acc = {}
     launches0 = ctx.launch_count()
     torch.cuda.synchronize()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
         for k, v in ctx.last_phase_times().items():
             phase_acc[k] = phase_acc.get(k, 0.0) + v
     ev1.record(stream)
     torch.cuda.synchronize()
-    launches = ctx.launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    ms_step = ms_total / args.steps
+    ms_step = ev0.elapsed_time(ev1) / steps
+    return ms_step, {k: v / steps for k, v in phase_acc.items() if k != "end"}, (ctx.launch_count() - launches0), cnt
+
+
+class _DevView:
+    """A device buffer of the library as a zero-copy torch tensor (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def dev_view(torch, buf, n, typestr="<i8"):
+    return torch.as_tensor(_DevView(buf.ptr, n, typestr), device="cuda")
+
+
+def fk_probe_keys(torch, build_view, out_view, zipf, seed):
+    """Probe-side foreign keys: build row r's key, r ~ uniform (zipf = 0) or r + 1 ~ Zipf(s) over the build rows (continuous
+    inverse-CDF sampler).  The build keys are a pseudo-random permutation, so hot ranks map to keys spread over the domain
+    ("mapped through a fixed permutation")."""
+    nb, n = build_view.numel(), out_view.numel()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
+    step = 1 << 27
+    for a in range(0, n, step):
+        m = min(step, n - a)
+        if zipf <= 0:
+            r = torch.randint(0, nb, (m,), device="cuda", generator=gen)
+        else:
+            u = torch.rand(m, dtype=torch.float64, device="cuda", generator=gen)
+            if abs(zipf - 1.0) < 1e-9:
+                r = torch.exp(u * torch.log(torch.tensor(float(nb), dtype=torch.float64, device="cuda")))
+            else:
+                e = 1.0 - zipf
+                r = ((float(nb) ** e - 1.0) * u + 1.0) ** (1.0 / e)
+            r = (r.to(torch.int64) - 1).clamp_(0, nb - 1)
+        out_view[a:a + m] = build_view[r]
+
+
+def bench_group_by(ctx, g, args, torch, stream, peak, peak_kind):
+    """BASELINE config 3: hash group-by SUM/COUNT/MIN/MAX over 2^log2_gb_rows rows, cardinality sweep.  Device-resident inputs,
+    CUDA events on the launching stream; rows/s = input rows / time; roofline on 16 B/row + 40 B per group."""
+    import ctypes as C
+    import numpy as np
+    from gpu_olap_engine_b200._lib import AggSpec, check
+    n = 1 << args.log2_gb_rows
+    vals = ctx.generate(n, 0, 5, 1 << 20)          # i64 uniform [0, 2^20): SUM < 2^50 stays exact
+    keys = ctx.alloc(n, np.int64)
+    out = []
+    for G in [int(float(x)) for x in args.gb_groups.split(",")]:
+        ctx.generate(n, 0, 4, G, out=keys)
+        aggs = [(g.SUM, vals, g.I64), (g.COUNT, vals, g.I64), (g.MIN, vals, g.I64), (g.MAX, vals, g.I64)]
+        cap = min(G, n)
+        ok = ctx.alloc(cap, np.int64); oa = ctx.alloc(4 * cap, np.uint64)
+        specs = (AggSpec * 4)(*[AggSpec(v.ptr, f, t) for f, v, t in aggs])
+
+        def run():
+            gg = C.c_uint64()
+            check(ctx.lib.olap_group_by_i64(ctx.handle, keys.ptr, specs, 4, n, G, None, 0, ok.ptr, oa.ptr, cap, None, C.byref(gg), None))
+            return gg.value
+        for _ in range(3):
+            ng = run()
+        launches0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record(stream)
+        for _ in range(args.gb_steps):
+            ng = run()
+        e1.record(stream); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.gb_steps
+        # parity inside the bench: COUNT sums to n, SUM equals the column sum, group count = distinct keys
+        assert int(dev_view(torch, oa, 4 * cap)[cap:cap + ng].sum()) == n, "group-by COUNT does not add up"
+        by = 16.0 * n + 40.0 * ng
+        out.append({"groups_hint": G, "groups_found": int(ng), "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "rows/s",
+                    "roofline": {"bound": "hbm", "achieved": by / (ms * 1e-3) / 1e9, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                                 "frac": by / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": by},
+                    "phases_ms": {k: v for k, v in ctx.last_phase_times().items() if k != "end"},
+                    "gpu_launches_per_step": (ctx.launch_count() - launches0) / args.gb_steps})
+        del ok, oa
+    del keys, vals
+    return {"op": f"hash group-by SUM/COUNT/MIN/MAX, i64 keys uniform in [0, G), i64 values, 2^{args.log2_gb_rows} rows", "steps": args.gb_steps,
+            "warmup": 3, "sweep": out}
+
+
+def cpu_reference_group_by(log2_rows, G, threads):
+    import numpy as np
+    import oracle as O
+    n = 1 << log2_rows
+    k = O.gen_uniform_i64(n, 4, G); v = O.gen_uniform_i64(n, 5, 1 << 20)
+    t0 = time.perf_counter()
+    keys, res = O.group_by_i64(k, [v, v, v, v], [O.SUM, O.COUNT, O.MIN, O.MAX], threads=threads)
+    dt = time.perf_counter() - t0
+    assert int(res[1].sum()) == n
+    return n / dt, dt
+
+
+def bench_single(ctx, g, args, local_rank, peak, peak_kind):
+    import ctypes as C
+    import numpy as np
+    import torch
+    nb, npb = 1 << args.log2_build, 1 << args.log2_probe
+    rows = nb + npb
+    traffic = load_traffic()
+    stream = torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 0))  # the stream the kernels launch on
+    # SURVEY.md 8(d) C2: build keys = permutation of [0, 2^27) (unique), probe = uniform FK over the build domain, seed 3
+    dbuild = ctx.generate(nb, 1, 3, nb)
+    if args.zipf > 0:
+        dprobe = ctx.alloc(npb, np.int64)
+        ctx.synchronize()
+        fk_probe_keys(torch, dev_view(torch, dbuild, nb), dev_view(torch, dprobe, npb), args.zipf, 33)
+        torch.cuda.synchronize()
+    else:
+        dprobe = ctx.generate(npb, 0, 33, nb)
+    pairs = ctx.alloc(2 * npb, np.uint32)
+    ctx.synchronize()
+    sampler = ClockSampler(local_rank)
+    ms_step, phases, launches, cnt = timed_join(ctx, g, torch, stream, dbuild, nb, dprobe, npb, pairs, args.steps, args.warmup, expect=npb)
     value = rows / (ms_step * 1e-3)
-    phases = {k: v / args.steps for k, v in phase_acc.items()}
+    # every pair of the last timed step, checked on the device: each probe row exactly once, equal keys
+    verify_pairs(torch, dbuild, dprobe, pairs, nb, npb, cnt)
 
     if args.skip_e2e or args.skip_cpu:
         clocks = sampler.stop()
         print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": ms_step, "phases_ms": phases, "gpu_launches": int(launches),
                           "clocks": clocks}))
         return 0
+
+    # ---- the general path: sparse build keys (2^27 unique keys of a 2^33 domain) take hash partitions + bucket tables
+    general = None
+    if not args.skip_general:
+        gb_ = ctx.generate(nb, 1, 7, 1 << 33)                      # permutation of [0, 2^33) evaluated at rows 0..nb-1: unique, sparse
+        gp_ = ctx.alloc(npb, np.int64)
+        ctx.synchronize()
+        fk_probe_keys(torch, dev_view(torch, gb_, nb), dev_view(torch, gp_, npb), 0.0, 34)   # FK: the key of a uniformly drawn build row
+        torch.cuda.synchronize()
+        gms, gph, gl, gcnt = timed_join(ctx, g, torch, stream, gb_, nb, gp_, npb, pairs, max(2, args.steps // 2), 3, expect=npb)
+        verify_pairs(torch, gb_, gp_, pairs, nb, npb, gcnt)
+        general = {"value": rows / (gms * 1e-3), "unit": "rows/s", "ms_per_step": gms, "phases_ms": gph,
+                   "workload": f"same sizes, build keys = 2^{args.log2_build} unique keys of a 2^33 domain (sparse: hash partitions + two-slot bucket tables in L2)",
+                   "kernels": kernel_rooflines(gph, GENERAL_PHASE_BYTES, nb, npb, gcnt, peak, {}),
+                   "job_roofline_frac": (8.0 * rows + 8.0 * gcnt) / (gms * 1e-3) / 1e9 / peak}
+        del gb_, gp_
+
     # ---- e2e: host (pinned) buffers through the C-ABI, copies inside the timed region
-    import ctypes as C
     hb, hp, hout = C.c_void_p(), C.c_void_p(), C.c_void_p()
     g._lib.check(ctx.lib.olap_host_alloc(nb * 8, C.byref(hb)))
     g._lib.check(ctx.lib.olap_host_alloc(npb * 8, C.byref(hp)))
@@ -206,9 +368,6 @@ def run_ours(args):
     # reference executor's Vec<RecordBatch>); H2D of batch i+1, the join of batch i and D2H of batch i-1's pairs overlap
     # on three streams.  Everything -- every copy, every kernel -- is inside the timed region.
     n_batches = int(os.environ.get("OLAP_E2E_BATCHES", "8"))
-    e2e_strategy = g.JOIN_RADIX if os.environ.get("OLAP_E2E_STRATEGY") == "radix" else g.JOIN_BROADCAST
-    # batch streaming uses the single-table strategy: built once, nothing is rebuilt per batch (measured device-resident:
-    # 34 ms for 8 batches vs 59 ms when every batch re-builds the 256 L2-sized partition tables)
     bsz = npb // n_batches
     s_comp = torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 0))
     s_h2d = torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 4))
@@ -222,7 +381,7 @@ def run_ours(args):
             ev_p[i].record(s_h2d)
         s_comp.wait_event(ev_b)
         total = 0
-        with g.JoinBuild(ctx, db2, nb, e2e_strategy) as jb:
+        with g.JoinBuild(ctx, db2, nb, g.JOIN_RADIX) as jb:
             for i in range(n_batches):
                 s_comp.wait_event(ev_p[i])
                 c = jb.probe(dp2.ptr + 8 * i * bsz, bsz, probe_row_base=i * bsz, out_pairs=pairs.ptr + 8 * total, max_matches=npb - total)
@@ -240,32 +399,25 @@ def run_ours(args):
         c = e2e_step()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    clocks = sampler.stop()
-    # spot-check the host-visible result of the last e2e step
+    e2e_path = ",".join(k for k in ctx.last_phase_times() if k.startswith("build_probe"))
+    # the host-visible result of the last e2e step: every probe row exactly once, equal keys (all pairs, numpy on the host)
     out = np.ctypeslib.as_array(C.cast(hout, C.POINTER(C.c_uint32)), shape=(2 * npb,)).reshape(-1, 2)
     hbv = np.ctypeslib.as_array(C.cast(hb, C.POINTER(C.c_int64)), shape=(nb,))
     hpv = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_int64)), shape=(npb,))
-    sl = out[:: max(1, npb // 100000)]
+    sl = out[:: max(1, npb // (1 << 22))]
     assert c == npb and (hbv[sl[:, 0]] == hpv[sl[:, 1]]).all(), "e2e result check failed"
+    seen = np.zeros(npb, np.uint8); seen[out[:, 1]] = 1
+    assert int(seen.sum()) == npb, "e2e result check failed: a probe row is missing or repeated"
+    del seen, db2, dp2
 
-    # ---- roofline.  Dominant kernel by share of the step (profiles/r01_ncu_launches_*_summary.csv): join_pipeline_kernel,
-    # ONE persistent launch per step that clears, builds and probes the L2-resident tables of all partitions.  Algorithmic
-    # bytes per launch = partitioned (key 8 B + row id 4 B) of both sides read once + 8 B per pair written.  Its duration is
-    # the CUDA-event time between the marks around that launch inside the timed steps.  The second kernel (probe-side
-    # partition_kernel: reads 8 B key, writes 8 B key + 4 B row id per row) is reported next to it.
-    traffic = {}
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f)
-    except Exception:
-        pass
-    direct = "build_probe_direct" in phases   # dense unique build keys detected: direct-address tables instead of bucket tables
-    bp_ms = phases.get("build_probe_direct") or phases.get("build_probe")
-    bp_bytes = 12.0 * rows + 8.0 * npb
-    bp_gbs = bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms else None
-    part_ms = phases.get("partition_probe")
-    part_bytes = 20.0 * npb
-    achieved = part_bytes / (part_ms * 1e-3) / 1e9 if part_ms else None
+    # ---- group-by (the other half of BASELINE's metric), same process, same clocks record
+    group_by = None if args.skip_groupby else bench_group_by(ctx, g, args, torch, stream, peak, peak_kind)
+    clocks = sampler.stop()
+
+    # ---- roofline: every kernel of the step from the CUDA-event marks around it inside the timed steps; `roofline` = the one with
+    # the largest share of the step
+    kernels = kernel_rooflines(phases, PHASE_BYTES, nb, npb, cnt, peak, traffic)
+    top = kernels[0]
     job_bytes = 8.0 * rows + 8.0 * npb  # keys read once + pairs written once (the JoinParams contract)
 
     # ---- CPU baseline (oracle port of the reference CPU path) on a bounded sample, all host cores and single-thread
@@ -274,38 +426,62 @@ def run_ours(args):
     cpu1_rps, _, _ = cpu_reference_join(args.cpu_log2_build - 3, args.cpu_log2_probe - 3, 1)
     sample = (f"2^{args.cpu_log2_build} unique-key build x 2^{args.cpu_log2_probe} FK probe (same generator), pairs materialised, "
               f"{cores} threads, {cpu_sec:.2f} s; single-thread ref1 on an 8x smaller sample: {cpu1_rps / 1e6:.1f} M rows/s")
+    if group_by is not None:
+        gb_cpu = []
+        for G in (100, 100000):
+            r, sec = cpu_reference_group_by(args.cpu_log2_gb_rows, G, cores)
+            gb_cpu.append({"groups": G, "value": r, "unit": "rows/s", "seconds": sec})
+        group_by["cpu_baseline"] = {"kind": "port", "cores": cores, "sample": f"oracle orc_group_by_i64_mt on 2^{args.cpu_log2_gb_rows} rows of the same generator", "runs": gb_cpu}
 
+    direct = "build_probe_smem" in phases
     line = {
         "metric": "join rows/sec (|build|+|probe|)/time", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
-        "config": {"workload": f"single-GPU radix hash join 2^{args.log2_build} unique-key build x 2^{args.log2_probe} FK probe, int64 keys, uniform",
-                   "output": "(u32 build row, u32 probe row) pairs, all 2^%d materialised" % args.log2_probe,
+        "config": {"workload": f"single-GPU radix hash join 2^{args.log2_build} unique-key build x 2^{args.log2_probe} FK probe, int64 keys, " + (f"Zipf s = {args.zipf}" if args.zipf > 0 else "uniform (Zipf s = 0)"),
+                   "output": "(u32 build row, u32 probe row) pairs, all 2^%d materialised; every pair verified after the timed steps" % args.log2_probe,
                    "l2": "inputs (%.1f GB) are larger than the 126 MB L2; no flush needed" % (rows * 8 / 1e9),
                    "strategy": "RadixHashJoin",
-                   "tables": ("direct-address row-id tables per key range (dense, unique build keys detected at run time)" if direct
-                              else "two-slot bucket tables per hash partition")},
+                   "tables": ("direct-address row-id tables in shared memory, one per range of 2^15 keys (dense unique build keys: key range remembered per column, verified by the build pass)"
+                              if direct else "L2-resident tables (see phases_ms)")},
         "clocks": clocks,
         "e2e": {"value": rows / (e2e_ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": rows * 8, "d2h_bytes_per_step": npb * 8 + 8,
                 "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "how": "olap_join_build_create + 8 x olap_join_probe on pinned host buffers; H2D / join / D2H pipelined on 3 streams; wall clock"},
+                "how": f"olap_join_build_create(RADIX) + {n_batches} x olap_join_probe on pinned host buffers; H2D / join / D2H pipelined on 3 streams; wall clock; "
+                       f"join path of the batches: {e2e_path}; all pairs checked on the host"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "join_pipeline_kernel<%s> (one persistent launch per step: clear + build + probe of all partitions' L2-resident tables)" % ("direct" if direct else "buckets"),
-                     "achieved": bp_gbs, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": (bp_gbs / peak) if bp_gbs else None,
-                     "traffic": traffic.get("join_pipeline_dram_bytes_per_launch" if direct else "join_pipeline_buckets_dram_bytes_per_launch"), "algorithmic_bytes_per_launch": bp_bytes, "ms_per_launch": bp_ms,
-                     "note": "bound by L2 sector requests (one table gather per probe row, one atomic per build row), not by HBM: DESIGN.md section 4"},
-        "roofline_partition": {"bound": "hbm", "kernel": "partition_kernel<0,true,true> (probe side; second largest launch)",
-                               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                               "traffic": traffic.get("partition_probe_dram_bytes_per_launch"), "algorithmic_bytes_per_launch": part_bytes,
-                               "ms_per_launch": part_ms},
+        "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved"], "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                     "frac": top["frac"], "traffic": (top["traffic"] or {}).get("dram_bytes_per_launch") if isinstance(top["traffic"], dict) else top["traffic"],
+                     "traffic_source": "ncu --set full, one capture per kernel (profiles/traffic.json): static, not re-measured in this run",
+                     "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"], "ms_per_launch": top["ms_per_launch"],
+                     "share_of_step": top["ms_per_launch"] / ms_step},
+        "roofline_kernels": kernels,
         "job_roofline": {"algorithmic_bytes": job_bytes, "achieved_gbs": job_bytes / (ms_step * 1e-3) / 1e9,
                          "frac": job_bytes / (ms_step * 1e-3) / 1e9 / peak,
                          "note": "keys read once + pairs written once; SURVEY 8(d)'s 15.03 GB also counts payload columns the join never touches"},
         "phases_ms": phases,
+        "value_general": general,
+        "group_by": group_by,
         "cpu_baseline": {"value": cpu_rps, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
     }
     print(json.dumps(line))
     return 0
+
+
+def verify_pairs(torch, dbuild, dprobe, pairs, nb, npb, cnt):
+    """ALL pairs of a join, checked on the device (torch views of the library's buffers, outside every timed region):
+    build_key[left] == probe_key[right] for every pair, and no probe row appears twice (unique build keys: at most one match)."""
+    assert cnt <= npb
+    pr = dev_view(torch, pairs, 2 * cnt, "<u4").view(torch.int32).view(-1, 2)
+    bk, pk = dev_view(torch, dbuild, nb), dev_view(torch, dprobe, npb)
+    seen = torch.zeros(npb, dtype=torch.uint8, device="cuda")
+    step = 1 << 26
+    for a in range(0, cnt, step):
+        l = pr[a:a + step, 0].to(torch.int64) & 0xFFFFFFFF
+        r = pr[a:a + step, 1].to(torch.int64) & 0xFFFFFFFF
+        assert bool((bk[l] == pk[r]).all()), "join pairs: build_key[left] != probe_key[right]"
+        seen[r] = 1
+    assert int(seen.sum(dtype=torch.int64)) == cnt, "join pairs: a probe row appears twice"
 
 
 def main():
@@ -318,7 +494,13 @@ def main():
     ap.add_argument("--log2-probe", type=int, default=29)
     ap.add_argument("--cpu-log2-build", type=int, default=26)
     ap.add_argument("--cpu-log2-probe", type=int, default=28)
-    ap.add_argument("--zipf", type=float, default=0.0)
+    ap.add_argument("--zipf", type=float, default=0.0, help="Zipf exponent of the probe-side foreign keys (0 = uniform)")
+    ap.add_argument("--log2-gb-rows", type=int, default=30)
+    ap.add_argument("--gb-groups", default="1e2,1e5,1e8")
+    ap.add_argument("--gb-steps", type=int, default=3)
+    ap.add_argument("--cpu-log2-gb-rows", type=int, default=26)
+    ap.add_argument("--skip-groupby", action="store_true")
+    ap.add_argument("--skip-general", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: omit the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: omit the CPU baseline leg")
     args = ap.parse_args()

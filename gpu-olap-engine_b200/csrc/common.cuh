@@ -57,6 +57,11 @@ struct olap_ctx {
   uint64_t table_arena_bytes = 0;
   uint32_t table_generation = 0;
   cudaEvent_t fork_ev = nullptr, join_ev[8] = {};
+  // column statistics remembered per (device pointer, rows): min / max of a join's build keys (verified by the build pass
+  // itself: a key outside the remembered range raises a flag and the range is recomputed) and whether a probe column needed
+  // heavy-hitter handling
+  struct KeyStats { uint64_t n = 0; int64_t min = 0, max = 0; bool have_range = false; bool skewed = false; };
+  std::unordered_map<const void*, KeyStats> key_stats;
   // operator layer state (in-memory catalog of device-resident tables), owned by operators.cu
   void* op_state = nullptr;
   void (*op_state_free)(void*) = nullptr;

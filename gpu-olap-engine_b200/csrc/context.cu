@@ -44,6 +44,7 @@ olap_status pool_free(olap_ctx* ctx, void* p, cudaStream_t s) {
   if (it == ctx->live.end()) { set_error("pool_free: pointer %p was not allocated from this context", p); return OLAP_ERR_BAD_ARG; }
   ctx->used -= it->second;
   ctx->live.erase(it);
+  ctx->key_stats.erase(p);  // statistics remembered for a column die with its allocation
   OLAP_CUDA(cudaFreeAsync(p, s));
   return OLAP_OK;
 }

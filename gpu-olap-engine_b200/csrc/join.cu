@@ -16,6 +16,7 @@
 //   * one global atomic per match (the reference's probe) serialises on one address (1.5 G/s) -> matches are staged
 //     per CTA tile in shared memory and reserved with one atomic per tile.
 #include "common.cuh"
+#include "djoin.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -843,9 +844,11 @@ __global__ void __launch_bounds__(kJoinThreads, DIRECT ? 6 : 4) join_pipeline_ke
     const PartWork w = part_work(b0, b1, p0, p1, a.load_pct, a.direct_entries);
     Bucket* table = a.arena + (uint64_t)(p % a.R) * a.stride;
     if (phase == 0) {
-      uint32_t need = 0;
-      if (p >= a.R) { const uint32_t q = p - a.R; need = part_work(a.bb[q], a.bb[P + q], a.pb[q], a.pb[P + q], a.load_pct, a.direct_entries).n_probe; }
-      pipe_wait(probed + (p >= a.R ? p - a.R : 0), need, a.waited + 0);
+      // the slot's previous user: the most recent ACTIVE partition q = p - R, p - 2R, ... (an inactive one has no items and
+      // signals nothing; the chain clear -> build -> probe of q already orders everything before q)
+      uint32_t need = 0, q = p;
+      while (q >= a.R && !need) { q -= a.R; need = part_work(a.bb[q], a.bb[P + q], a.pb[q], a.pb[P + q], a.load_pct, a.direct_entries).n_probe; }
+      pipe_wait(probed + q, need, a.waited + 0);
       const uint32_t c0 = idx * kClearTile, c1 = min(w.nbk, c0 + kClearTile);
       const uint64_t fill = DIRECT ? ~0ULL : 0ULL;  // direct tables: every entry = kDirectEmpty
       const u64x4 z = {fill, fill, fill, fill};
@@ -970,24 +973,70 @@ constexpr olap_status OLAP_ERR_INTERNAL_RETRY = (olap_status)1000;  // never lea
 
 // min / max of the build keys; r->rrange > 0 when they are dense enough for direct-address tables: the key range is at most
 // 5 x the rows (a direct table then takes <= 20 bytes per build row against 32 for the bucket table; 5 rather than 4 so that a
-// rank holding a quarter of a dense global domain qualifies whatever its exact row count) and fits 32-bit offsets
-static olap_status detect_dense_keys(olap_ctx* ctx, const uint64_t* keys, uint64_t n, cudaStream_t s, KeyRange* r) {
-  Scratch sc(ctx, s);
-  long long* d = nullptr;
-  OLAP_TRY(sc.get<long long>(2, &d));
-  const long long init[2] = {INT64_MAX, INT64_MIN};
+// rank holding a quarter of a dense global domain qualifies whatever its exact row count) and fits 32-bit offsets.
+// The range of a (pointer, rows) column is remembered in the context: a join against the same dimension table does not pay
+// the extra read again.  A remembered range is only a hint -- the build-side partition pass flags any key outside it and the
+// caller then calls this again with refresh = true.
+static olap_status detect_dense_keys(olap_ctx* ctx, const uint64_t* keys, uint64_t n, cudaStream_t s, KeyRange* r, bool refresh = false) {
   long long mm[2];
-  OLAP_CUDA(cudaMemcpyAsync(d, init, 16, cudaMemcpyHostToDevice, s));
-  key_minmax_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(keys, n, d);
-  count_launch(ctx);
-  OLAP_CUDA(cudaGetLastError());
-  OLAP_CUDA(cudaMemcpyAsync(mm, d, 16, cudaMemcpyDeviceToHost, s));
-  OLAP_CUDA(cudaStreamSynchronize(s));
-  phase_mark(ctx, s, "minmax");
+  bool fresh = false;
+  auto it = ctx->key_stats.find(keys);
+  if (!refresh && env_u64("OLAP_KEY_STATS", 1) && it != ctx->key_stats.end() && it->second.n == n && it->second.have_range) {
+    mm[0] = it->second.min; mm[1] = it->second.max;
+  } else {
+    Scratch sc(ctx, s);
+    long long* d = nullptr;
+    OLAP_TRY(sc.get<long long>(2, &d));
+    const long long init[2] = {INT64_MAX, INT64_MIN};
+    OLAP_CUDA(cudaMemcpyAsync(d, init, 16, cudaMemcpyHostToDevice, s));
+    key_minmax_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(keys, n, d);
+    count_launch(ctx);
+    OLAP_CUDA(cudaGetLastError());
+    OLAP_CUDA(cudaMemcpyAsync(mm, d, 16, cudaMemcpyDeviceToHost, s));
+    OLAP_CUDA(cudaStreamSynchronize(s));
+    phase_mark(ctx, s, "minmax");
+    fresh = true;
+  }
   const uint64_t span = (uint64_t)mm[1] - (uint64_t)mm[0];  // max - min, exact in unsigned arithmetic
   *r = KeyRange();
   if (mm[1] >= mm[0] && span < 0xFFFFFFF0ULL && span + 1 <= 5 * n) { r->rmin = mm[0]; r->rrange = span + 1; }
+  if (fresh) {
+    // only a DENSE range is remembered: it is verified by the pass that uses it.  A remembered "sparse" verdict would never be
+    // checked again and would keep new, dense contents at the same address off the fast path for good.
+    if (r->rrange) {
+      if (ctx->key_stats.size() > 4096) ctx->key_stats.clear();
+      auto& st = ctx->key_stats[keys];
+      st.n = n; st.min = mm[0]; st.max = mm[1]; st.have_range = true;
+    } else if (it != ctx->key_stats.end()) ctx->key_stats.erase(it);
+  }
   return OLAP_OK;
+}
+
+// The direct join with shared-memory tables (djoin.cu), run to completion: *retry = 0 when pairs / count stand, else the OR of
+// (1 << kFlag*) telling the caller why another path is needed.
+static olap_status smem_join(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, const uint64_t* pk, uint64_t np, const KeyRange& r, uint32_t pid_base,
+                             olap_pair* out, uint64_t max_matches, unsigned long long* d_count, int hot, cudaStream_t s, uint32_t* retry) {
+  DJBuild b;
+  RInput in;
+  in.keys = bk; in.n = nb;
+  olap_status st = dj_build_prepare(ctx, in, r.rmin, r.rrange, 0, s, &b);
+  Scratch sc(ctx, s);
+  uint32_t* d_flags = nullptr;
+  if (st == OLAP_OK) st = sc.get<uint32_t>(kFlagWords, &d_flags);
+  if (st == OLAP_OK) {
+    in.keys = pk; in.n = np; in.id_base = pid_base;
+    st = dj_probe(b, in, np, out, max_matches, d_count, hot, 0, s, d_flags);
+  }
+  uint32_t hf[kFlagWords] = {0, 0, 0, 0};
+  if (st == OLAP_OK) {
+    cudaError_t e = cudaMemcpyAsync(hf, d_flags, sizeof(hf), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) st = cuda_fail(e, "reading the join flags", __FILE__, __LINE__);
+  }
+  dj_build_free(b, s);
+  *retry = 0;
+  for (int i = 0; i < kFlagWords; i++) if (hf[i]) *retry |= 1u << i;
+  return st;
 }
 
 // The build side of a join, prepared once and probed by one or many batches of the probe side (the reference executor hands
@@ -1004,9 +1053,14 @@ struct BuildSide {
   uint32_t* d_bounds = nullptr;  // partition bounds on the device, [2P]
   std::vector<uint32_t> hb;      // ... and on the host
   uint64_t max_part = 0;
+  // radix, dense unique keys: partitioned by key range for the shared-memory direct join (djoin.cu).  The general layout above
+  // is then prepared only if a probe reports that this representation cannot serve (repeated key, skew)
+  DJBuild dj; bool use_dj = false; bool general_ready = true;
+  const uint64_t* bkeys = nullptr;  // the caller keeps the build keys alive while the handle lives
 };
 
 static olap_status build_side_free(BuildSide& b, cudaStream_t s) {
+  if (b.use_dj) { dj_build_free(b.dj, s); b.use_dj = false; }
   if (b.table) { pool_free(b.ctx, b.table, s); b.table = nullptr; }
   if (b.pkb) { pool_free(b.ctx, b.pkb, s); b.pkb = nullptr; }
   if (b.pib) { pool_free(b.ctx, b.pib, s); b.pib = nullptr; }
@@ -1280,11 +1334,32 @@ olap_status olap_hash_join_i64(olap_ctx* ctx, const int64_t* build_keys, uint64_
   if (n_build && n_probe) {  // executor.rs:231-233: an empty side yields no rows
     bool done = false;
     if (strategy == OLAP_JOIN_RADIX && n_build >= (1u << 20) && env_u64("OLAP_JOIN_DIRECT", 1)) {
-      // dense build keys?  (a 1 GB read at C2: 0.2 ms)  Then try direct-address tables; a duplicate key or very uneven key
-      // ranges send the join back to the general path below.
+      // dense build keys?  (min / max: remembered per column, else a 1 GB read at C2: 0.2 ms)  Then direct-address tables over key
+      // ranges; a repeated build key or badly skewed probe keys send the join back to the general path below.
       KeyRange r;
       st = detect_dense_keys(ctx, (const uint64_t*)build_keys, n_build, s, &r);
-      if (st == OLAP_OK && r.rrange) {
+      bool try_l2_tables = st == OLAP_OK && r.rrange != 0;
+      if (try_l2_tables && djoin_eligible(r.rrange) && env_u64("OLAP_JOIN_SMEM", 1)) {
+        auto ps = ctx->key_stats.find(probe_keys);
+        int hot = (ps != ctx->key_stats.end() && ps->second.n == n_probe && ps->second.skewed) || env_u64("OLAP_JOIN_HOT", 0);
+        for (int attempt = 0; attempt < 4 && st == OLAP_OK && !done; attempt++) {
+          uint32_t retry = 0;
+          st = smem_join(ctx, (const uint64_t*)build_keys, n_build, (const uint64_t*)probe_keys, n_probe, r, 0, out_pairs, max_matches, d_count, hot, s, &retry);
+          if (st != OLAP_OK) break;
+          if (!retry) { done = true; break; }
+          OLAP_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+          if (retry & (1u << kFlagOutOfRange)) {  // the remembered key range is stale: recompute it
+            st = detect_dense_keys(ctx, (const uint64_t*)build_keys, n_build, s, &r, true);
+            if (st != OLAP_OK || !r.rrange || !djoin_eligible(r.rrange)) break;
+          } else if ((retry & (1u << kFlagOverflow)) && !(retry & (1u << kFlagDup)) && !hot) {  // skewed probe keys: pull the heavy hitters out first
+            hot = 1;
+            auto& st2 = ctx->key_stats[probe_keys];
+            st2.n = n_probe; st2.skewed = true;
+          } else break;
+        }
+        try_l2_tables = false;  // whatever defeated the shared-memory tables (a repeated key, skew) defeats the L2 direct tables too
+      }
+      if (!done && try_l2_tables && st == OLAP_OK) {
         b.range = r;
         st = build_side_prepare(ctx, (const uint64_t*)build_keys, n_build, strategy, s, &b);
         if (st == OLAP_OK) st = build_side_probe(b, (const uint64_t*)probe_keys, n_probe, 0, out_pairs, max_matches, d_count, s);
@@ -1310,6 +1385,18 @@ struct olap_join_build { BuildSide b; };
 
 extern "C" {
 
+static olap_status dj_side_prepare(olap_ctx* ctx, BuildSide& b, cudaStream_t s, bool refresh) {
+  KeyRange r;
+  OLAP_TRY(detect_dense_keys(ctx, b.bkeys, b.nb, s, &r, refresh));
+  if (b.use_dj) { dj_build_free(b.dj, s); b.use_dj = false; }
+  if (!r.rrange || !djoin_eligible(r.rrange)) return OLAP_OK;
+  RInput in;
+  in.keys = b.bkeys; in.n = b.nb;
+  OLAP_TRY(dj_build_prepare(ctx, in, r.rmin, r.rrange, 0, s, &b.dj));
+  b.use_dj = true;
+  return OLAP_OK;
+}
+
 olap_status olap_join_build_create(olap_ctx* ctx, const int64_t* build_keys, uint64_t n_build, int32_t strategy, void* stream,
                                    olap_join_build** out) {
   OLAP_REQUIRE(ctx && out, "NULL argument");
@@ -1321,8 +1408,15 @@ olap_status olap_join_build_create(olap_ctx* ctx, const int64_t* build_keys, uin
   cudaStream_t s = ctx->stream_of(stream);
   if (strategy == OLAP_JOIN_AUTO) strategy = olap_choose_join_strategy(n_build);
   auto* h = new olap_join_build();
-  olap_status st = build_side_prepare(ctx, (const uint64_t*)build_keys, n_build, strategy, s, &h->b);
-  if (st != OLAP_OK) { build_side_free(h->b, s); delete h; return st; }
+  BuildSide& b = h->b;
+  olap_status st = OLAP_OK;
+  if (strategy == OLAP_JOIN_RADIX && n_build >= (1u << 20) && env_u64("OLAP_JOIN_DIRECT", 1) && env_u64("OLAP_JOIN_SMEM", 1)) {
+    b.ctx = ctx; b.strategy = strategy; b.nb = n_build; b.bkeys = (const uint64_t*)build_keys;
+    st = dj_side_prepare(ctx, b, s, false);
+    if (st == OLAP_OK && b.use_dj) b.general_ready = false;
+  }
+  if (st == OLAP_OK && !b.use_dj) st = build_side_prepare(ctx, (const uint64_t*)build_keys, n_build, strategy, s, &b);
+  if (st != OLAP_OK) { build_side_free(b, s); delete h; return st; }
   *out = h;
   return OLAP_OK;
 }
@@ -1332,7 +1426,8 @@ olap_status olap_join_probe(olap_join_build* build, const int64_t* probe_keys, u
   OLAP_REQUIRE(build, "build handle is NULL");
   OLAP_REQUIRE(n_probe == 0 || probe_keys, "probe_keys is NULL");
   OLAP_REQUIRE(n_probe < 0xFFFFFFFFULL && (uint64_t)probe_row_base + n_probe < 0xFFFFFFFFULL, "row ids are u32");
-  olap_ctx* ctx = build->b.ctx;
+  BuildSide& b = build->b;
+  olap_ctx* ctx = b.ctx;
   std::lock_guard<std::mutex> g(ctx->mu);
   OLAP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream_of(stream);
@@ -1341,7 +1436,33 @@ olap_status olap_join_probe(olap_join_build* build, const int64_t* probe_keys, u
   unsigned long long* d_count = (unsigned long long*)out_count_dptr;
   if (!d_count) OLAP_TRY(sc.get<unsigned long long>(1, &d_count));
   OLAP_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
-  OLAP_TRY(build_side_probe(build->b, (const uint64_t*)probe_keys, n_probe, probe_row_base, out_pairs, max_matches, d_count, s));
+  bool done = b.nb == 0 || n_probe == 0;
+  if (!done && b.use_dj) {
+    uint32_t* d_flags = nullptr;
+    OLAP_TRY(sc.get<uint32_t>(kFlagWords, &d_flags));
+    int hot = 0;
+    for (int attempt = 0; attempt < 4 && b.use_dj && !done; attempt++) {
+      RInput in;
+      in.keys = (const uint64_t*)probe_keys; in.n = n_probe; in.id_base = probe_row_base;
+      OLAP_TRY(dj_probe(b.dj, in, n_probe, out_pairs, max_matches, d_count, hot, 0, s, d_flags));
+      uint32_t hf[kFlagWords];
+      OLAP_CUDA(cudaMemcpyAsync(hf, d_flags, sizeof(hf), cudaMemcpyDeviceToHost, s));
+      OLAP_CUDA(cudaStreamSynchronize(s));
+      if (!hf[0] && !hf[1] && !hf[2] && !hf[3]) { done = true; break; }
+      OLAP_CUDA(cudaMemsetAsync(d_count, 0, 8, s));
+      if (hf[kFlagOutOfRange]) OLAP_TRY(dj_side_prepare(ctx, b, s, true));          // stale remembered key range
+      else if (hf[kFlagOverflow] && !hf[kFlagDup] && !hot) hot = 1;                  // skewed probe keys
+      else { dj_build_free(b.dj, s); b.use_dj = false; }                             // repeated build key: bucket tables from now on
+    }
+    if (!done && b.use_dj) { dj_build_free(b.dj, s); b.use_dj = false; }
+  }
+  if (!done) {
+    if (!b.general_ready) {
+      OLAP_TRY(build_side_prepare(ctx, b.bkeys, b.nb, b.strategy, s, &b));
+      b.general_ready = true;
+    }
+    OLAP_TRY(build_side_probe(b, (const uint64_t*)probe_keys, n_probe, probe_row_base, out_pairs, max_matches, d_count, s));
+  }
   return finish_count(ctx, d_count, host_count, out_pairs, max_matches, s);
 }
 
