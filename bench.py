@@ -105,6 +105,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
+    if args.gpus > 1 and not args.sizes_given:
+        args.log2_build, args.log2_probe = 28, 30   # the arm it is compared with (BASELINE config 5 per GPU)
     lb, lp = args.cpu_log2_build, args.cpu_log2_probe
     rps, sec, _ = cpu_reference_join(lb, lp, cores, steps=args.steps, warmup=min(args.warmup, 1))
     sample = (f"bounded sample of the workload: 2^{lb} unique-key build x 2^{lp} FK probe, int64 keys, pairs materialised; "
@@ -150,7 +152,15 @@ def run_ours(args):
 
     if world > 1:
         from gpu_olap_engine_b200 import sharded
-        return sharded.bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, ClockSampler)
+        if not args.sizes_given:   # BASELINE config 5: per GPU 2^28 x 2^30 (2^31 x 2^33 at 8 GPUs)
+            args.log2_build, args.log2_probe = 28, 30
+
+        def cpu():
+            cores = os.cpu_count() or 1
+            rps, sec, _ = cpu_reference_join(args.cpu_log2_build, args.cpu_log2_probe, cores)
+            return {"value": rps, "unit": "rows/s", "cores": cores, "kind": "port",
+                    "sample": f"2^{args.cpu_log2_build} unique-key build x 2^{args.cpu_log2_probe} FK probe (same generator), pairs materialised, {cores} threads, {sec:.2f} s"}
+        return sharded.bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, ClockSampler, cpu)
 
     return bench_single(ctx, g, args, local_rank, peak, peak_kind)
 
@@ -318,10 +328,7 @@ def bench_single(ctx, g, args, local_rank, peak, peak_kind):
     # build keys = permutation of [0, 2^27) (unique), probe = uniform FK over the build domain, seed 3
     dbuild = ctx.generate(nb, 1, 3, nb)
     if args.zipf > 0:
-        dprobe = ctx.alloc(npb, np.int64)
-        ctx.synchronize()
-        fk_probe_keys(torch, dev_view(torch, dbuild, nb), dev_view(torch, dprobe, npb), args.zipf, 33)
-        torch.cuda.synchronize()
+        dprobe = ctx.generate_fk(npb, 3, nb, 33, args.zipf)     # FK ~ Zipf(s) over the build rows, keys through the build permutation
     else:
         dprobe = ctx.generate(npb, 0, 33, nb)
     pairs = ctx.alloc(2 * npb, np.uint32)
@@ -490,8 +497,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log2-build", type=int, default=27)
-    ap.add_argument("--log2-probe", type=int, default=29)
+    ap.add_argument("--log2-build", type=int, default=None)
+    ap.add_argument("--log2-probe", type=int, default=None)
     ap.add_argument("--cpu-log2-build", type=int, default=26)
     ap.add_argument("--cpu-log2-probe", type=int, default=28)
     ap.add_argument("--zipf", type=float, default=0.0, help="Zipf exponent of the probe-side foreign keys (0 = uniform)")
@@ -504,6 +511,9 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: omit the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: omit the CPU baseline leg")
     args = ap.parse_args()
+    args.sizes_given = args.log2_build is not None or args.log2_probe is not None
+    args.log2_build = 27 if args.log2_build is None else args.log2_build
+    args.log2_probe = 29 if args.log2_probe is None else args.log2_probe
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     sys.exit(run_reference(args) if args.impl == "reference" else run_ours(args))

@@ -74,6 +74,28 @@ SIGNATURES = {
     "olap_shuffle_scratch_words": (u64, [vp, i32]),
     "olap_shuffle_count_i64": (i32, [vp, vp, u64, i32, vp, vp, vp]),
     "olap_shuffle_scatter_i64": (i32, [vp, vp, u64, i32, vp, vp, vp, vp, vp]),
+    "olap_shard_create": (i32, [vp, i32, i32, u64, u64, i32, pvp]),
+    "olap_shard_destroy": (i32, [vp]),
+    "olap_shard_slab_bytes": (u64, [vp]),
+    "olap_shard_attach": (i32, [vp, pvp]),
+    "olap_shard_barrier": (i32, [vp, vp]),
+    "olap_shard_key_range": (i32, [vp, vp, u64, C.POINTER(i64), C.POINTER(i64), vp]),
+    "olap_shard_plan": (i32, [vp, i64, i64, u64, i32, vp]),
+    "olap_shard_scatter": (i32, [vp, i32, i32, vp, u64, u32, vp]),
+    "olap_shard_send": (i32, [vp, i32, i32, vp]),
+    "olap_shard_build": (i32, [vp, vp]),
+    "olap_shard_probe": (i32, [vp, i32, vp, u64, vp]),
+    "olap_shard_finish": (i32, [vp, pu64, pu64, C.POINTER(u32), vp]),
+    "olap_shard_hot_candidates": (i32, [vp, vp, u64, C.POINTER(u32), C.POINTER(u32), u32, C.POINTER(u32), vp]),
+    "olap_shard_hot_set": (i32, [vp, C.POINTER(u32), u32, vp]),
+    "olap_shard_hot_resolve": (i32, [vp, vp, vp]),
+    "olap_shard_hot_finalize": (i32, [vp, vp, vp, u64, vp]),
+    "olap_shard_pairs_to_global": (i32, [vp, vp, u64, vp, vp, vp, vp, vp]),
+    "olap_shard_layout": (i32, [vp, pu64]),
+    "olap_shard_sent_rows": (i32, [vp, pu64, vp]),
+    "olap_shard_ctx_create_all": (i32, [i32, C.POINTER(i32), u64, u64, u64, i32, pvp, pvp]),
+    "olap_sharded_hash_join_i64": (i32, [pvp, i32, pvp, pu64, pvp, pu64, pvp, pu64, pu64, pvp, pu64, pu64]),
+    "olap_shard_hot_table": (i32, [vp, pu64, vp]),
     "olap_group_by_i64": (i32, [vp, vp, C.POINTER(AggSpec), i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_group_by_prog_i64": (i32, [vp, vp, C.POINTER(AggSpec), vp, i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_agg_identity": (i64, [i32]),
@@ -96,6 +118,7 @@ SIGNATURES = {
     "olap_result_export": (i32, [vp, i32, vp, vp]),
     "olap_result_free": (None, [vp]),
     "olap_generate": (i32, [vp, vp, u64, i32, u64, u64, u64, vp]),
+    "olap_generate_fk": (i32, [vp, vp, u64, u64, u64, u64, u64, C.c_double, vp]),
     "olap_set_profiling": (i32, [vp, i32]),
     "olap_last_phase_times": (i32, [vp, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_float)), C.POINTER(i32)]),
     "olap_launch_count": (u64, [vp]),

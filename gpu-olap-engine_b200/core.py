@@ -170,6 +170,12 @@ class Context:
         check(self.lib.olap_generate(self.handle, _ptr(out), n, kind, seed, row0, domain, stream))
         return out
 
+    def generate_fk(self, n: int, perm_seed: int, domain: int, fk_seed: int, zipf_s: float = 0.0, row0: int = 0, out=None, stream=None):
+        """Foreign keys into a build side made by generate(kind=1, seed=perm_seed, domain): uniform or Zipf(zipf_s) over its rows."""
+        out = out if out is not None else self.alloc(n, np.int64)
+        check(self.lib.olap_generate_fk(self.handle, _ptr(out), n, perm_seed, domain, fk_seed, row0, float(zipf_s), stream))
+        return out
+
     # ------------------------------------------------------------------ filter / projection
     def filter(self, terms: Sequence[Term], n_rows: int, want_mask=True, want_sel=True, stream=None):
         """Returns (count, mask DeviceBuffer|None, sel DeviceBuffer|None)."""

@@ -57,11 +57,14 @@ struct olap_ctx {
   uint64_t table_arena_bytes = 0;
   uint32_t table_generation = 0;
   cudaEvent_t fork_ev = nullptr, join_ev[8] = {};
+  cudaEvent_t arena_ev = nullptr;   // recorded behind every use of table_arena; the next user (on any stream) waits for it first
+  bool arena_used = false;
   // column statistics remembered per (device pointer, rows): min / max of a join's build keys (verified by the build pass
   // itself: a key outside the remembered range raises a flag and the range is recomputed) and whether a probe column needed
   // heavy-hitter handling
   struct KeyStats { uint64_t n = 0; int64_t min = 0, max = 0; bool have_range = false; bool skewed = false; };
   std::unordered_map<const void*, KeyStats> key_stats;
+  std::unordered_map<const void*, KeyStats> shard_key_stats;  // per-rank shards of a multi-GPU join (shard.cu)
   // operator layer state (in-memory catalog of device-resident tables), owned by operators.cu
   void* op_state = nullptr;
   void (*op_state_free)(void*) = nullptr;

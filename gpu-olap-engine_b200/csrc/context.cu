@@ -45,6 +45,7 @@ olap_status pool_free(olap_ctx* ctx, void* p, cudaStream_t s) {
   ctx->used -= it->second;
   ctx->live.erase(it);
   ctx->key_stats.erase(p);  // statistics remembered for a column die with its allocation
+  ctx->shard_key_stats.erase(p);
   OLAP_CUDA(cudaFreeAsync(p, s));
   return OLAP_OK;
 }
@@ -123,6 +124,33 @@ __global__ void __launch_bounds__(256) generate_kernel(uint64_t* __restrict__ ou
   }
 }
 
+// Foreign keys into a permutation-keyed build side (kind 1 with the same seed / domain): row r of the probe side references
+// build row b(r) and carries that row's key perm(b).  b is uniform (zipf_s = 0) or b + 1 ~ Zipf(zipf_s) over the build rows, drawn
+// with the continuous inverse CDF ((N^(1-s) - 1) u + 1)^(1 / (1 - s)) (N^u for s = 1): the hot build rows are 0, 1, 2, ..., whose
+// keys the permutation spreads over the whole domain ("Zipf(s) over ranks mapped through a fixed permutation").
+__global__ void __launch_bounds__(256) generate_fk_kernel(uint64_t* __restrict__ out, uint64_t n, uint64_t perm_seed, uint64_t domain, int bits,
+                                                          uint64_t fk_seed, uint64_t row0, double zipf_s) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t k0 = splitmix64(perm_seed, 0), k1 = splitmix64(perm_seed, 1), k2 = splitmix64(perm_seed, 2), k3 = splitmix64(perm_seed, 3);
+  const double N = (double)domain, e = 1.0 - zipf_s;
+  const double a = zipf_s > 0.0 ? (fabs(e) < 1e-9 ? log(N) : pow(N, e) - 1.0) : 0.0;
+  for (; i < n; i += stride) {
+    const uint64_t h = splitmix64(fk_seed, row0 + i);
+    uint64_t b;
+    if (zipf_s <= 0.0) b = h % domain;
+    else {
+      const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+      const double x = fabs(e) < 1e-9 ? exp(u * a) : pow(a * u + 1.0, 1.0 / e);
+      b = (uint64_t)x;
+      b = b ? b - 1 : 0;
+      if (b >= domain) b = domain - 1;
+    }
+    uint64_t v = b;
+    do { v = perm_pow2(v, bits, k0, k1, k2, k3); } while (v >= domain);
+    out[i] = v;
+  }
+}
+
 static inline unsigned grid_for(uint64_t n, int block, int sms, int per_sm = 8) {
   uint64_t g = (n + block - 1) / block;
   uint64_t cap = (uint64_t)sms * per_sm;
@@ -175,6 +203,7 @@ olap_status olap_ctx_create(int32_t device, uint64_t max_gpu_memory, int32_t num
     if (e != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__); }
   }
   cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->arena_ev, cudaEventDisableTiming);
   for (auto& ev : ctx->join_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   *out = ctx;
   return OLAP_OK;
@@ -190,6 +219,7 @@ olap_status olap_ctx_destroy(olap_ctx* ctx) {
   for (auto& kv : ctx->live) cudaFree(kv.first);
   for (auto s : ctx->streams) cudaStreamDestroy(s);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  if (ctx->arena_ev) cudaEventDestroy(ctx->arena_ev);
   for (auto ev : ctx->join_ev) if (ev) cudaEventDestroy(ev);
   if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
   delete ctx;
@@ -320,6 +350,21 @@ olap_status olap_generate(olap_ctx* ctx, void* out, uint64_t n, int32_t kind, ui
   int bits = 1;
   while (bits < 64 && (1ULL << bits) < domain) bits++;
   generate_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream_of(stream)>>>((uint64_t*)out, n, kind, seed, row0, domain, bits);
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
+
+olap_status olap_generate_fk(olap_ctx* ctx, void* out, uint64_t n, uint64_t perm_seed, uint64_t domain, uint64_t fk_seed, uint64_t row0, double zipf_s,
+                             void* stream) {
+  OLAP_REQUIRE(ctx && (n == 0 || out), "NULL pointer");
+  OLAP_REQUIRE(domain > 0 && zipf_s >= 0.0, "domain must be > 0, zipf_s >= 0");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return OLAP_OK;
+  int bits = 1;
+  while (bits < 64 && (1ULL << bits) < domain) bits++;
+  generate_fk_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, ctx->stream_of(stream)>>>((uint64_t*)out, n, perm_seed, domain, bits, fk_seed, row0, zipf_s);
   count_launch(ctx);
   OLAP_CUDA(cudaGetLastError());
   return OLAP_OK;

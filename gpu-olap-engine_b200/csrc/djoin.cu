@@ -42,9 +42,9 @@ struct RPartArgs {
   uint64_t rmin, rrange;
   // kInRegions*: the fixed-capacity regions a previous pass (or the multi-GPU shuffle) filled with packed words
   // {offset : u32 hi, id : u32 lo}; region g holds min(reg_cur[g], reg_cap) rows, all of partitions
-  // [(g & reg_mask) << reg_bits, ((g & reg_mask) + 1) << reg_bits).  Carry: the id is kept; Pos: the id becomes the row's
-  // position g * reg_cap + row (multi-GPU: pairs then index the receive buffer, whose low words hold the source row ids)
-  const uint32_t* reg_cur; uint32_t reg_cap, n_reg, reg_mask; int reg_bits;
+  // [(g % reg_q) * reg_parts, (g % reg_q + 1) * reg_parts).  Carry: the id is kept; Pos: the id becomes the row's position
+  // id_base + g * reg_cap + row (multi-GPU: pairs then index the receive buffer, whose low words hold the source row ids)
+  const uint32_t* reg_cur; uint32_t reg_cap, n_reg, reg_q, reg_parts;
   int shift;               // partition = (offset >> shift) - first partition of the region
   uint32_t cap;            // partition p owns out[p * cap, (p + 1) * cap)
   uint32_t* cursor;        // rows handed out per partition (may exceed cap: overflow)
@@ -56,15 +56,29 @@ struct RPartArgs {
   const uint32_t* hot_keys;   // [kHotSlots] offset + 1, 0 = empty slot; NULL = no hot keys
   const uint32_t* hot_ids;    // [kHotSlots] build row of the slot's key
   olap_pair* pairs; uint64_t max_matches; unsigned long long* count;
+  // PEER output (multi-GPU shuffle, kInRaw only): partition j = offset / peer_subw (sub-ranges need not be a power of two wide, so
+  // that the ranks' slices tile the key domain evenly) belongs to rank j / peer_q; its rows go straight into region
+  // peer_rank * peer_q + j % peer_q of THAT rank's receive slab (peer-mapped pointer), as {offset - first offset of the rank's
+  // slice : u32 hi, source row id : u32 lo}.  Only this rank writes those regions, so the cursors stay in local memory; the
+  // counts are published afterwards (shard_publish_kernel).
+  uint64_t* peer_out[8]; uint32_t peer_q, peer_subw, peer_rank;
+  uint64_t peer_mf; uint32_t peer_mq;   // exact division by multiplication: offset / peer_subw and partition / peer_q (see peer_part / peer_dest)
 };
+
+// peer_subw = F << 15 with F <= 256, offsets < 2^32: (offset >> 15) < 2^17 and (x * ceil(2^32 / F)) >> 32 == x / F exactly (the error
+// term x / 2^32 < 2^-15 < 1 / F); partitions < 256: (p * ceil(2^24 / Q)) >> 24 == p / Q exactly
+__device__ __forceinline__ uint32_t peer_part(const RPartArgs& a, uint32_t d) { return (uint32_t)(((uint64_t)(d >> kRShift) * a.peer_mf) >> 32); }
+__device__ __forceinline__ uint32_t peer_dest(const RPartArgs& a, uint32_t part) { return (part * a.peer_mq) >> 24; }
 
 __device__ __forceinline__ uint32_t hot_slot_of(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - 11); }
 static_assert(kHotSlots == 2048, "hot_slot_of shifts for 2^11 slots");
 
 // CTAs per SM: 4 for raw keys (64 registers); the region passes keep the carried id next to offset and rank -- under a 64-register
 // cap ptxas serialises their 16 loads (2.18 ms instead of 1.35 ms for 2^29 rows) -- so they run 3 per SM with 80 registers
-template <int INPUT, bool HOT>
+template <int INPUT, bool HOT, bool PEER = false>
 __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kernel(const __grid_constant__ RPartArgs a) {
+  static_assert(!PEER || INPUT == kInRaw, "the shuffle reads raw keys");
+  __shared__ uint64_t* s_optr[PEER ? kRThreads : 1];                   // PEER: where staged row i of partition j goes = s_optr[j] + i
   constexpr int R = kRRows, NW = kRThreads / 32;
   __shared__ __align__(16) uint64_t stage[kRTile];                    // rows in partition order (32 KB)
   __shared__ uint32_t cnt[kRThreads];                                 // tile histogram, then exclusive offsets
@@ -94,8 +108,8 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
       src = a.in + (uint64_t)g * a.reg_cap;
       n = min(a.reg_cur[g], a.reg_cap);
       row0 = (uint64_t)(t - g * tiles_per_reg) * kRTile;
-      pbase = (g & a.reg_mask) << a.reg_bits;
-      idb = g * a.reg_cap;
+      pbase = (g % a.reg_q) * a.reg_parts;
+      idb = a.id_base + g * a.reg_cap;
       if (row0 >= n) continue;  // uniform over the CTA
     }
     par ^= 1;
@@ -113,6 +127,7 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
     for (int k = 0; k < R; k++) {
       const uint64_t row = row0 + (uint64_t)k * kRThreads + tid;
       bool ok = row < n;
+      if (INPUT == kInRegionsPos) ok = ok && key[k] != ~0ULL;  // padding word of the shuffle's 16-byte aligned runs
       if (INPUT != kInRaw) d[k] = (uint32_t)(key[k] >> 32);
       else {
         const uint64_t off = key[k] - a.rmin;
@@ -129,7 +144,7 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
           s = (s + 1) & (kHotSlots - 1);
         }
       }
-      if (ok) rk[k] = atomicAdd(&cnt[(d[k] >> a.shift) - pbase], 1u);
+      if (ok) rk[k] = atomicAdd(&cnt[(PEER ? peer_part(a, d[k]) : d[k] >> a.shift) - pbase], 1u);
     }
     if (INPUT == kInRaw && oob && a.oob_is_error) a.flags[kFlagOutOfRange] = 1;
     __syncthreads();
@@ -150,7 +165,11 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
       for (int w = 0; w < NW; w++) wbase += w < warp ? s_warp[w] : 0u;
       const uint32_t off = wbase + inc - c;
       cnt[tid] = off;
-      gbase[tid] = (pbase + (uint32_t)tid) * a.cap + got - off;
+      if (PEER) {
+        const uint32_t dest = min((uint32_t)tid / a.peer_q, 7u);
+        gbase[tid] = got - off;  // position inside the region
+        s_optr[tid] = a.peer_out[dest] + (uint64_t)(a.peer_rank * a.peer_q + (uint32_t)tid % a.peer_q) * a.cap + (int64_t)(int32_t)(got - off);
+      } else gbase[tid] = (pbase + (uint32_t)tid) * a.cap + got - off;
       if (got + c > a.cap) { s_over[par] = 1; a.flags[kFlagOverflow] = 1; }
       if (tid == kRThreads - 1) s_total = off + c;
     }
@@ -166,14 +185,23 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
         const uint32_t pos = kRTile - 1 - (atomicAdd(&s_hot[par], 0x10000u) >> 16);
         stage[pos] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (rk[k] & (kHotSlots - 1)));
       } else {
-        stage[cnt[(d[k] >> a.shift) - pbase] + rk[k]] = ((uint64_t)d[k] << 32) | id;
+        stage[cnt[(PEER ? peer_part(a, d[k]) : d[k] >> a.shift) - pbase] + rk[k]] = ((uint64_t)d[k] << 32) | id;
       }
     }
     __syncthreads();
     cnt[tid] = 0;  // the offsets are consumed: clear the histogram for the next tile
 
     // phase 4: every partition's run leaves with consecutive lanes on consecutive addresses
-    if (!s_over[par]) {
+    if (PEER) {
+      const bool over = s_over[par] != 0;
+      for (uint32_t i = tid; i < total; i += kRThreads) {
+        const uint64_t v = stage[i];
+        const uint32_t d0 = (uint32_t)(v >> 32), part = peer_part(a, d0);
+        if (over && gbase[part] + i >= a.cap) continue;  // the region is full: dropped, flagged
+        const uint32_t dl = d0 - peer_dest(a, part) * (a.peer_q * a.peer_subw);
+        s_optr[part][i] = ((uint64_t)dl << 32) | (uint32_t)v;
+      }
+    } else if (!s_over[par]) {
       for (uint32_t i = tid; i < total; i += kRThreads) {
         const uint64_t v = stage[i];
         a.out[gbase[((uint32_t)(v >> 32) >> a.shift) - pbase] + i] = v;
@@ -211,23 +239,25 @@ struct DJoinArgs {
   olap_pair* out; uint64_t max_matches; unsigned long long* count;
 };
 
-constexpr int kDJThreads = 1024;
-constexpr int kDJGroups = 4;                       // independent probe groups inside the CTA (named barriers)
-constexpr int kDJGroupThreads = kDJThreads / kDJGroups;
+// 1024 threads = 4 probe groups when the join owns the SM; 768 threads = 3 groups (36 K registers) when it shares the SM with a
+// shuffle CTA of the next chunk (multi-GPU: 24 K registers, 70 KB of shared memory)
+constexpr int kDJGroupThreads = 256;
 constexpr int kDJRows = 8;                         // probe rows per thread per group tile
 constexpr int kDJGroupTile = kDJGroupThreads * kDJRows;
 
 __device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kDJGroupThreads) : "memory"); }
 
-__global__ void __launch_bounds__(kDJThreads, 1) djoin_kernel(const __grid_constant__ DJoinArgs a) {
+template <int THREADS>
+__device__ __forceinline__ void djoin_body(const DJoinArgs& a) {
+  constexpr int GROUPS = THREADS / kDJGroupThreads;   // independent probe groups inside the CTA (named barriers)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw);   // [kRKeys] build row id per key of this range
   __shared__ uint32_t s_part;
-  __shared__ uint32_t s_n[kDJGroups];
-  __shared__ unsigned long long s_base[kDJGroups];
+  __shared__ uint32_t s_n[GROUPS];
+  __shared__ unsigned long long s_base[GROUPS];
   const int tid = threadIdx.x, lane = tid & 31;
   const int g = tid / kDJGroupThreads, gt = tid % kDJGroupThreads;
-  if (tid < kDJGroups) s_n[tid] = 0;
+  if (tid < GROUPS) s_n[tid] = 0;
   for (;;) {
     __syncthreads();  // the previous partition's probes are done with the table; s_part may be rewritten
     if (tid == 0) s_part = atomicAdd(a.ticket, 1u);
@@ -239,26 +269,25 @@ __global__ void __launch_bounds__(kDJThreads, 1) djoin_kernel(const __grid_const
     {
       const uint4 e = make_uint4(kREmpty, kREmpty, kREmpty, kREmpty);
       uint4* t4 = reinterpret_cast<uint4*>(table);
-#pragma unroll
-      for (int i = 0; i < (int)(kRKeys / 4 / kDJThreads); i++) t4[i * kDJThreads + tid] = e;
+      for (uint32_t i = tid; i < kRKeys / 4; i += THREADS) t4[i] = e;
     }
     __syncthreads();
     {
       const uint64_t* rows = a.brows + (uint64_t)p * a.bcap;
       bool dup = false;
-      for (uint32_t i0 = 0; i0 < nb; i0 += kDJThreads * 8) {
+      for (uint32_t i0 = 0; i0 < nb; i0 += THREADS * 8) {
         uint64_t v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) { const uint32_t i = i0 + k * kDJThreads + tid; v[k] = i < nb ? ld_stream_u64(rows + i) : ~0ULL; }
+        for (int k = 0; k < 8; k++) { const uint32_t i = i0 + k * THREADS + tid; v[k] = i < nb ? ld_stream_u64(rows + i) : ~0ULL; }
 #pragma unroll
         for (int k = 0; k < 8; k++)
-          if (i0 + k * kDJThreads + tid < nb) dup = dup || atomicExch(&table[(uint32_t)(v[k] >> 32) & (kRKeys - 1)], (uint32_t)v[k]) != kREmpty;
+          if (i0 + k * THREADS + tid < nb) dup = dup || atomicExch(&table[(uint32_t)(v[k] >> 32) & (kRKeys - 1)], (uint32_t)v[k]) != kREmpty;
       }
       if (dup) a.flags[kFlagDup] = 1;  // a repeated build key: this representation cannot hold it (the caller redoes the join with bucket tables)
     }
     __syncthreads();
     const uint64_t* rows = a.prows + (uint64_t)p * a.pcap;
-    for (uint32_t t0 = (uint32_t)g * kDJGroupTile; t0 < np; t0 += kDJGroups * kDJGroupTile) {
+    for (uint32_t t0 = (uint32_t)g * kDJGroupTile; t0 < np; t0 += GROUPS * kDJGroupTile) {
       uint64_t v[kDJRows];
 #pragma unroll
       for (int k = 0; k < kDJRows; k++) { const uint32_t i = t0 + k * kDJGroupThreads + gt; v[k] = i < np ? ld_stream_u64(rows + i) : ~0ULL; }
@@ -295,6 +324,10 @@ __global__ void __launch_bounds__(kDJThreads, 1) djoin_kernel(const __grid_const
     }
   }
 }
+
+__global__ void __launch_bounds__(1024, 1) djoin_kernel(const __grid_constant__ DJoinArgs a) { djoin_body<1024>(a); }
+// 48 registers x 768 threads = 36 K: fits an SM together with one shuffle CTA (96 x 256 = 24 K)
+__global__ void __maxnreg__(48) djoin_shared_kernel(const __grid_constant__ DJoinArgs a) { djoin_body<768>(a); }
 
 // ------------------------------------------------------------------------------------------- heavy hitters
 // Sample the probe keys, count the samples per key in a small global table, keep the keys seen at least `min_count` times (at
@@ -374,9 +407,19 @@ __global__ void __launch_bounds__(256) hot_resolve_kernel(uint32_t* hot_keys, ui
   }
 }
 
-template <int INPUT, bool HOT>
-static olap_status launch_rpart_t(olap_ctx* ctx, const RPartArgs& a, unsigned grid, cudaStream_t s) {
-  rpart_kernel<INPUT, HOT><<<grid, kRThreads, 0, s>>>(a);
+// Kernels of different launches share an SM only if they agree on its shared-memory / L1 split.  In the multi-GPU path (shared =
+// true) every kernel of this file asks for the maximum shared-memory carveout, so that a shuffle CTA, partition CTAs and a join
+// CTA can be resident together (chunk k + 1's shuffle next to chunk k's join).  On its own a partition pass keeps the default
+// split: with the L1 cut down to the minimum it ran 20-27 % slower (1.65 -> 2.09 ms for the 2^29-row coarse pass).
+template <class K>
+static cudaError_t set_carveout(K kernel, bool shared) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, shared ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
+}
+
+template <int INPUT, bool HOT, bool PEER = false>
+static olap_status launch_rpart_t(olap_ctx* ctx, const RPartArgs& a, unsigned grid, bool shared, cudaStream_t s) {
+  OLAP_CUDA(set_carveout(rpart_kernel<INPUT, HOT, PEER>, shared));
+  rpart_kernel<INPUT, HOT, PEER><<<grid, kRThreads, 0, s>>>(a);
   count_launch(ctx);
   return OLAP_OK;
 }
@@ -388,10 +431,11 @@ static olap_status launch_rpart(olap_ctx* ctx, const RPartArgs& a, int input, un
   uint64_t grid = (uint64_t)ctx->sm_count * (input == kInRaw ? 4 : 3);
   if (grid_limit && grid > grid_limit) grid = grid_limit;
   if (grid > tiles) grid = tiles;
-  const bool hot = a.hot_keys != nullptr;
-  if (input == kInRaw) return hot ? launch_rpart_t<kInRaw, true>(ctx, a, (unsigned)grid, s) : launch_rpart_t<kInRaw, false>(ctx, a, (unsigned)grid, s);
-  if (input == kInRegionsCarry) return launch_rpart_t<kInRegionsCarry, false>(ctx, a, (unsigned)grid, s);
-  return launch_rpart_t<kInRegionsPos, false>(ctx, a, (unsigned)grid, s);
+  const bool hot = a.hot_keys != nullptr, peer = a.peer_out[0] != nullptr, shared = grid_limit != 0;
+  if (input == kInRaw && peer) return hot ? launch_rpart_t<kInRaw, true, true>(ctx, a, (unsigned)grid, shared, s) : launch_rpart_t<kInRaw, false, true>(ctx, a, (unsigned)grid, shared, s);
+  if (input == kInRaw) return hot ? launch_rpart_t<kInRaw, true>(ctx, a, (unsigned)grid, shared, s) : launch_rpart_t<kInRaw, false>(ctx, a, (unsigned)grid, shared, s);
+  if (input == kInRegionsCarry) return launch_rpart_t<kInRegionsCarry, false>(ctx, a, (unsigned)grid, shared, s);
+  return launch_rpart_t<kInRegionsPos, false>(ctx, a, (unsigned)grid, shared, s);
 }
 
 uint32_t djoin_partitions(uint64_t rrange) { return (uint32_t)((rrange + kRKeys - 1) >> kRShift); }
@@ -417,8 +461,9 @@ static olap_status partition_rows(olap_ctx* ctx, const RInput& in, int64_t rmin,
   memset(&a, 0, sizeof(a));
   a.rmin = (uint64_t)rmin; a.rrange = rrange; a.flags = flags; a.oob_is_error = unique ? 1 : 0;
   if (in.regions) {  // multi-GPU: the shuffle already did the coarse level
-    if ((1u << in.reg_bits) > (uint32_t)kRThreads) { set_error("shuffle regions span more than 256 key ranges"); return OLAP_ERR_BAD_ARG; }
-    a.in = in.regions; a.reg_cur = in.reg_cur; a.reg_cap = in.reg_cap; a.n_reg = in.n_reg; a.reg_mask = in.reg_mask; a.reg_bits = in.reg_bits;
+    if (in.reg_parts > (uint32_t)kRThreads || !in.reg_q) { set_error("shuffle regions span more than 256 key ranges"); return OLAP_ERR_BAD_ARG; }
+    a.in = in.regions; a.reg_cur = in.reg_cur; a.reg_cap = in.reg_cap; a.n_reg = in.n_reg; a.reg_q = in.reg_q; a.reg_parts = in.reg_parts;
+    a.id_base = in.id_base;
     a.shift = kRShift; a.cap = cap; a.cursor = cursor; a.out = out;
     OLAP_TRY(launch_rpart(ctx, a, kInRegionsPos, grid_limit, s));
     if (mark_fine) phase_mark(ctx, s, mark_fine);
@@ -445,7 +490,7 @@ static olap_status partition_rows(olap_ctx* ctx, const RInput& in, int64_t rmin,
   if (mark_coarse) phase_mark(ctx, s, mark_coarse);
   RPartArgs f;
   memset(&f, 0, sizeof(f));
-  f.in = coarse; f.reg_cur = cur1; f.reg_cap = cap1; f.n_reg = C; f.reg_mask = 0xFFFFFFFFu; f.reg_bits = kRFineBits;
+  f.in = coarse; f.reg_cur = cur1; f.reg_cap = cap1; f.n_reg = C; f.reg_q = C; f.reg_parts = 1u << kRFineBits;
   f.shift = kRShift; f.cap = cap; f.cursor = cursor; f.out = out; f.flags = flags;
   OLAP_TRY(launch_rpart(ctx, f, kInRegionsCarry, grid_limit, s));
   count_launch(ctx);
@@ -473,35 +518,48 @@ olap_status dj_build_prepare(olap_ctx* ctx, const RInput& in, int64_t rmin, uint
   return OLAP_OK;
 }
 
-// Probe one batch: partition it by key range, then build + probe every range in shared memory.  Asynchronous on s.
-// d_flags (device, kFlagWords u32, written here) receives the probe-side flags OR-ed with the build side's: a set word means the
-// pairs / count of this call must not be used and the caller takes another path (overflow: skewed probe keys, retry with hot = 1
-// or bucket tables; out of range: stale remembered key range; dup: repeated build key -> bucket tables).
-// np_cap: upper bound of the batch's rows (sizes the regions).
-olap_status dj_probe(const DJBuild& b, const RInput& in, uint64_t np_cap, olap_pair* out, uint64_t max_matches, unsigned long long* d_count, int hot,
-                     unsigned grid_limit, cudaStream_t s, uint32_t* d_flags) {
+// ---- probing in three steps, so that rows can arrive batch by batch and still be joined with ONE build of every table:
+//   dj_probe_begin  regions for up to np_cap rows (pool memory, cursors zeroed)
+//   dj_probe_add    partition one batch of rows into the regions (appends; any number of times)
+//   dj_probe_join   build + probe every key range in shared memory over what has been added, then reset the regions
+// The multi-GPU path adds a chunk as soon as its shuffle has landed and joins once per group of chunks: a join CTA rebuilds its
+// 128 KB table per call, which costs as much as probing 2^15 rows -- chunk-wise joins at 2^14 probe rows per range spent more time
+// building than probing (14.3 ms of local work per 2^28 x 2^30 join in 8 chunks against 8.3 ms in one piece).
+olap_status dj_probe_begin(const DJBuild& b, uint64_t np_cap, int hot, cudaStream_t s, DJProbe* p) {
   olap_ctx* ctx = b.ctx;
-  const uint32_t P = b.P, PP = b.PP;
-  const uint32_t slack = hot ? 60 : 25;
-  const uint32_t pcap = region_cap(np_cap, P, slack);
-  OLAP_CUDA(cudaMemcpyAsync(d_flags, b.bctl + PP, kFlagWords * 4, cudaMemcpyDeviceToDevice, s));
-  if ((uint64_t)P * pcap >= 0xFFFFFFFFULL) {  // positions are u32
-    OLAP_CUDA(cudaMemsetAsync(d_flags + kFlagOverflow, 1, 4, s));
-    return OLAP_OK;
-  }
-  Scratch sc(ctx, s);
-  uint64_t* prows = nullptr;
-  uint32_t* ctl = nullptr;  // [PP] probe cursors | ticket (4) | hot keys | hot ids | hot_n (4)
-  const uint64_t ctl_words = (uint64_t)PP + 4 + 2 * kHotSlots + 4;
-  OLAP_TRY(sc.get<uint64_t>((uint64_t)P * pcap, &prows));
-  OLAP_TRY(sc.get<uint32_t>(ctl_words, &ctl));
-  OLAP_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
+  p->b = &b; p->hot = hot == 1; p->np_cap = np_cap;   // hot = 2: room for skew, but the heavy hitters were handled upstream (multi-GPU shuffle)
+  p->slack = hot == 2 ? 100 : hot ? 60 : 25;
+  p->pcap = region_cap(np_cap, b.P, p->slack);
+  p->prows = nullptr; p->ctl = nullptr;
+  if ((uint64_t)b.P * p->pcap >= 0xFFFFFFFFULL) { p->pcap = 0; return OLAP_OK; }  // positions are u32: every add raises the overflow flag
+  const uint64_t ctl_words = (uint64_t)b.PP + 4 + 2 * kHotSlots + 4;
+  OLAP_TRY(pool_alloc(ctx, (uint64_t)b.P * p->pcap * 8 + 32, s, (void**)&p->prows));
+  OLAP_TRY(pool_alloc(ctx, ctl_words * 4, s, (void**)&p->ctl));
+  OLAP_CUDA(cudaMemsetAsync(p->ctl, 0, ctl_words * 4, s));
   count_launch(ctx);
-  uint32_t *pcur = ctl, *ticket = ctl + PP, *hot_keys = ticket + 4, *hot_ids = hot_keys + kHotSlots, *hot_n = hot_ids + kHotSlots;
+  return OLAP_OK;
+}
 
+void dj_probe_end(DJProbe& p, cudaStream_t s) {
+  if (!p.b) return;
+  if (p.prows) { pool_free(p.b->ctx, p.prows, s); p.prows = nullptr; }
+  if (p.ctl) { pool_free(p.b->ctx, p.ctl, s); p.ctl = nullptr; }
+  p.b = nullptr;
+}
+
+// d_flags (device, kFlagWords u32): words are only ever SET here (overflow: skewed probe keys, retry with hot = 1 or bucket
+// tables).  out / max_matches / d_count: where heavy-hitter pairs go when p.hot (they are joined in this very pass).
+olap_status dj_probe_add(DJProbe& p, const RInput& in, olap_pair* out, uint64_t max_matches, unsigned long long* d_count, unsigned grid_limit,
+                         cudaStream_t s, uint32_t* d_flags) {
+  const DJBuild& b = *p.b;
+  olap_ctx* ctx = b.ctx;
+  if (!p.pcap) { OLAP_CUDA(cudaMemsetAsync(d_flags + kFlagOverflow, 1, 4, s)); return OLAP_OK; }
+  uint32_t *pcur = p.ctl, *ticket = p.ctl + b.PP, *hot_keys = ticket + 4, *hot_ids = hot_keys + kHotSlots, *hot_n = hot_ids + kHotSlots;
+  Scratch sc(ctx, s);
   RPartArgs ha;
   memset(&ha, 0, sizeof(ha));
-  if (hot && !in.regions) {
+  bool hot = false;
+  if (p.hot && !in.regions) {
     HotArgs h;
     memset(&h, 0, sizeof(h));
     h.n_samples = 1u << 16;
@@ -511,6 +569,7 @@ olap_status dj_probe(const DJBuild& b, const RInput& in, uint64_t np_cap, olap_p
     uint32_t* tab = nullptr;
     OLAP_TRY(sc.get<uint32_t>(2ULL * h.tab_slots, &tab));
     OLAP_CUDA(cudaMemsetAsync(tab, 0, 2ULL * h.tab_slots * 4, s));
+    OLAP_CUDA(cudaMemsetAsync(hot_keys, 0, (2ULL * kHotSlots + 4) * 4, s));
     h.tab_key = tab; h.tab_cnt = tab + h.tab_slots;
     h.hot_keys = hot_keys; h.hot_ids = hot_ids; h.hot_n = hot_n;
     h.min_count = 3;
@@ -520,22 +579,350 @@ olap_status dj_probe(const DJBuild& b, const RInput& in, uint64_t np_cap, olap_p
     count_launch(ctx, 4);
     phase_mark(ctx, s, "hot_keys");
     ha.hot_keys = hot_keys; ha.hot_ids = hot_ids; ha.pairs = out; ha.max_matches = max_matches; ha.count = d_count;
-  } else hot = 0;
+    hot = true;
+  }
+  return partition_rows(ctx, in, b.rmin, b.rrange, b.P, p.pcap, pcur, p.prows, d_flags, false, p.slack, hot ? &ha : nullptr, grid_limit, s, sc,
+                        "partition_probe_coarse", "partition_probe");
+}
 
-  OLAP_TRY(partition_rows(ctx, in, b.rmin, b.rrange, P, pcap, pcur, prows, d_flags, false, slack, hot ? &ha : nullptr, grid_limit, s, sc,
-                          "partition_probe_coarse", "partition_probe"));
-
+// d_flags: dup (a repeated build key -> bucket tables) is set here.  Afterwards the regions are empty again.
+olap_status dj_probe_join(DJProbe& p, olap_pair* out, uint64_t max_matches, unsigned long long* d_count, unsigned grid_limit, cudaStream_t s,
+                          uint32_t* d_flags) {
+  const DJBuild& b = *p.b;
+  olap_ctx* ctx = b.ctx;
+  if (!p.pcap) return OLAP_OK;
   DJoinArgs j;
   memset(&j, 0, sizeof(j));
-  j.brows = b.brows; j.bcur = b.bctl; j.bcap = kRKeys; j.prows = prows; j.pcur = pcur; j.pcap = pcap; j.P = P;
-  j.ticket = ticket; j.flags = d_flags; j.out = out; j.max_matches = max_matches; j.count = d_count;
+  j.brows = b.brows; j.bcur = b.bctl; j.bcap = kRKeys; j.prows = p.prows; j.pcur = p.ctl; j.pcap = p.pcap; j.P = b.P;
+  j.ticket = p.ctl + b.PP; j.flags = d_flags; j.out = out; j.max_matches = max_matches; j.count = d_count;
   const size_t smem = (size_t)kRKeys * 4;
-  OLAP_CUDA(cudaFuncSetAttribute(djoin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unsigned grid = (unsigned)std::min<uint32_t>((uint32_t)ctx->sm_count, P);
-  if (grid_limit && grid > grid_limit) grid = grid_limit;
-  djoin_kernel<<<grid, kDJThreads, smem, s>>>(j);
+  unsigned grid = (unsigned)std::min<uint32_t>((uint32_t)ctx->sm_count, b.P);
+  if (grid_limit) {  // shared SMs (multi-GPU: a shuffle CTA of the next chunk lives next to every join CTA)
+    OLAP_CUDA(cudaFuncSetAttribute(djoin_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OLAP_CUDA(set_carveout(djoin_shared_kernel, true));
+    djoin_shared_kernel<<<grid, 768, smem, s>>>(j);
+  } else {
+    OLAP_CUDA(cudaFuncSetAttribute(djoin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OLAP_CUDA(set_carveout(djoin_kernel, false));
+    djoin_kernel<<<grid, 1024, smem, s>>>(j);
+  }
   count_launch(ctx);
   phase_mark(ctx, s, "build_probe_smem");
+  OLAP_CUDA(cudaGetLastError());
+  OLAP_CUDA(cudaMemsetAsync(p.ctl, 0, ((uint64_t)b.PP + 4) * 4, s));  // cursors + ticket: ready for the next group
+  return OLAP_OK;
+}
+
+// Probe one batch in one go.  Asynchronous on s.  d_flags (device, kFlagWords u32, written here) receives the probe-side flags
+// OR-ed with the build side's: a set word means the pairs / count of this call must not be used and the caller takes another path
+// (overflow: skewed probe keys, retry with hot = 1 or bucket tables; out of range: stale remembered key range; dup: repeated build
+// key -> bucket tables).  np_cap: upper bound of the batch's rows (sizes the regions).
+olap_status dj_probe(const DJBuild& b, const RInput& in, uint64_t np_cap, olap_pair* out, uint64_t max_matches, unsigned long long* d_count, int hot,
+                     unsigned grid_limit, cudaStream_t s, uint32_t* d_flags) {
+  OLAP_CUDA(cudaMemcpyAsync(d_flags, b.bctl + b.PP, kFlagWords * 4, cudaMemcpyDeviceToDevice, s));
+  DJProbe p;
+  olap_status st = dj_probe_begin(b, np_cap, hot && !in.regions, s, &p);
+  if (st == OLAP_OK) st = dj_probe_add(p, in, out, max_matches, d_count, grid_limit, s, d_flags);
+  if (st == OLAP_OK) st = dj_probe_join(p, out, max_matches, d_count, grid_limit, s, d_flags);
+  dj_probe_end(p, s);
+  return st;
+}
+
+// ------------------------------------------------------------------------------------------- the shuffle kernel (TMA write-out)
+// The multi-GPU shuffle as its own kernel, built to saturate NVLink from ONE CTA per SM so that the local partition + join
+// kernels of the previous chunk keep the rest of the SM (registers, shared memory):
+//   * every (tile, region) run is padded to an even number of rows (the pad is the all-ones word, which the receiver's partition
+//     pass skips) so that runs start 16-byte aligned both in the stage and in the region;
+//   * the write-out is one cp.async.bulk (shared -> global, the TMA engine; UBLKCP in SASS) per non-empty run, issued by the thread
+//     that owns the partition -- no LSU instructions, no registers, full-size NVLink packets;
+//   * the stage is double-buffered: the bulk copies of tile t drain over NVLink while tile t + 1 is loaded, ranked and staged;
+//     a thread waits for its own copy of tile t - 1 (cp.async.bulk.wait_group.read 1) before that buffer is overwritten.
+// Measured before this kernel (rpart_kernel<raw, peer>, 8-byte stores from 2 CTAs per SM): 436 GB/s per direction at 2 GPUs, and
+// the shuffle's register footprint kept the join kernel off the SMs (20.4 ms per step = shuffle 12.3 + local 8, no overlap).
+constexpr int kShufStage = kRTile + kRThreads;   // rows per stage buffer: a tile plus one pad word per partition
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 96 registers x 256 threads = 24 K: one shuffle CTA + two partition CTAs (2 x 20 K) or one join CTA (36 K) fill an SM's 64 K
+template <bool HOT>
+__global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs a) {
+  constexpr int R = kRRows, NW = kRThreads / 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* stage0 = reinterpret_cast<uint64_t*>(smem_raw);           // [2][kShufStage]
+  __shared__ uint32_t cnt[kRThreads];
+  __shared__ uint32_t hotk[HOT ? kHotSlots : 1];
+  __shared__ uint32_t s_warp[NW];
+  __shared__ uint32_t s_hot[2];
+  __shared__ unsigned long long s_hotbase;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cnt[tid] = 0;
+  if (HOT) {
+    for (int i = tid; i < kHotSlots; i += kRThreads) hotk[i] = a.hot_keys[i];
+  }
+  if (tid == 0) { s_hot[0] = s_hot[1] = 0; }
+  __syncthreads();
+  // this thread's partition: destination rank, region there
+  const uint32_t my_dest = min(peer_dest(a, (uint32_t)tid), 7u);
+  uint64_t* const my_region = a.peer_out[my_dest] + (uint64_t)(a.peer_rank * a.peer_q + (uint32_t)tid % a.peer_q) * a.cap;
+
+  const uint32_t tiles = (uint32_t)((a.n + kRTile - 1) / kRTile);
+  int par = 1;
+  uint64_t key[R];
+  {
+    const uint64_t row0 = (uint64_t)blockIdx.x * kRTile;
+#pragma unroll
+    for (int k = 0; k < R; k++) { const uint64_t row = row0 + (uint64_t)k * kRThreads + tid; key[k] = row < a.n ? ld_stream_u64(a.in + row) : 0; }
+  }
+  for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    par ^= 1;
+    uint64_t* stage = stage0 + (size_t)par * kShufStage;
+    const uint64_t row0 = (uint64_t)t * kRTile;
+    // phase 1: offset, partition (= sub-range of the global domain), rank inside the tile.  All of a thread's 16 shared-memory
+    // atomics are issued before any result is used: with one CTA of 8 warps per SM nothing else hides their latency.
+    uint32_t d[R], pr[R];   // pr = partition << 16 | rank; kREmpty: dead row; bit 31: heavy hitter (slot in the low bits)
+    const bool full = row0 + kRTile <= a.n;   // uniform: interior tiles skip the per-row bounds checks
+    bool oob = false;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      bool ok = full || row0 + (uint64_t)k * kRThreads + tid < a.n;
+      const uint64_t off = key[k] - a.rmin;
+      if (off >= a.rrange) { oob = oob || ok; ok = false; }
+      d[k] = (uint32_t)off;
+      pr[k] = ok ? 0u : kREmpty;
+      if (HOT && ok) {
+        uint32_t s = hot_slot_of(d[k]);
+        for (;;) {
+          const uint32_t hk = hotk[s];
+          if (hk == 0) break;
+          if (hk == d[k] + 1) { pr[k] = 0x80000000u | s; atomicAdd(&s_hot[par], 1u); break; }
+          s = (s + 1) & (kHotSlots - 1);
+        }
+      }
+    }
+    uint32_t rank[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) rank[k] = pr[k] == 0u ? atomicAdd(&cnt[peer_part(a, d[k])], 1u) : 0u;
+    if (oob && a.oob_is_error) a.flags[kFlagOutOfRange] = 1;
+    // the next tile's keys: in flight during the scan, the staging and the write-out of this one
+    {
+      const uint64_t nrow0 = row0 + (uint64_t)gridDim.x * kRTile;
+      if (nrow0 + kRTile <= a.n) {
+#pragma unroll
+        for (int k = 0; k < R; k++) key[k] = ld_stream_u64(a.in + nrow0 + (uint64_t)k * kRThreads + tid);
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; k++) { const uint64_t row = nrow0 + (uint64_t)k * kRThreads + tid; key[k] = row < a.n ? ld_stream_u64(a.in + row) : 0; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) if (pr[k] == 0u) pr[k] = (peer_part(a, d[k]) << 16) | rank[k];
+    __syncthreads();
+    // phase 2: runs padded to an even length; one global atomic (local memory: this rank is the only writer of its regions)
+    const uint32_t c = cnt[tid], cp = (c + 1) & ~1u;
+    const uint32_t got = c ? atomicAdd(&a.cursor[tid], cp) : 0u;
+    if (tid == 0) s_hot[par ^ 1] = 0;
+    uint32_t inc = cp;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) s_warp[warp] = inc;
+    // the bulk copy this thread issued two tiles ago read from the buffer that is about to be overwritten
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+    uint32_t wbase = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) wbase += w < warp ? s_warp[w] : 0u;
+    const uint32_t off = wbase + inc - cp;
+    cnt[tid] = off;
+    if (c & 1) stage[off + c] = ~0ULL;  // the pad word
+    __syncthreads();
+    // phase 3: scatter into the stage in partition order, already in the receiver's form {offset in its slice, source row id}
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      if (pr[k] == kREmpty) continue;
+      const uint32_t id = a.id_base + (uint32_t)(row0 + (uint64_t)k * kRThreads + tid);
+      if (HOT && (pr[k] & 0x80000000u)) {
+        const uint32_t pos = kShufStage - 1 - (atomicAdd(&s_hot[par], 0x10000u) >> 16);
+        stage[pos] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (pr[k] & (kHotSlots - 1)));
+      } else {
+        const uint32_t part = pr[k] >> 16;
+        const uint32_t dl = d[k] - peer_dest(a, part) * (a.peer_q * a.peer_subw);
+        stage[cnt[part] + (pr[k] & 0xFFFFu)] = ((uint64_t)dl << 32) | id;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staged rows become visible to the TMA engine
+    __syncthreads();
+    // phase 4: one bulk copy per run, shared -> (peer) global.  The reservation's round trip (an atomic in local memory) is first
+    // needed here, two barriers after it was issued.
+    const bool over = got + cp > a.cap;
+    if (over) a.flags[kFlagOverflow] = 1;
+    if (c && !over) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(my_region + got), "r"(smem_u32(stage + off)), "r"(cp * 8u)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    cnt[tid] = 0;
+    if (HOT) {
+      const uint32_t nh = s_hot[par] & 0xFFFFu;
+      if (nh) {
+        if (tid == 0) s_hotbase = atomicAdd(a.count, (unsigned long long)nh);
+        __syncthreads();
+        const unsigned long long base = s_hotbase;
+        for (uint32_t i = tid; i < nh; i += kRThreads) {
+          const uint64_t v = stage[kShufStage - 1 - i];  // {probe row : hi, replicated build row : lo}
+          if (a.pairs && base + i < a.max_matches) a.pairs[base + i] = olap_pair{(uint32_t)v, (uint32_t)(v >> 32)};
+        }
+      }
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all copies have landed before the CTA's shared memory goes away
+}
+
+// ------------------------------------------------------------------------------------------- multi-GPU shuffle by key range
+// Rows of `keys` -> the peers' receive slabs (see RPartArgs PEER).  cursor: [256] u32 in local memory, zeroed by the caller on the
+// same stream; flags: local kFlagWords.  hot: optional heavy-hitter table -- probe rows carrying a hot key stay on this rank and
+// are joined here against the replicated build rows of those keys.
+olap_status range_shuffle(olap_ctx* ctx, const uint64_t* keys, uint64_t n, uint32_t id_base, int64_t gmin, uint64_t grange, uint32_t q, uint32_t subw,
+                          int rank, int world, uint64_t* const* peer_regions, uint32_t cap, uint32_t* cursor, uint32_t* flags, bool build_side,
+                          const HotRef* hot, unsigned grid_limit, bool tma, cudaStream_t s) {
+  if (world > 8 || (uint64_t)world * q > (uint64_t)kRThreads) { set_error("the range shuffle serves <= 8 ranks and <= 256 regions per pass"); return OLAP_ERR_BAD_ARG; }
+  RPartArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = keys; a.n = n; a.id_base = id_base; a.rmin = (uint64_t)gmin; a.rrange = grange;
+  a.cap = cap; a.cursor = cursor; a.flags = flags; a.oob_is_error = build_side ? 1 : 0;
+  for (int i = 0; i < world; i++) a.peer_out[i] = peer_regions[i];
+  a.peer_q = q; a.peer_subw = subw; a.peer_rank = (uint32_t)rank;
+  {
+    const uint64_t F = subw >> kRShift;
+    if (F == 0 || F > 256 || (F << kRShift) != subw || q == 0 || q > 256) { set_error("shuffle sub-ranges must be F x 2^15 keys wide, F <= 256"); return OLAP_ERR_BAD_ARG; }
+    a.peer_mf = ((1ULL << 32) + F - 1) / F;
+    a.peer_mq = (uint32_t)(((1u << 24) + q - 1) / q);
+  }
+  if (hot && hot->hot_keys) { a.hot_keys = hot->hot_keys; a.hot_ids = hot->hot_ids; a.pairs = hot->pairs; a.max_matches = hot->max_matches; a.count = hot->count; }
+  if (!tma) {  // plain stores from the partition kernel at full occupancy: the rows go to local memory (outbox / own slab)
+    OLAP_TRY(launch_rpart(ctx, a, kInRaw, grid_limit, s));
+  } else {
+    const uint64_t tiles = (n + kRTile - 1) / kRTile;
+    uint64_t grid = grid_limit ? grid_limit : (uint64_t)ctx->sm_count;
+    if (grid > tiles) grid = tiles;
+    const size_t smem = (size_t)2 * kShufStage * 8;
+    if (a.hot_keys) {
+      OLAP_CUDA((cudaFuncSetAttribute(shuffle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+      OLAP_CUDA(set_carveout(shuffle_kernel<true>, true));
+      shuffle_kernel<true><<<(unsigned)grid, kRThreads, smem, s>>>(a);
+    } else {
+      OLAP_CUDA((cudaFuncSetAttribute(shuffle_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
+      OLAP_CUDA(set_carveout(shuffle_kernel<false>, true));
+      shuffle_kernel<false><<<(unsigned)grid, kRThreads, smem, s>>>(a);
+    }
+    count_launch(ctx);
+  }
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
+
+// after the shuffle kernel: this rank's row count of every region it filled, written into the owners' count arrays
+__global__ void shard_publish_kernel(const uint32_t* __restrict__ cursor, uint32_t cap, uint32_t q, uint32_t rank, uint32_t world, uint32_t* const* peer_counts8,
+                                     uint32_t* p0, uint32_t* p1, uint32_t* p2, uint32_t* p3, uint32_t* p4, uint32_t* p5, uint32_t* p6, uint32_t* p7) {
+  uint32_t* pc[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
+  const uint32_t j = threadIdx.x;
+  if (j < world * q) pc[j / q][rank * q + j % q] = min(cursor[j], cap);
+}
+
+olap_status range_shuffle_publish(olap_ctx* ctx, const uint32_t* cursor, uint32_t cap, uint32_t q, int rank, int world, uint32_t* const* peer_counts,
+                                  cudaStream_t s) {
+  uint32_t* pc[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < world; i++) pc[i] = peer_counts[i];
+  shard_publish_kernel<<<1, 256, 0, s>>>(cursor, cap, q, (uint32_t)rank, (uint32_t)world, nullptr, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
+
+// ------------------------------------------------------------------------------------------- heavy hitters across ranks
+uint32_t hot_table_slots() { return kHotSlots; }
+uint32_t hot_slot_host(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - 11); }
+
+// (offset + 1, sample count) of every sampled key seen at least min_count times -> list (at most cap entries)
+__global__ void hot_extract_kernel(const uint32_t* __restrict__ tab_key, const uint32_t* __restrict__ tab_cnt, uint32_t slots, uint32_t min_count,
+                                   uint32_t* __restrict__ out_key, uint32_t* __restrict__ out_cnt, uint32_t cap, uint32_t* __restrict__ out_n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += gridDim.x * blockDim.x) {
+    const uint32_t k = tab_key[i], c = tab_cnt[i];
+    if (k && c >= min_count) {
+      const uint32_t pos = atomicAdd(out_n, 1u);
+      if (pos < cap) { out_key[pos] = k; out_cnt[pos] = c; }
+    }
+  }
+}
+
+// Sample one rank's probe shard (2^16 rows) and list the keys seen >= 3 times.  scratch: 2 x 2^18 + 2 x cap + 4 u32.
+olap_status hot_candidates(olap_ctx* ctx, const uint64_t* keys, uint64_t n, int64_t gmin, uint64_t grange, uint32_t* scratch, uint32_t cap,
+                           uint32_t** out_key, uint32_t** out_cnt, uint32_t** out_n, cudaStream_t s) {
+  HotArgs h;
+  memset(&h, 0, sizeof(h));
+  h.n_samples = 1u << 17;   // per rank; the ranks' counts are summed before the cut
+  h.keys = keys; h.n = n; h.stride = std::max<uint64_t>(n / h.n_samples, 1);
+  h.rmin = (uint64_t)gmin; h.rrange = grange;
+  h.tab_slots = 1u << 18;
+  h.tab_key = scratch; h.tab_cnt = scratch + h.tab_slots;
+  *out_key = scratch + 2 * h.tab_slots; *out_cnt = *out_key + cap; *out_n = *out_cnt + cap;
+  OLAP_CUDA(cudaMemsetAsync(scratch, 0, (2ULL * h.tab_slots + 2ULL * cap + 4) * 4, s));
+  if (n) {
+    hot_sample_kernel<<<(h.n_samples + 255) / 256, 256, 0, s>>>(h);
+    hot_extract_kernel<<<64, 256, 0, s>>>(h.tab_key, h.tab_cnt, h.tab_slots, 3, *out_key, *out_cnt, cap, *out_n);
+    count_launch(ctx, 2);
+  }
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
+
+// The build row of every hot key this rank owns, in (source rank, source row) form: one CTA per slot scans the key's range
+// partition of the partitioned build side.  out[slot] = ((src_rank << 32) | src_row) + 1, or 0 when the key is not in this rank's
+// slice / has no build row (the ranks then take the maximum).
+__global__ void __launch_bounds__(256) hot_resolve_global_kernel(const uint32_t* __restrict__ hot_keys, uint64_t* __restrict__ out, const uint64_t* brows,
+                                                                 const uint32_t* bcur, uint32_t bcap_fine, const uint64_t* slab_b, uint32_t slab_bcap,
+                                                                 uint32_t q, uint64_t slice, uint32_t rank) {
+  __shared__ uint32_t s_found;
+  const uint32_t slot = blockIdx.x, k = hot_keys[slot];
+  if (threadIdx.x == 0) out[slot] = 0;
+  if (k == 0 || k == 0xFFFFFFFFu) return;
+  const uint64_t d = k - 1;
+  if (d / slice != rank) return;
+  const uint32_t dl = (uint32_t)(d - (uint64_t)rank * slice), p = dl >> kRShift, n = min(bcur[p], bcap_fine);
+  if (threadIdx.x == 0) s_found = kREmpty;
+  __syncthreads();
+  const uint64_t* rows = brows + (uint64_t)p * bcap_fine;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint64_t v = rows[i];
+    if ((uint32_t)(v >> 32) == dl) s_found = (uint32_t)v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_found != kREmpty) {
+    const uint32_t pos = s_found;   // position in this rank's build slab
+    out[slot] = (((uint64_t)((pos / slab_bcap) / q) << 32) | (uint32_t)slab_b[pos]) + 1;
+  }
+}
+
+olap_status hot_resolve_global(olap_ctx* ctx, const uint32_t* hot_keys, uint64_t* out, const DJBuild& b, const uint64_t* slab_b, uint32_t slab_bcap,
+                               uint32_t q, uint64_t slice, int rank, cudaStream_t s) {
+  hot_resolve_global_kernel<<<kHotSlots, 256, 0, s>>>(hot_keys, out, b.brows, b.bctl, kRKeys, slab_b, slab_bcap, q, slice, (uint32_t)rank);
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
+
+// merged[slot] == 0: no rank holds a build row for the key -> tombstone (its probe rows travel the normal way and match nothing);
+// hot_ids[slot] = slot: the pair emitted for a hot probe row names the slot, whose build row is merged[slot] - 1
+__global__ void hot_finalize_kernel(uint32_t* hot_keys, uint32_t* hot_ids, const uint64_t* merged) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kHotSlots) return;
+  hot_ids[i] = i;
+  if (hot_keys[i] && merged[i] == 0) hot_keys[i] = 0xFFFFFFFFu;
+}
+
+olap_status hot_finalize(olap_ctx* ctx, uint32_t* hot_keys, uint32_t* hot_ids, const uint64_t* merged, cudaStream_t s) {
+  hot_finalize_kernel<<<kHotSlots / 256, 256, 0, s>>>(hot_keys, hot_ids, merged);
+  count_launch(ctx);
   OLAP_CUDA(cudaGetLastError());
   return OLAP_OK;
 }

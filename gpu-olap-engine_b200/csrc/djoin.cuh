@@ -10,8 +10,8 @@ enum { kFlagOverflow = 0, kFlagOutOfRange = 1, kFlagDup = 2, kFlagWords = 4 };
 struct RInput {
   const uint64_t* keys = nullptr; uint64_t n = 0; uint32_t id_base = 0;   // raw keys; row id = id_base + row
   // n_reg regions of reg_cap packed words {key - rmin : u32 hi, source row id : u32 lo}, row counts on the device; region g
-  // holds keys of sub-range (g & reg_mask), 2^(15 + reg_bits) keys wide.  Row ids become positions g * reg_cap + row.
-  const uint64_t* regions = nullptr; const uint32_t* reg_cur = nullptr; uint32_t reg_cap = 0, n_reg = 0, reg_mask = 0; int reg_bits = 0;
+  // holds keys of sub-range g % reg_q, reg_parts * 2^15 keys wide.  Row ids become positions id_base + g * reg_cap + row.
+  const uint64_t* regions = nullptr; const uint32_t* reg_cur = nullptr; uint32_t reg_cap = 0, n_reg = 0, reg_q = 0, reg_parts = 0;
 };
 
 // The build side, partitioned by key range once and probed by one or many batches.
@@ -29,5 +29,34 @@ olap_status dj_build_prepare(olap_ctx* ctx, const RInput& in, int64_t rmin, uint
 olap_status dj_probe(const DJBuild& b, const RInput& in, uint64_t np_cap, olap_pair* out, uint64_t max_matches, unsigned long long* d_count,
                      int hot, unsigned grid_limit, cudaStream_t s, uint32_t* d_flags);
 void dj_build_free(DJBuild& b, cudaStream_t s);
+
+// a group of probe batches joined with one build of every shared-memory table (dj_probe_begin / _add ... / _join / _end)
+struct DJProbe {
+  const DJBuild* b = nullptr;
+  int hot = 0; uint32_t slack = 25, pcap = 0; uint64_t np_cap = 0;
+  uint64_t* prows = nullptr;   // [P][pcap] packed probe rows
+  uint32_t* ctl = nullptr;     // [PP] cursors | ticket (4) | hot keys | hot ids | hot_n (4)
+};
+olap_status dj_probe_begin(const DJBuild& b, uint64_t np_cap, int hot, cudaStream_t s, DJProbe* p);
+olap_status dj_probe_add(DJProbe& p, const RInput& in, olap_pair* out, uint64_t max_matches, unsigned long long* d_count, unsigned grid_limit,
+                         cudaStream_t s, uint32_t* d_flags);
+olap_status dj_probe_join(DJProbe& p, olap_pair* out, uint64_t max_matches, unsigned long long* d_count, unsigned grid_limit, cudaStream_t s,
+                          uint32_t* d_flags);
+void dj_probe_end(DJProbe& p, cudaStream_t s);
+
+// heavy-hitter table handed to a pass over raw probe keys: rows whose key is in it are joined on the spot
+struct HotRef { const uint32_t* hot_keys = nullptr; const uint32_t* hot_ids = nullptr; olap_pair* pairs = nullptr; uint64_t max_matches = 0; unsigned long long* count = nullptr; };
+uint32_t hot_table_slots();
+uint32_t hot_slot_host(uint32_t d);
+olap_status hot_candidates(olap_ctx* ctx, const uint64_t* keys, uint64_t n, int64_t gmin, uint64_t grange, uint32_t* scratch, uint32_t cap,
+                           uint32_t** out_key, uint32_t** out_cnt, uint32_t** out_n, cudaStream_t s);
+olap_status hot_resolve_global(olap_ctx* ctx, const uint32_t* hot_keys, uint64_t* out, const DJBuild& b, const uint64_t* slab_b, uint32_t slab_bcap,
+                               uint32_t q, uint64_t slice, int rank, cudaStream_t s);
+olap_status hot_finalize(olap_ctx* ctx, uint32_t* hot_keys, uint32_t* hot_ids, const uint64_t* merged, cudaStream_t s);
+olap_status range_shuffle(olap_ctx* ctx, const uint64_t* keys, uint64_t n, uint32_t id_base, int64_t gmin, uint64_t grange, uint32_t q, uint32_t subw,
+                          int rank, int world, uint64_t* const* peer_regions, uint32_t cap, uint32_t* cursor, uint32_t* flags, bool build_side,
+                          const HotRef* hot, unsigned grid_limit, bool tma, cudaStream_t s);
+olap_status range_shuffle_publish(olap_ctx* ctx, const uint32_t* cursor, uint32_t cap, uint32_t q, int rank, int world, uint32_t* const* peer_counts,
+                                  cudaStream_t s);
 
 }  // namespace olap

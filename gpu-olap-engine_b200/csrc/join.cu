@@ -875,11 +875,26 @@ __global__ void __launch_bounds__(kJoinThreads, DIRECT ? 6 : 4) join_pipeline_ke
 }
 
 // table arena: grown on demand, kept across calls; every table is cleared right before its build
+// The arena is ONE buffer per context while calls may come in on different streams: every user first makes its stream wait for
+// the previous user's event (arena_acquire) and records its own behind its last kernel (arena_release), so two joins on different
+// streams of one context run their pipelines one after the other instead of on top of each other.
 static olap_status ensure_arena(olap_ctx* ctx, uint64_t bytes) {
   if (ctx->table_arena_bytes >= bytes) return OLAP_OK;
-  if (ctx->table_arena) { OLAP_CUDA(cudaDeviceSynchronize()); OLAP_CUDA(cudaFree(ctx->table_arena)); ctx->table_arena = nullptr; ctx->table_arena_bytes = 0; }
+  if (ctx->table_arena) {
+    if (ctx->arena_used) OLAP_CUDA(cudaEventSynchronize(ctx->arena_ev));  // the last user is done with the old buffer
+    OLAP_CUDA(cudaFree(ctx->table_arena)); ctx->table_arena = nullptr; ctx->table_arena_bytes = 0;
+  }
   OLAP_CUDA(cudaMalloc(&ctx->table_arena, bytes));
   ctx->table_arena_bytes = bytes;
+  return OLAP_OK;
+}
+static olap_status arena_acquire(olap_ctx* ctx, cudaStream_t s) {
+  if (ctx->arena_used) OLAP_CUDA(cudaStreamWaitEvent(s, ctx->arena_ev, 0));
+  return OLAP_OK;
+}
+static olap_status arena_release(olap_ctx* ctx, cudaStream_t s) {
+  OLAP_CUDA(cudaEventRecord(ctx->arena_ev, s));
+  ctx->arena_used = true;
   return OLAP_OK;
 }
 
@@ -1012,6 +1027,29 @@ static olap_status detect_dense_keys(olap_ctx* ctx, const uint64_t* keys, uint64
   return OLAP_OK;
 }
 
+// min / max of a rank's shard of a key column for the multi-GPU join (shard.cu), remembered per (pointer, rows) in a map of its
+// own: a shard's range is judged against the GLOBAL row count, not the local one, and is verified by the shuffle pass.
+olap_status key_min_max(olap_ctx* ctx, const uint64_t* keys, uint64_t n, cudaStream_t s, int64_t* mn, int64_t* mx) {
+  auto it = ctx->shard_key_stats.find(keys);
+  if (env_u64("OLAP_KEY_STATS", 1) && it != ctx->shard_key_stats.end() && it->second.n == n) { *mn = it->second.min; *mx = it->second.max; return OLAP_OK; }
+  Scratch sc(ctx, s);
+  long long* d = nullptr;
+  OLAP_TRY(sc.get<long long>(2, &d));
+  const long long init[2] = {INT64_MAX, INT64_MIN};
+  long long mm[2];
+  OLAP_CUDA(cudaMemcpyAsync(d, init, 16, cudaMemcpyHostToDevice, s));
+  key_minmax_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, s>>>(keys, n, d);
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  OLAP_CUDA(cudaMemcpyAsync(mm, d, 16, cudaMemcpyDeviceToHost, s));
+  OLAP_CUDA(cudaStreamSynchronize(s));
+  if (ctx->shard_key_stats.size() > 4096) ctx->shard_key_stats.clear();
+  auto& st = ctx->shard_key_stats[keys];
+  st.n = n; st.min = mm[0]; st.max = mm[1]; st.have_range = true;
+  *mn = mm[0]; *mx = mm[1];
+  return OLAP_OK;
+}
+
 // The direct join with shared-memory tables (djoin.cu), run to completion: *retry = 0 when pairs / count stand, else the OR of
 // (1 << kFlag*) telling the caller why another path is needed.
 static olap_status smem_join(olap_ctx* ctx, const uint64_t* bk, uint64_t nb, const uint64_t* pk, uint64_t np, const KeyRange& r, uint32_t pid_base,
@@ -1057,6 +1095,7 @@ struct BuildSide {
   // is then prepared only if a probe reports that this representation cannot serve (repeated key, skew)
   DJBuild dj; bool use_dj = false; bool general_ready = true;
   const uint64_t* bkeys = nullptr;  // the caller keeps the build keys alive while the handle lives
+  cudaEvent_t last_use = nullptr;   // recorded behind every probe: the handle's memory is freed in order behind it
 };
 
 static olap_status build_side_free(BuildSide& b, cudaStream_t s) {
@@ -1151,6 +1190,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     while (R > 3 && R * nbk * 32 > (96ULL << 20)) R--;
     R = std::min<uint64_t>(R, P);
     OLAP_TRY(ensure_arena(ctx, R * nbk * 32));
+    OLAP_TRY(arena_acquire(ctx, s));
     uint32_t* sync = nullptr;
     const uint64_t sync_words = 1 + 3 * (uint64_t)P + 1 + 12;  // counters, padding to 8 bytes, 6 x u64 wait statistics
     OLAP_TRY(sc.get<uint32_t>(sync_words, &sync));
@@ -1187,6 +1227,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
     }
     phase_mark(ctx, s, direct ? "build_probe_direct" : "build_probe");
     OLAP_CUDA(cudaGetLastError());
+    OLAP_TRY(arena_release(ctx, s));
     if (direct) {  // a repeated build key cannot live in a direct table: the caller redoes the join with bucket tables
       uint32_t dup = 0;
       OLAP_CUDA(cudaMemcpyAsync(&dup, d_dup, 4, cudaMemcpyDeviceToHost, s));
@@ -1210,6 +1251,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   if (S < 1) S = 1;
   if (S > 8) S = 8;
   OLAP_TRY(ensure_arena(ctx, (uint64_t)S * nbk * 32));
+  OLAP_TRY(arena_acquire(ctx, s));
   OLAP_CUDA(cudaEventRecord(ctx->fork_ev, s));
   for (int k = 0; k < S; k++) OLAP_CUDA(cudaStreamWaitEvent(ctx->streams[k], ctx->fork_ev, 0));
   for (uint32_t p = 0; p < P; p++) {
@@ -1235,6 +1277,7 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   }
   phase_mark(ctx, s, "build_probe");
   OLAP_CUDA(cudaGetLastError());
+  OLAP_TRY(arena_release(ctx, s));
   return OLAP_OK;
 }
 
@@ -1463,6 +1506,8 @@ olap_status olap_join_probe(olap_join_build* build, const int64_t* probe_keys, u
     }
     OLAP_TRY(build_side_probe(b, (const uint64_t*)probe_keys, n_probe, probe_row_base, out_pairs, max_matches, d_count, s));
   }
+  if (!b.last_use) OLAP_CUDA(cudaEventCreateWithFlags(&b.last_use, cudaEventDisableTiming));
+  OLAP_CUDA(cudaEventRecord(b.last_use, s));
   return finish_count(ctx, d_count, host_count, out_pairs, max_matches, s);
 }
 
@@ -1472,7 +1517,10 @@ olap_status olap_join_build_destroy(olap_join_build* build) {
   {
     std::lock_guard<std::mutex> g(ctx->mu);
     cudaSetDevice(ctx->device);
+    // probes may still be running on the caller's stream (asynchronous when no host count was asked for): free behind them
+    if (build->b.last_use) { cudaStreamWaitEvent(ctx->streams[0], build->b.last_use, 0); }
     build_side_free(build->b, ctx->streams[0]);
+    if (build->b.last_use) { cudaEventDestroy(build->b.last_use); build->b.last_use = nullptr; }
   }
   delete build;
   return OLAP_OK;

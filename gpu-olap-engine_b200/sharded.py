@@ -269,8 +269,9 @@ class PeerExchange:
         lib, ctx = ops.lib, ops.ctx
         words = int(lib.olap_shuffle_scratch_words(ctx.handle, bits))
         scratch = ops.buffer("shuffle_scratch_" + names[0], words, torch.int32)
-        cnt = ops.empty(W, torch.int32)
-        _lib.check(lib.olap_shuffle_count_i64(ctx.handle, keys.data_ptr(), n, bits, scratch.data_ptr(), cnt.data_ptr(), ops._stream()))
+        cnt = torch.zeros(W, dtype=torch.int32, device=dev)
+        if n:   # a rank without rows still takes part in every collective below
+            _lib.check(lib.olap_shuffle_count_i64(ctx.handle, keys.data_ptr(), n, bits, scratch.data_ptr(), cnt.data_ptr(), ops._stream()))
         allc = torch.empty(W * W, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allc, cnt.to(torch.int64), group=self.group)
         Cm = allc.view(W, W).tolist()                       # Cm[s][d]: rows s sends to d (host waits: tiny)
@@ -283,7 +284,8 @@ class PeerExchange:
         dk = (C.c_void_p * W)(*[int(p) for p in hk.buffer_ptrs])
         di = (C.c_void_p * W)(*[int(p) for p in hi.buffer_ptrs])
         off = (C.c_uint64 * W)(*[sum(Cm[s2][d] for s2 in range(r)) for d in range(W)])
-        _lib.check(lib.olap_shuffle_scatter_i64(ctx.handle, keys.data_ptr(), n, bits, scratch.data_ptr(), dk, di, off, ops._stream()))
+        if n:
+            _lib.check(lib.olap_shuffle_scatter_i64(ctx.handle, keys.data_ptr(), n, bits, scratch.data_ptr(), dk, di, off, ops._stream()))
         hk.barrier()                                        # every rank's stores have landed
         self.bytes_sent += (n - Cm[r][r]) * 12
         return [tk[:recv_tot[r]], ti[:recv_tot[r]]], [(s2, Cm[s2][r]) for s2 in range(W)]
@@ -325,9 +327,16 @@ class ShardedJoin:
 
     def _fused(self, keys, n, tag):
         """Fused partition + peer-store shuffle of one side, or None when it is unavailable / would overflow."""
-        if self.peer is None or not self.fuse or n == 0 or self.x.world > 8 or not hasattr(self.ops, "lib"):
+        if self.peer is None or not self.fuse or self.x.world > 8 or not hasattr(self.ops, "lib"):
             return None
-        got = self.peer.fused_shuffle(self.ops, keys, n, ["recv_k" + tag, "recv_i" + tag], self._capacity(n))
+        # the capacity (it sizes a symmetric buffer: a collective) and the go / no-go decision must be the same on every rank:
+        # both derive from the LARGEST shard, not from this rank's row count
+        nmax = torch.tensor([n], dtype=torch.int64, device=keys.device)
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX, group=self.x.group)
+        nmax = int(nmax.item())
+        if nmax == 0:
+            return None
+        got = self.peer.fused_shuffle(self.ops, keys, n, ["recv_k" + tag, "recv_i" + tag], self._capacity(nmax))
         if got is None:
             return None
         (rk, ri), segs = got
@@ -339,7 +348,7 @@ class ShardedJoin:
         if got is not None:
             return got
         pk, pid, begin, count = self.ops.shuffle_partition(keys, n, self.x.bits, tag)
-        return self._exchange(pk, pid, begin, count, tag, self._capacity(n))
+        return self._exchange(pk, pid, begin, count, tag, None)   # NCCL path: no symmetric buffer, so no per-rank capacity to agree on
 
     def shuffle_both(self, build_keys, n_build, probe_keys, n_probe):
         """Both sides; on CUDA the build-side exchange runs on a side stream while the probe side is being partitioned."""
@@ -493,107 +502,197 @@ class ShardedGroupBy:
 
 
 # ------------------------------------------------------------------------------------------------- bench (N > 1)
-def bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, ClockSampler):
-    """bench.py's N > 1 leg: weak scaling, per-GPU 2^log2_build unique-key build x 2^log2_probe FK probe over the GLOBAL
-    key domain; rows are contiguous-sharded (not pre-partitioned by key).  value = rows of all ranks / max-over-ranks time."""
+def _slab_views(rj, torch):
+    """(build words, probe words) of this rank's receive slab as int64 tensors, plus the layout."""
+    lay = (C.c_uint64 * 8)()
+    _lib.check(rj.lib.olap_shard_layout(rj.handle, lay))
+    words_b, words_p = int(lay[0]), int(lay[1])
+    w = rj.slab.view(torch.int64)
+    return w[:words_b], w[words_b:words_b + words_p * rj.chunks], [int(x) for x in lay]
+
+
+def verify_range_join(rj, torch, dist, pairs, count, npb_global, hot_count=0):
+    """Every pair of this rank, on the device: the build word and the probe word the pair points at carry the same key offset,
+    no probe position appears twice, and (all probe keys match exactly one build key) the global count is the global probe rows."""
+    bw, pw, lay = _slab_views(rj, torch)
+    pr = pairs[:2 * count].view(-1, 2)
+    seen = torch.zeros(pw.numel(), dtype=torch.uint8, device=pairs.device)
+    step = 1 << 26
+    for a in range(0, count, step):
+        l = pr[a:a + step, 0].to(torch.int64) & 0xFFFFFFFF
+        r = pr[a:a + step, 1].to(torch.int64) & 0xFFFFFFFF
+        assert bool(((bw[l] >> 32) == (pw[r] >> 32)).all()), "sharded join: pair with different keys"
+        seen[r] = 1
+    assert int(seen.sum(dtype=torch.int64)) == count, "sharded join: a received probe row appears twice"
+    tot = torch.tensor([count + hot_count], dtype=torch.int64, device=pairs.device)
+    dist.all_reduce(tot)
+    assert int(tot.item()) == npb_global, f"global join count {int(tot.item())} != {npb_global}"
+
+
+def bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, ClockSampler, cpu_baseline=None):
+    """bench.py's N > 1 leg: weak scaling, per-GPU 2^log2_build unique-key build x 2^log2_probe FK probe over the GLOBAL key
+    domain; rows are contiguous-sharded (not pre-partitioned by key).  value = rows of all ranks / max-over-ranks time."""
+    from .shard import RangeShardedJoin
     ops = DeviceOps(ctx)
-    sj = ShardedJoin(ops)
-    # one stream for everything: torch's copies and NCCL collectives run on the context's stream 0, like the kernels
-    torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 0), device=ops.device))
+    dev = ops.device
     nb, npb = 1 << args.log2_build, 1 << args.log2_probe
     gnb = nb * world
-    dev = ops.device
+    chunks = int(os.environ.get("OLAP_SHARD_CHUNKS", "8"))
     build = ops.empty(nb, torch.int64); probe = ops.empty(npb, torch.int64)
-    ctx.generate(nb, 1, 3, gnb, row0=rank * nb, out=build.data_ptr())        # slice of a permutation of [0, world * 2^27)
-    ctx.generate(npb, 0, 33, gnb, row0=rank * npb, out=probe.data_ptr())     # uniform FK over the global build domain
+    ctx.generate(nb, 1, 3, gnb, row0=rank * nb, out=build.data_ptr())        # slice of a permutation of [0, world * 2^log2_build)
+    zipf = float(getattr(args, "zipf", 0.0) or 0.0)
+    if zipf > 0:
+        ctx.generate_fk(npb, 3, gnb, 33, zipf, row0=rank * npb, out=probe.data_ptr())   # FK ~ Zipf(s) over the global build rows
+    else:
+        ctx.generate(npb, 0, 33, gnb, row0=rank * npb, out=probe.data_ptr())            # uniform FK over the global build domain
     ctx.synchronize()
+    rj = RangeShardedJoin(ctx, nb, npb, chunks)
+    mm = int(npb * (2.5 if zipf > 0 else 1.25)) + 4096       # skew: the owners of warm (not hot) keys receive more than an even share
+    pairs = torch.empty(2 * mm, dtype=torch.int32, device=dev)
+    hot_pairs = torch.empty(2 * npb, dtype=torch.int32, device=dev) if zipf > 0 else None
 
     def step():
-        return sj.join(build, nb, probe, npb, max_matches=int(npb * 1.25) + 4096)
+        res = rj.join(build, nb, probe, npb, pairs, mm, hot=1 if zipf > 0 else 0, hot_pairs=hot_pairs, max_hot_pairs=npb)
+        assert res["supported"] and not any(res["flags"]), f"range-sharded join refused / flagged: {res}"
+        return res
 
     for _ in range(args.warmup):
         res = step()
-    total = torch.tensor([res["count"]], dtype=torch.int64, device=dev)
-    dist.all_reduce(total)
-    assert int(total.item()) == npb * world, f"global join count {int(total.item())} != {npb * world}"
+    verify_range_join(rj, torch, dist, pairs, res["count"], npb * world, res["hot_count"])     # all pairs of every rank, after warm-up
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sj.x.bytes_sent = 0
     launches0 = ctx.launch_count()
     dist.barrier(); torch.cuda.synchronize()
-    ev0.record()
+    ev0.record(rj.comm)
     for _ in range(args.steps):
         res = step()
-        torch.cuda.synchronize()
-    ev1.record()
+    rj.comm.wait_stream(rj.comp)
+    ev1.record(rj.comm)
     torch.cuda.synchronize(); dist.barrier()
-    sent = sj.x.bytes_sent / args.steps
-    # the exchange alone (both sides partitioned and shipped, no join), for the NVLink figure; outside the timed region
+    launches = ctx.launch_count() - launches0
+    phases = {k: v for k, v in ctx.last_phase_times().items() if k != "end"}
+    verify_range_join(rj, torch, dist, pairs, res["count"], npb * world, res["hot_count"])     # and of the last timed step
+    sent = (C.c_uint64 * world)()
+    _lib.check(rj.lib.olap_shard_sent_rows(rj.handle, sent, rj.comp.cuda_stream))
+    bytes_out = 8 * sum(int(sent[d]) for d in range(world) if d != rank)
+
+    # the exchange alone (both sides scattered into the peers' slabs, no local work), >= 5 warmed repetitions, for the NVLink figure
+    def shuffle_only():
+        lib, h, comm = rj.lib, rj.handle, rj.comm
+        gmin, gmax, gn = rj._global_range(build, nb)
+        _lib.check(lib.olap_shard_plan(h, gmin, gmax, gn, 0, comm.cuda_stream))
+        rj._barrier()
+        if rj.part is not comm:
+            ev = torch.cuda.Event(); ev.record(comm); rj.part.wait_event(ev)
+        rj._scatter(0, 0, build.data_ptr(), nb, 0)
+        cc = rj.chunk_cap
+        for k in range(rj.chunks):
+            lo = min(k * cc, npb); hi = min(lo + cc, npb)
+            rj._scatter(1, k, probe.data_ptr() + 8 * lo, hi - lo, lo)
+        rj._barrier()
+
+    # ... and the local work alone (second partition level + shared-memory join of every chunk, on what the last shuffle delivered)
+    def local_only():
+        lib, h, comp = rj.lib, rj.handle, rj.comp
+        _lib.check(lib.olap_shard_build(h, comp.cuda_stream))
+        for k in range(rj.chunks):
+            _lib.check(lib.olap_shard_probe(h, k, pairs.data_ptr(), mm, comp.cuda_stream))
+
+    torch.cuda.synchronize()
+    for _ in range(2):
+        shuffle_only()
+    torch.cuda.synchronize()
+    local_only()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    l0.record(rj.comp)
+    for _ in range(3):
+        local_only()
+    l1.record(rj.comp)
+    torch.cuda.synchronize()
+    local_ms = l0.elapsed_time(l1) / 3
+    reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize()
-    e0.record()
-    sj.shuffle_both(build, nb, probe, npb)
-    e1.record()
+    e0.record(rj.comm)
+    for _ in range(reps):
+        shuffle_only()
+    e1.record(rj.comm)
     torch.cuda.synchronize()
-    t_shuffle = e0.elapsed_time(e1) * args.steps
-    ms = torch.tensor([ev0.elapsed_time(ev1), t_shuffle], dtype=torch.float64, device=dev)
+    ms = torch.tensor([ev0.elapsed_time(ev1) / args.steps, e0.elapsed_time(e1) / reps, local_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_step = ms[0].item() / args.steps
-    shuffle_ms = ms[1].item() / args.steps
-    launches = ctx.launch_count() - launches0
-    phases = ctx.last_phase_times()
+    ms_step, shuffle_ms, local_ms = ms[0].item(), ms[1].item(), ms[2].item()
     rows = (nb + npb) * world
 
-    # e2e: host (pinned) key columns -> H2D -> sharded join -> D2H of this rank's pairs
+    # e2e: host (pinned) key columns -> H2D -> sharded join -> D2H of this rank's pairs; wall clock, max over ranks
     hb = torch.empty(nb, dtype=torch.int64).pin_memory(); hp = torch.empty(npb, dtype=torch.int64).pin_memory()
     hb.copy_(build); hp.copy_(probe)
-    hout = torch.empty(2 * (int(npb * 1.25) + 4096), dtype=torch.int32).pin_memory()
+    hout = torch.empty(2 * mm, dtype=torch.int32).pin_memory()
     db2, dp2 = torch.empty_like(build), torch.empty_like(probe)
 
     def e2e_step():
         db2.copy_(hb, non_blocking=True); dp2.copy_(hp, non_blocking=True)
-        r = sj.join(db2, nb, dp2, npb, max_matches=int(npb * 1.25) + 4096)
-        hout[:2 * r["count"]].copy_(r["pairs"][:2 * r["count"]], non_blocking=True)
+        r = rj.join(db2, nb, dp2, npb, pairs, mm)
+        hout[:2 * r["count"]].copy_(pairs[:2 * r["count"]], non_blocking=True)
         torch.cuda.synchronize()
         return r["count"]
 
-    e2e_step()
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
     n_e2e = max(1, min(args.steps, 2))
     out_rows = 0
-    for _ in range(n_e2e):
-        out_rows = e2e_step()
-    dist.barrier()
+    t0 = time.perf_counter()
+    if not args.skip_e2e:
+        e2e_step()
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out_rows = e2e_step()
+        dist.barrier()
     e2e = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], dtype=torch.float64, device=dev)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
-        bp_ms = phases.get("build_probe_direct") or phases.get("build_probe")      # rank 0's local join_pipeline_kernel (last step)
-        bp_bytes = 12.0 * (res["n_build_local"] + res["n_probe_local"]) + 8.0 * res["count"]
-        achieved = bp_bytes / (bp_ms * 1e-3) / 1e9 if bp_ms else None
+        lay = (C.c_uint64 * 8)()
+        _lib.check(rj.lib.olap_shard_layout(rj.handle, lay))
+        nvl = bytes_out / (shuffle_ms * 1e-3) / 1e9 if shuffle_ms else None
+        cpu = cpu_baseline() if cpu_baseline and not args.skip_cpu else None
         line = {
             "metric": "join rows/sec (|build|+|probe|)/time", "value": rows / (ms_step * 1e-3), "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": f"{world}-GPU key-sharded radix hash join, per GPU 2^{args.log2_build} unique-key build x 2^{args.log2_probe} FK probe "
-                                   f"(global 2^{args.log2_build}*{world} x 2^{args.log2_probe}*{world}), int64 keys, uniform, rows contiguous-sharded",
-                       "exchange": "NCCL all_to_all of (key i64, source row id u32), both sides; rows that stay local are joined in place while the others travel", "l2": "inputs larger than L2",
-                       "parallelism": f"key-radix shards x{world}"},
+            "config": {"exchange_mode": "ce" if rj.ce_mode else "tma",
+                       "workload": f"{world}-GPU key-range-sharded radix hash join, per GPU 2^{args.log2_build} unique-key build x 2^{args.log2_probe} FK probe "
+                                   f"(global 2^{args.log2_build}*{world} x 2^{args.log2_probe}*{world}), int64 keys, " + (f"Zipf s = {zipf}" if zipf > 0 else "uniform (Zipf s = 0)") + ", rows contiguous-sharded",
+                       "exchange": (f"dense key domain: one contiguous key slice per rank ({int(lay[4])} sub-ranges of {int(lay[5])} x 2^15 keys); rows travel as packed 8-byte words "
+                                    f"{{key - slice start, source row id}} into fixed-capacity single-writer regions of the owner's receive slab (torch symmetric memory, peer-mapped), no count pass; "
+                                    + ("copy-engine mode: the partition kernel fills a local outbox laid out like the receivers' regions (own rows go straight into the own slab), one peer "
+                                       "cudaMemcpyAsync per destination moves each block -- NVLink runs next to the SMs' partition + join work; "
+                                       if rj.ce_mode else
+                                       "TMA mode: ONE kernel partitions and ships -- every run leaves the shared-memory stage with cp.async.bulk into the peer's slab, one CTA per SM next to the join kernels; ")
+                                    + f"probe side in {chunks} chunks, chunk k+1 on the wire while chunk k is partitioned and joined in shared memory; barriers are a one-warp kernel signalling "
+                                    "through the slabs; NCCL carries only the min/max/flag reductions"),
+                       "l2": "inputs larger than L2", "parallelism": f"key-range shards x{world}",
+                       "verified": "all pairs of every rank after warm-up and after the timed steps (equal keys, each received probe row once, global count)"},
             "clocks": clocks,
             "e2e": {"value": rows / (e2e.item() * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": (nb + npb) * 8 * world,
-                    "d2h_bytes_per_step": int(out_rows) * 8 * world, "ms_per_step": e2e.item(), "steps": n_e2e},
+                    "d2h_bytes_per_step": int(out_rows) * 8 * world, "ms_per_step": e2e.item(), "steps": n_e2e,
+                    "how": "pinned host key columns -> H2D -> range-sharded join -> D2H of every rank's pairs; wall clock, max over ranks"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "join_pipeline_kernel of rank 0's local join (one persistent launch per step)", "achieved": achieved,
-                         "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "algorithmic_bytes_per_launch": bp_bytes, "ms_per_launch": bp_ms},
-            "nvlink": {"shuffle_ms_per_step": shuffle_ms, "bytes_out_per_rank_per_step": sent,
-                       "achieved_gbs_per_direction": sent / (shuffle_ms * 1e-3) / 1e9 if shuffle_ms else None, "peak_nominal_gbs": 900.0,
-                       "peak_measured_gbs": 770.0, "note": "shuffle_ms: both sides partitioned by destination and exchanged, measured alone outside the timed region; inside the step the probe-side exchange overlaps the join of the rows that stay local"},
-            "phases_ms": phases,
+            "roofline": {"bound": "nvlink", "kernel": "rpart_kernel<raw, peer> (shuffle: both sides of one join scattered into the peers' slabs, measured alone)",
+                         "achieved": nvl, "peak": 770.0, "peak_kind": "measured peer copy per direction (B200_PROFILING.md); nominal 900", "unit": "GB/s",
+                         "frac": nvl / 770.0 if nvl else None, "traffic": None,
+                         "algorithmic_bytes_per_launch": bytes_out, "ms_per_launch": shuffle_ms, "repetitions": reps},
+            "nvlink": {"shuffle_ms_per_join": shuffle_ms, "bytes_out_per_rank_per_join": bytes_out, "achieved_gbs_per_direction": nvl,
+                       "peak_nominal_gbs": 900.0, "peak_measured_gbs": 770.0,
+                       "floor_ms_per_join_at_measured_peak": bytes_out / 770e9 * 1e3,
+                       "note": "8 bytes leave the rank per row whose key another rank owns; inside the step the shuffle of chunk k+1 overlaps the local join of chunk k"},
+            "overlap": {"shuffle_alone_ms": shuffle_ms, "local_alone_ms": local_ms, "step_ms": ms_step,
+                        "hidden_ms": shuffle_ms + local_ms - ms_step,
+                        "note": "shuffle = both sides scattered; local = second partition level + shared-memory join of all chunks; hidden = how much of their sum the step does not pay"},
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     dist.barrier()
+    rj.close()
     dist.destroy_process_group()
     return 0

@@ -192,6 +192,78 @@ OLAP_API olap_status olap_shuffle_scatter_i64(olap_ctx* ctx, const int64_t* keys
                                               const uint64_t* dest_row_offset, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Key-range-sharded join across the GPUs of one box (SURVEY 8(b) "multi-GPU" group; no reference analogue: README.md:414).
+ * For a DENSE build-key domain (global max - min + 1 <= 5 x global build rows) the domain is cut into one contiguous slice per
+ * rank; every rank's partition kernel stores its rows -- as packed 8-byte words {key - slice start, source row id} -- straight
+ * into the owning rank's receive slab over NVLink (peer-mapped pointers), so the owner runs only the second partition level and
+ * the shared-memory build + probe of the 1-GPU direct join.  Fixed-capacity, single-writer slab regions: no count pass, no count
+ * collective.  The probe side moves in `probe_chunks` chunks so that chunk k + 1 is on the wire while chunk k is joined.
+ *
+ * One olap_shard per rank.  Two ways to drive a group:
+ *   (a) one process, all ranks: olap_shard_ctx_create_all + olap_sharded_hash_join_i64 (stream events order the ranks; the
+ *       devices may repeat, which is how the exchange is tested on a 1-GPU box);
+ *   (b) one process per GPU: olap_shard_create on every rank, each rank provides a slab of olap_shard_slab_bytes() bytes that
+ *       its peers can address (CUDA IPC / torch symmetric memory), olap_shard_attach(all ranks' pointers), then per join:
+ *         olap_shard_key_range -> reduce min / max / rows over the ranks -> olap_shard_plan (same values on every rank)
+ *         olap_shard_scatter(side 0) -> olap_shard_send -> BARRIER -> olap_shard_build
+ *         for every chunk k: olap_shard_scatter(side 1, k) -> olap_shard_send -> BARRIER -> olap_shard_probe(k)   (separate streams: they overlap)
+ *         olap_shard_finish -> OR the flags over the ranks; any flag set = discard, take the hash-sharded path
+ *       BARRIER = "every rank's scatter of that (side, chunk) has completed": olap_shard_barrier on the scatter stream (a
+ *       one-warp kernel signalling through the slabs), or any collective of the host language.  Before the first scatter of a join every rank must have finished
+ *       reading the slabs of the previous join (same barrier).
+ * Pairs index the rank's receive slabs; olap_shard_pairs_to_global turns them into global row ids
+ * (row offset of the source rank + source row id) for both sides.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct olap_shard olap_shard;
+OLAP_API olap_status olap_shard_create(olap_ctx* ctx, int32_t rank, int32_t world, uint64_t build_rows_cap, uint64_t probe_rows_cap,
+                                       int32_t probe_chunks, olap_shard** out);
+OLAP_API olap_status olap_shard_destroy(olap_shard* shard);
+OLAP_API uint64_t olap_shard_slab_bytes(const olap_shard* shard);
+OLAP_API olap_status olap_shard_attach(olap_shard* shard, void* const* peer_slabs /* [world], [rank] = own */);
+/* BARRIER for groups with one process per GPU: a one-warp kernel on `stream` that signals every peer through its slab and waits for
+ * every peer's signal.  Every rank calls it the same number of times in the same order.  Not for ranks that share a GPU.       */
+OLAP_API olap_status olap_shard_barrier(olap_shard* shard, void* stream);
+OLAP_API olap_status olap_shard_key_range(olap_shard* shard, const int64_t* keys, uint64_t n_rows, int64_t* out_min, int64_t* out_max, void* stream);
+OLAP_API olap_status olap_shard_plan(olap_shard* shard, int64_t global_min, int64_t global_max, uint64_t global_build_rows, int32_t hot, void* stream);
+OLAP_API olap_status olap_shard_scatter(olap_shard* shard, int32_t side, int32_t chunk, const int64_t* keys, uint64_t n_rows, uint32_t row_base,
+                                        void* stream);
+/* second half of a scatter, on a stream ordered behind it: the peer copies of the copy-engine mode (OLAP_SHARD_MODE=ce, default:
+ * one cudaMemcpyAsync per destination rank, no SM involved) and the publication of this rank's row counts; then the BARRIER     */
+OLAP_API olap_status olap_shard_send(olap_shard* shard, int32_t side, int32_t chunk, void* stream);
+OLAP_API olap_status olap_shard_build(olap_shard* shard, void* stream);
+OLAP_API olap_status olap_shard_probe(olap_shard* shard, int32_t chunk, olap_pair* out_pairs, uint64_t max_matches, void* stream);
+OLAP_API olap_status olap_shard_finish(olap_shard* shard, uint64_t* host_count, uint64_t* host_hot_count /* nullable */, uint32_t* host_flags /* [4] */,
+                                       void* stream);
+/* Heavy hitters (Zipf-skewed probe keys), olap_shard_plan(hot = 1).  Order within a join:
+ *   olap_shard_hot_candidates on every rank (samples its probe shard; keys as key - global_min + 1 in u32, with sample counts)
+ *   -> the host language gathers the lists, sums the counts per key, keeps the <= 1024 most frequent -> olap_shard_hot_set
+ *   build side as before (scatter, BARRIER, olap_shard_build)
+ *   olap_shard_hot_resolve (2048 x u64 on the device) -> element-wise MAX over the ranks -> olap_shard_hot_finalize
+ *   probe scatters: a row carrying a hot key never leaves its rank; its pair {hot slot, local probe row} goes to hot_pairs and the
+ *   slot's build row is merged[slot] - 1 = (source rank << 32 | source row).                                                    */
+OLAP_API olap_status olap_shard_hot_candidates(olap_shard* shard, const int64_t* probe_keys, uint64_t n_rows, uint32_t* host_keys_plus1,
+                                               uint32_t* host_counts, uint32_t capacity, uint32_t* host_n, void* stream);
+OLAP_API olap_status olap_shard_hot_set(olap_shard* shard, const uint32_t* keys_plus1, uint32_t n_keys, void* stream);
+OLAP_API olap_status olap_shard_hot_resolve(olap_shard* shard, uint64_t* out_dptr /* 2048 x u64 */, void* stream);
+OLAP_API olap_status olap_shard_hot_finalize(olap_shard* shard, const uint64_t* merged_dptr, olap_pair* hot_pairs, uint64_t max_hot_pairs, void* stream);
+OLAP_API olap_status olap_shard_pairs_to_global(olap_shard* shard, const olap_pair* pairs, uint64_t n_pairs, const uint64_t* build_row_offsets_dptr,
+                                                const uint64_t* probe_row_offsets_dptr, uint64_t* out_left, uint64_t* out_right, void* stream);
+/* out8: words reserved for the build regions, words per probe chunk, build / probe region capacity, Q, F, byte offset of the
+ * count arrays, chunks -- for callers that inspect the slabs */
+OLAP_API olap_status olap_shard_layout(const olap_shard* shard, uint64_t* out8);
+/* rows this rank stored into every rank's slab during the current join (the NVLink volume); synchronises the stream */
+OLAP_API olap_status olap_shard_sent_rows(olap_shard* shard, uint64_t* host_rows_per_dest /* [world] */, void* stream);
+OLAP_API olap_status olap_shard_ctx_create_all(int32_t n_ranks, const int32_t* devices, uint64_t max_gpu_memory, uint64_t build_rows_cap,
+                                               uint64_t probe_rows_cap, int32_t probe_chunks, olap_ctx** out_ctxs, olap_shard** out_shards);
+/* hot_pairs / max_hot_pairs / host_hot_counts: all NULL = no heavy-hitter handling; else per-rank buffers for the {hot slot, local
+ * probe row} pairs of probe rows that carry a heavy-hitter key (olap_shard_hot_table gives the slots' build rows).             */
+OLAP_API olap_status olap_sharded_hash_join_i64(olap_shard* const* shards, int32_t n_ranks, const int64_t* const* build_keys, const uint64_t* n_build,
+                                                const int64_t* const* probe_keys, const uint64_t* n_probe, olap_pair* const* out_pairs,
+                                                const uint64_t* max_matches, uint64_t* host_counts, olap_pair* const* hot_pairs,
+                                                const uint64_t* max_hot_pairs, uint64_t* host_hot_counts);
+OLAP_API olap_status olap_shard_hot_table(olap_shard* shard, uint64_t* host_merged /* [2048] */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Aggregation.  Replaces AggregateParams/AggregateSpec/AggregateKernel::aggregate
  * (gpu-kernel-compiler/src/aggregate_kernel.rs:37-125) and hash_aggregate_kernel (join_kernels.cuh:216-240).
  * keys == NULL: one global group (what execute_aggregate does today, executor.rs:307).  Output: out_keys[g],
@@ -306,6 +378,12 @@ OLAP_API void olap_result_free(olap_result* r);
  * 2 dyadic f64 = (u % domain) / 1024; 3 uniform f64 in [0, 1).                                              */
 OLAP_API olap_status olap_generate(olap_ctx* ctx, void* out_dptr, uint64_t n_rows, int32_t kind, uint64_t seed,
                                    uint64_t row0, uint64_t domain, void* stream);
+
+/* Probe-side foreign keys for a build side generated with kind 1 (perm_seed, domain): row r carries the key of build row b(r),
+ * b uniform over [0, domain) for zipf_s = 0, else b + 1 ~ Zipf(zipf_s) (continuous inverse-CDF sampler) -- BASELINE config 5's
+ * skew: the hot build rows are rows 0, 1, 2, ... and the permutation spreads their keys over the domain.                  */
+OLAP_API olap_status olap_generate_fk(olap_ctx* ctx, void* out_dptr, uint64_t n_rows, uint64_t perm_seed, uint64_t domain, uint64_t fk_seed,
+                                      uint64_t row0, double zipf_s, void* stream);
 
 /* per-phase device timings of the last join / group-by on this ctx (ms, CUDA events on the call's stream);
  * names is a ';'-separated list valid until the next call.  Enabled by olap_set_profiling(ctx, 1).          */

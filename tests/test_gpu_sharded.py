@@ -39,4 +39,4 @@ def test_sharded_world2_nccl():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", script], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "sharded join ok" in r.stdout and "sharded group-by ok" in r.stdout
+    assert "sharded join ok" in r.stdout and "sharded group-by ok" in r.stdout and "range-sharded join ok" in r.stdout and "range-sharded zipf join ok" in r.stdout
