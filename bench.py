@@ -146,7 +146,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    ctx = g.Context(local_rank, 0, 8)
+    ctx = g.Context(local_rank, 0, 8 if world == 1 else 12)   # N > 1: streams 3.. carry the peer copies, one per destination
     ctx.set_profiling(True)
     peak, peak_kind = peak_hbm()
 

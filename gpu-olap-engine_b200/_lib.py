@@ -79,6 +79,8 @@ SIGNATURES = {
     "olap_shard_slab_bytes": (u64, [vp]),
     "olap_shard_attach": (i32, [vp, pvp]),
     "olap_shard_barrier": (i32, [vp, vp]),
+    "olap_shard_signal": (i32, [vp, vp]),
+    "olap_shard_wait": (i32, [vp, vp]),
     "olap_shard_key_range": (i32, [vp, vp, u64, C.POINTER(i64), C.POINTER(i64), vp]),
     "olap_shard_plan": (i32, [vp, i64, i64, u64, i32, vp]),
     "olap_shard_scatter": (i32, [vp, i32, i32, vp, u64, u32, vp]),

@@ -28,7 +28,8 @@ constexpr int kRRows = 16;                        // rows per thread per tile
 constexpr int kRTile = kRThreads * kRRows;        // 4096 rows ranked / staged per CTA iteration
 constexpr int kRFineBits = 6;                     // second level: every coarse region is split into 64 ranges of 2^15 keys
 constexpr uint32_t kRMaxParts = 256u << kRFineBits;
-constexpr int kHotSlots = 2048;                   // open-addressing slots of the heavy-hitter table (<= 1024 keys)
+constexpr int kHotSlots = 8192;                   // open-addressing slots of the heavy-hitter table (<= 4096 keys, 32 KB of shared memory)
+constexpr uint32_t kHotSampleSlots = 1u << 19;    // counting table of the sampling pass
 
 // Why two levels (scratch/part_bench.cu on a B200, 2^29 rows, 16 B/row of traffic): ONE pass to 4096 partitions is bound by its
 // global atomics -- one per (tile, partition), i.e. one per 2 rows with 8 K-row tiles: 6.1 ms (3.7 ms with 16 K-row tiles; 1.4 ms
@@ -70,20 +71,67 @@ struct RPartArgs {
 __device__ __forceinline__ uint32_t peer_part(const RPartArgs& a, uint32_t d) { return (uint32_t)(((uint64_t)(d >> kRShift) * a.peer_mf) >> 32); }
 __device__ __forceinline__ uint32_t peer_dest(const RPartArgs& a, uint32_t part) { return (part * a.peer_mq) >> 24; }
 
-__device__ __forceinline__ uint32_t hot_slot_of(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - 11); }
-static_assert(kHotSlots == 2048, "hot_slot_of shifts for 2^11 slots");
+__device__ __forceinline__ uint32_t hot_slot_of(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - 13); }
+static_assert(kHotSlots == 8192, "hot_slot_of shifts for 2^13 slots");
 
 // CTAs per SM: 4 for raw keys (64 registers); the region passes keep the carried id next to offset and rank -- under a 64-register
 // cap ptxas serialises their 16 loads (2.18 ms instead of 1.35 ms for 2^29 rows) -- so they run 3 per SM with 80 registers
+// Heavy-hitter lookup of a thread's R rows at once (linear probing, table at most half full).  state[k]: 0 = dead row, 1 = live row
+// still to be looked up; on return a live row is 2 (not a heavy hitter) or 0x80000000 | slot (heavy hitter).  The first rounds probe
+// all rows together -- independent shared-memory loads in flight -- because a row-by-row probing loop left every load's latency
+// exposed (3.3 ms instead of 1.0 ms per 2^27-row chunk at Zipf 1.0); the rare long chains are finished one by one.
+template <int R>
+__device__ __forceinline__ uint32_t hot_lookup(const uint32_t* hotk, const uint32_t (&d)[R], uint32_t (&state)[R]) {
+  uint32_t slot[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) slot[k] = hot_slot_of(d[k]);
+  uint32_t nhot = 0;
+#pragma unroll
+  for (int round = 0; round < 3; round++) {
+    uint32_t hk[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) hk[k] = state[k] == 1u ? hotk[slot[k]] : 0u;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      if (state[k] != 1u) continue;
+      if (hk[k] == 0u) state[k] = 2u;
+      else if (hk[k] == d[k] + 1u) { state[k] = 0x80000000u | slot[k]; nhot++; }
+      else slot[k] = (slot[k] + 1) & (kHotSlots - 1);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    while (state[k] == 1u) {
+      const uint32_t h = hotk[slot[k]];
+      if (h == 0u) state[k] = 2u;
+      else if (h == d[k] + 1u) { state[k] = 0x80000000u | slot[k]; nhot++; }
+      else slot[k] = (slot[k] + 1) & (kHotSlots - 1);
+    }
+  }
+  return nhot;
+}
+
+// Stage position of a heavy-hitter row: the hot rows of a warp instruction reserve their slots with ONE shared-memory atomic
+// (a per-row atomic on the single counter serialised the whole CTA: 38 % of the rows are hot at Zipf 1.0).  All 32 lanes call it.
+__device__ __forceinline__ uint32_t hot_stage_slot(uint32_t* counter, bool is_hot) {
+  const uint32_t m = __ballot_sync(0xffffffffu, is_hot);
+  if (m == 0) return 0;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m) << 16) >> 16;
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(m & ((1u << lane) - 1));
+}
+
 template <int INPUT, bool HOT, bool PEER = false>
-__global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kernel(const __grid_constant__ RPartArgs a) {
+__global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) rpart_kernel(const __grid_constant__ RPartArgs a) {
   static_assert(!PEER || INPUT == kInRaw, "the shuffle reads raw keys");
   __shared__ uint64_t* s_optr[PEER ? kRThreads : 1];                   // PEER: where staged row i of partition j goes = s_optr[j] + i
   constexpr int R = kRRows, NW = kRThreads / 32;
   __shared__ __align__(16) uint64_t stage[kRTile];                    // rows in partition order (32 KB)
   __shared__ uint32_t cnt[kRThreads];                                 // tile histogram, then exclusive offsets
   __shared__ uint32_t gbase[kRThreads];                               // global position of staged row i = gbase[part] + i
-  __shared__ uint32_t hotk[HOT ? kHotSlots : 1];                      // hot keys (8 KB); their build rows are read through L1
+  extern __shared__ __align__(16) uint32_t hotk[];                    // HOT: the hot keys (32 KB, dynamic); their build rows are read through L1
   __shared__ uint32_t s_warp[NW];
   __shared__ uint32_t s_total, s_over[2], s_hot[2];  // indexed by tile parity: reset one tile ahead, between barriers
   __shared__ unsigned long long s_hotbase;
@@ -123,6 +171,8 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
       key[k] = row < n ? ld_stream_u64(src + row) : 0;
     }
     bool oob = false;
+    uint32_t nhot = 0;
+    // rk: kREmpty = dead row, 0x80000000 | slot = heavy hitter, else the rank inside the tile
 #pragma unroll
     for (int k = 0; k < R; k++) {
       const uint64_t row = row0 + (uint64_t)k * kRThreads + tid;
@@ -134,26 +184,36 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
         if (off >= a.rrange) { oob = oob || ok; ok = false; }
         d[k] = (uint32_t)off;
       }
-      rk[k] = kREmpty;
-      if (HOT && ok) {  // heavy hitter?  (linear probing; the table is at most half full)
-        uint32_t s = hot_slot_of(d[k]);
-        for (;;) {
-          const uint32_t hk = hotk[s];
-          if (hk == 0) break;
-          if (hk == d[k] + 1) { ok = false; rk[k] = 0x80000000u | s; atomicAdd(&s_hot[par], 1u); break; }
-          s = (s + 1) & (kHotSlots - 1);
-        }
+      if (HOT) rk[k] = ok ? 1u : 0u;
+      else rk[k] = ok ? atomicAdd(&cnt[(PEER ? peer_part(a, d[k]) : d[k] >> a.shift) - pbase], 1u) : kREmpty;   // one loop: fewest live registers
+    }
+    if (HOT) {
+      nhot = hot_lookup<R>(hotk, d, rk);
+#pragma unroll
+      for (int k = 0; k < R; k++) {
+        if (rk[k] == 1u || rk[k] == 2u) rk[k] = atomicAdd(&cnt[(PEER ? peer_part(a, d[k]) : d[k] >> a.shift) - pbase], 1u);   // live, not a heavy hitter
+        else if (rk[k] == 0u) rk[k] = kREmpty;
       }
-      if (ok) rk[k] = atomicAdd(&cnt[(PEER ? peer_part(a, d[k]) : d[k] >> a.shift) - pbase], 1u);
     }
     if (INPUT == kInRaw && oob && a.oob_is_error) a.flags[kFlagOutOfRange] = 1;
+    if (HOT) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nhot += __shfl_xor_sync(0xffffffffu, nhot, o);
+      if (lane == 0 && nhot) atomicAdd(&s_hot[par], nhot);
+    }
     __syncthreads();
 
     // phase 2: exclusive scan of the tile histogram (one partition per thread); every non-empty (tile, partition) run is
     // reserved in the partition's region with one global atomic, whose round trip overlaps the scan
     const uint32_t c = cnt[tid];
     const uint32_t got = c ? atomicAdd(&a.cursor[pbase + tid], c) : 0u;
-    if (tid == 0) { s_over[par ^ 1] = 0; s_hot[par ^ 1] = 0; }  // the previous tile is done with them, the next one starts after a barrier
+    if (tid == 0) {
+      s_over[par ^ 1] = 0; s_hot[par ^ 1] = 0;  // the previous tile is done with them, the next one starts after a barrier
+      if (HOT) {  // the tile's heavy-hitter pairs are reserved in the output now; the round trip is over by the time they are written
+        const uint32_t nh = s_hot[par] & 0xFFFFu;
+        if (nh) s_hotbase = atomicAdd(a.count, (unsigned long long)nh);
+      }
+    }
     uint32_t inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
@@ -179,11 +239,13 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
     const uint32_t total = s_total;
 #pragma unroll
     for (int k = 0; k < R; k++) {
+      const bool is_hot = HOT && rk[k] != kREmpty && (rk[k] & 0x80000000u);
+      uint32_t hslot = 0;
+      if (HOT) hslot = hot_stage_slot(&s_hot[par], is_hot);
       if (rk[k] == kREmpty) continue;
       const uint32_t id = INPUT == kInRegionsCarry ? (uint32_t)key[k] : idb + (uint32_t)(row0 + (uint64_t)k * kRThreads + tid);
-      if (HOT && (rk[k] & 0x80000000u)) {
-        const uint32_t pos = kRTile - 1 - (atomicAdd(&s_hot[par], 0x10000u) >> 16);
-        stage[pos] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (rk[k] & (kHotSlots - 1)));
+      if (is_hot) {
+        stage[kRTile - 1 - hslot] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (rk[k] & (kHotSlots - 1)));
       } else {
         stage[cnt[(PEER ? peer_part(a, d[k]) : d[k] >> a.shift) - pbase] + rk[k]] = ((uint64_t)d[k] << 32) | id;
       }
@@ -216,8 +278,6 @@ __global__ void __launch_bounds__(kRThreads, INPUT == kInRaw ? 4 : 3) rpart_kern
     if (HOT) {
       const uint32_t nh = s_hot[par] & 0xFFFFu;
       if (nh) {
-        if (tid == 0) s_hotbase = atomicAdd(a.count, (unsigned long long)nh);
-        __syncthreads();
         const unsigned long long base = s_hotbase;
         for (uint32_t i = tid; i < nh; i += kRThreads) {
           const uint64_t v = stage[kRTile - 1 - i];  // {probe row : hi, build row : lo}
@@ -419,7 +479,9 @@ static cudaError_t set_carveout(K kernel, bool shared) {
 template <int INPUT, bool HOT, bool PEER = false>
 static olap_status launch_rpart_t(olap_ctx* ctx, const RPartArgs& a, unsigned grid, bool shared, cudaStream_t s) {
   OLAP_CUDA(set_carveout(rpart_kernel<INPUT, HOT, PEER>, shared));
-  rpart_kernel<INPUT, HOT, PEER><<<grid, kRThreads, 0, s>>>(a);
+  const size_t dyn = HOT ? (size_t)kHotSlots * 4 : 0;
+  if (HOT) OLAP_CUDA((cudaFuncSetAttribute(rpart_kernel<INPUT, HOT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)));
+  rpart_kernel<INPUT, HOT, PEER><<<grid, kRThreads, dyn, s>>>(a);
   count_launch(ctx);
   return OLAP_OK;
 }
@@ -528,7 +590,7 @@ olap_status dj_build_prepare(olap_ctx* ctx, const RInput& in, int64_t rmin, uint
 olap_status dj_probe_begin(const DJBuild& b, uint64_t np_cap, int hot, cudaStream_t s, DJProbe* p) {
   olap_ctx* ctx = b.ctx;
   p->b = &b; p->hot = hot == 1; p->np_cap = np_cap;   // hot = 2: room for skew, but the heavy hitters were handled upstream (multi-GPU shuffle)
-  p->slack = hot == 2 ? 100 : hot ? 60 : 25;
+  p->slack = hot == 2 ? 200 : hot ? 60 : 25;
   p->pcap = region_cap(np_cap, b.P, p->slack);
   p->prows = nullptr; p->ctl = nullptr;
   if ((uint64_t)b.P * p->pcap >= 0xFFFFFFFFULL) { p->pcap = 0; return OLAP_OK; }  // positions are u32: every add raises the overflow flag
@@ -562,10 +624,10 @@ olap_status dj_probe_add(DJProbe& p, const RInput& in, olap_pair* out, uint64_t 
   if (p.hot && !in.regions) {
     HotArgs h;
     memset(&h, 0, sizeof(h));
-    h.n_samples = 1u << 16;
+    h.n_samples = 1u << 18;
     h.keys = in.keys; h.n = in.n; h.stride = std::max<uint64_t>(h.n / h.n_samples, 1);
     h.rmin = (uint64_t)b.rmin; h.rrange = b.rrange;
-    h.tab_slots = 1u << 18;
+    h.tab_slots = kHotSampleSlots;
     uint32_t* tab = nullptr;
     OLAP_TRY(sc.get<uint32_t>(2ULL * h.tab_slots, &tab));
     OLAP_CUDA(cudaMemsetAsync(tab, 0, 2ULL * h.tab_slots * 4, s));
@@ -682,22 +744,22 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
     uint32_t d[R], pr[R];   // pr = partition << 16 | rank; kREmpty: dead row; bit 31: heavy hitter (slot in the low bits)
     const bool full = row0 + kRTile <= a.n;   // uniform: interior tiles skip the per-row bounds checks
     bool oob = false;
+    uint32_t nhot = 0;
 #pragma unroll
     for (int k = 0; k < R; k++) {
       bool ok = full || row0 + (uint64_t)k * kRThreads + tid < a.n;
       const uint64_t off = key[k] - a.rmin;
       if (off >= a.rrange) { oob = oob || ok; ok = false; }
       d[k] = (uint32_t)off;
-      pr[k] = ok ? 0u : kREmpty;
-      if (HOT && ok) {
-        uint32_t s = hot_slot_of(d[k]);
-        for (;;) {
-          const uint32_t hk = hotk[s];
-          if (hk == 0) break;
-          if (hk == d[k] + 1) { pr[k] = 0x80000000u | s; atomicAdd(&s_hot[par], 1u); break; }
-          s = (s + 1) & (kHotSlots - 1);
-        }
-      }
+      pr[k] = ok ? 1u : 0u;
+    }
+    if (HOT) nhot = hot_lookup<R>(hotk, d, pr);
+#pragma unroll
+    for (int k = 0; k < R; k++) pr[k] = (pr[k] == 1u || pr[k] == 2u) ? 0u : (pr[k] == 0u ? kREmpty : pr[k]);   // 0 = live, to be ranked below
+    if (HOT) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nhot += __shfl_xor_sync(0xffffffffu, nhot, o);
+      if (lane == 0 && nhot) atomicAdd(&s_hot[par], nhot);
     }
     uint32_t rank[R];
 #pragma unroll
@@ -720,7 +782,13 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
     // phase 2: runs padded to an even length; one global atomic (local memory: this rank is the only writer of its regions)
     const uint32_t c = cnt[tid], cp = (c + 1) & ~1u;
     const uint32_t got = c ? atomicAdd(&a.cursor[tid], cp) : 0u;
-    if (tid == 0) s_hot[par ^ 1] = 0;
+    if (tid == 0) {
+      s_hot[par ^ 1] = 0;
+      if (HOT) {
+        const uint32_t nh = s_hot[par] & 0xFFFFu;
+        if (nh) s_hotbase = atomicAdd(a.count, (unsigned long long)nh);
+      }
+    }
     uint32_t inc = cp;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
@@ -738,11 +806,13 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
     // phase 3: scatter into the stage in partition order, already in the receiver's form {offset in its slice, source row id}
 #pragma unroll
     for (int k = 0; k < R; k++) {
+      const bool is_hot = HOT && pr[k] != kREmpty && (pr[k] & 0x80000000u);
+      uint32_t hslot = 0;
+      if (HOT) hslot = hot_stage_slot(&s_hot[par], is_hot);
       if (pr[k] == kREmpty) continue;
       const uint32_t id = a.id_base + (uint32_t)(row0 + (uint64_t)k * kRThreads + tid);
-      if (HOT && (pr[k] & 0x80000000u)) {
-        const uint32_t pos = kShufStage - 1 - (atomicAdd(&s_hot[par], 0x10000u) >> 16);
-        stage[pos] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (pr[k] & (kHotSlots - 1)));
+      if (is_hot) {
+        stage[kShufStage - 1 - hslot] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (pr[k] & (kHotSlots - 1)));
       } else {
         const uint32_t part = pr[k] >> 16;
         const uint32_t dl = d[k] - peer_dest(a, part) * (a.peer_q * a.peer_subw);
@@ -764,8 +834,6 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
     if (HOT) {
       const uint32_t nh = s_hot[par] & 0xFFFFu;
       if (nh) {
-        if (tid == 0) s_hotbase = atomicAdd(a.count, (unsigned long long)nh);
-        __syncthreads();
         const unsigned long long base = s_hotbase;
         for (uint32_t i = tid; i < nh; i += kRThreads) {
           const uint64_t v = stage[kShufStage - 1 - i];  // {probe row : hi, replicated build row : lo}
@@ -841,7 +909,8 @@ olap_status range_shuffle_publish(olap_ctx* ctx, const uint32_t* cursor, uint32_
 
 // ------------------------------------------------------------------------------------------- heavy hitters across ranks
 uint32_t hot_table_slots() { return kHotSlots; }
-uint32_t hot_slot_host(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - 11); }
+uint32_t hot_slot_host(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - 13); }
+uint32_t hot_sample_slots() { return kHotSampleSlots; }
 
 // (offset + 1, sample count) of every sampled key seen at least min_count times -> list (at most cap entries)
 __global__ void hot_extract_kernel(const uint32_t* __restrict__ tab_key, const uint32_t* __restrict__ tab_cnt, uint32_t slots, uint32_t min_count,
@@ -855,15 +924,15 @@ __global__ void hot_extract_kernel(const uint32_t* __restrict__ tab_key, const u
   }
 }
 
-// Sample one rank's probe shard (2^16 rows) and list the keys seen >= 3 times.  scratch: 2 x 2^18 + 2 x cap + 4 u32.
+// Sample one rank's probe shard (2^18 rows) and list the keys seen >= 3 times.  scratch: 2 x hot_sample_slots() + 2 x cap + 4 u32.
 olap_status hot_candidates(olap_ctx* ctx, const uint64_t* keys, uint64_t n, int64_t gmin, uint64_t grange, uint32_t* scratch, uint32_t cap,
                            uint32_t** out_key, uint32_t** out_cnt, uint32_t** out_n, cudaStream_t s) {
   HotArgs h;
   memset(&h, 0, sizeof(h));
-  h.n_samples = 1u << 17;   // per rank; the ranks' counts are summed before the cut
+  h.n_samples = 1u << 18;   // per rank; the ranks' counts are summed before the cut
   h.keys = keys; h.n = n; h.stride = std::max<uint64_t>(n / h.n_samples, 1);
   h.rmin = (uint64_t)gmin; h.rrange = grange;
-  h.tab_slots = 1u << 18;
+  h.tab_slots = kHotSampleSlots;
   h.tab_key = scratch; h.tab_cnt = scratch + h.tab_slots;
   *out_key = scratch + 2 * h.tab_slots; *out_cnt = *out_key + cap; *out_n = *out_cnt + cap;
   OLAP_CUDA(cudaMemsetAsync(scratch, 0, (2ULL * h.tab_slots + 2ULL * cap + 4) * 4, s));

@@ -734,6 +734,248 @@ __global__ void __launch_bounds__(kGbThreads) gb_part_smem_kernel(GbParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------- dense-key regime
+// Group keys that fill a range (max - min + 1 <= 16 x the group-count hint: surrogate keys, dates, the benchmark's uniform
+// [0, G)) need no hash table at all: the row's slot is key - min.  What they need above ~7 K groups is a table that fits shared
+// memory, so the rows are first split by key RANGE -- the join's partition pass (djoin.cu) with 12-byte rows {key - min : u32,
+// value : u64} kept as two arrays -- into ranges of 2^12 keys (one pass up to 2^20 keys, two levels up to 2^28), and one CTA then
+// aggregates a range in a 4096-slot direct-address table in shared memory and writes its groups straight to the output.
+// Measured before (profiles/r01_bench_ops.jsonl, 2^30 rows): 10^5 groups 15.4 ms (hash partition of 16-byte rows + hash tables),
+// 10^6 30 ms, 10^8 57 ms (per-partition L2 tables, L2-atomic bound).
+constexpr int kGrKeysLog2 = 12;
+constexpr uint32_t kGrKeys = 1u << kGrKeysLog2;
+constexpr int kGrThreads = 256, kGrRows = 16, kGrTile = kGrThreads * kGrRows;
+enum { kGrFlagOverflow = 0, kGrFlagOutOfRange = 1, kGrFlagWords = 4 };
+
+struct GrPartArgs {
+  const uint64_t* keys; const uint64_t* vals; uint64_t n;        // level 0: raw columns (vals may be NULL: COUNT only)
+  uint64_t rmin, rrange;
+  const uint32_t* in_d; const uint64_t* in_v;                     // level 1: the regions of level 0
+  const uint32_t* reg_cur; uint32_t reg_cap, n_reg, reg_parts;
+  int shift; uint32_t cap;
+  uint32_t* cursor; uint32_t* out_d; uint64_t* out_v; uint32_t* flags;
+};
+
+template <bool REGIONS>
+__global__ void __launch_bounds__(kGrThreads, 3) gr_part_kernel(const __grid_constant__ GrPartArgs a) {
+  constexpr int R = kGrRows, NW = kGrThreads / 32;
+  extern __shared__ __align__(16) unsigned char gr_smem[];
+  uint64_t* stage_v = reinterpret_cast<uint64_t*>(gr_smem);               // [kGrTile]
+  uint32_t* stage_d = reinterpret_cast<uint32_t*>(stage_v + kGrTile);     // [kGrTile]
+  __shared__ uint32_t cnt[kGrThreads], gbase[kGrThreads], s_warp[NW];
+  __shared__ uint32_t s_total, s_over[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  cnt[tid] = 0;
+  if (tid == 0) s_over[0] = s_over[1] = 0;
+  __syncthreads();
+  const uint32_t tiles_per_reg = REGIONS ? (a.reg_cap + kGrTile - 1) / kGrTile : 1u;
+  const uint32_t tiles = REGIONS ? tiles_per_reg * a.n_reg : (uint32_t)((a.n + kGrTile - 1) / kGrTile);
+  int par = 1;
+  for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    uint64_t n = a.n, row0 = (uint64_t)t * kGrTile, base = 0;
+    uint32_t pbase = 0;
+    if (REGIONS) {
+      const uint32_t g = t / tiles_per_reg;
+      n = min(a.reg_cur[g], a.reg_cap);
+      row0 = (uint64_t)(t - g * tiles_per_reg) * kGrTile;
+      base = (uint64_t)g * a.reg_cap;
+      pbase = g * a.reg_parts;
+      if (row0 >= n) continue;
+    }
+    par ^= 1;
+    uint32_t d[R], rk[R];
+    uint64_t v[R];
+    bool oob = false;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      const uint64_t row = row0 + (uint64_t)k * kGrThreads + tid;
+      const bool in = row < n;
+      if (REGIONS) {
+        d[k] = in ? a.in_d[base + row] : 0u;
+        v[k] = in ? ld_stream_u64(a.in_v + base + row) : 0;
+        rk[k] = in ? 0u : 0xFFFFFFFFu;
+      } else {
+        const uint64_t off = (in ? ld_stream_u64(a.keys + row) : 0) - a.rmin;
+        v[k] = (in && a.vals) ? ld_stream_u64(a.vals + row) : 0;
+        const bool ok = in && off < a.rrange;
+        oob = oob || (in && !ok);
+        d[k] = (uint32_t)off;
+        rk[k] = ok ? 0u : 0xFFFFFFFFu;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) if (rk[k] == 0u) rk[k] = atomicAdd(&cnt[(d[k] >> a.shift) - pbase], 1u);
+    if (!REGIONS && oob) a.flags[kGrFlagOutOfRange] = 1;  // the remembered key range is stale: the caller recomputes it
+    __syncthreads();
+    const uint32_t c = cnt[tid];
+    const uint32_t got = c ? atomicAdd(&a.cursor[pbase + tid], c) : 0u;
+    if (tid == 0) s_over[par ^ 1] = 0;
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    {
+      uint32_t wbase = 0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) wbase += w < warp ? s_warp[w] : 0u;
+      const uint32_t off = wbase + inc - c;
+      cnt[tid] = off;
+      gbase[tid] = (pbase + (uint32_t)tid) * a.cap + got - off;
+      if (got + c > a.cap) { s_over[par] = 1; a.flags[kGrFlagOverflow] = 1; }
+      if (tid == kGrThreads - 1) s_total = off + c;
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+      if (rk[k] == 0xFFFFFFFFu) continue;
+      const uint32_t pos = cnt[(d[k] >> a.shift) - pbase] + rk[k];
+      stage_d[pos] = d[k];
+      stage_v[pos] = v[k];
+    }
+    __syncthreads();
+    cnt[tid] = 0;
+    const bool over = s_over[par] != 0;
+    for (uint32_t i = tid; i < total; i += kGrThreads) {
+      const uint32_t dd = stage_d[i], part = (dd >> a.shift) - pbase, dst = gbase[part] + i;
+      if (over && dst - (pbase + part) * a.cap >= a.cap) continue;  // the region is full: dropped, flagged, the caller takes another regime
+      a.out_d[dst] = dd;
+      a.out_v[dst] = stage_v[i];
+    }
+    __syncthreads();
+  }
+}
+
+struct GrAggArgs {
+  const uint32_t* d; const uint64_t* v; const uint32_t* cur; uint32_t cap, P;
+  uint32_t S;                                  // CTAs that share one range (few ranges: 10^4 groups are 3 ranges for 296 CTAs); S > 1: merge
+  unsigned long long* m_cnt; uint64_t* m_cells;  // S > 1: global direct table [P * 4096] (+ cells [n_cells][P * 4096]) the CTAs' tables are merged into
+  uint32_t* ticket;
+  int n_cells; int8_t cell_op[kMaxCells];
+  OutSpec out; int64_t* out_keys; uint64_t* out_aggs; uint64_t out_cap; unsigned long long* out_n;
+  int64_t rmin;
+};
+
+constexpr int kGrAggThreads = 512;
+
+__global__ void __launch_bounds__(kGrAggThreads, 2) gr_agg_kernel(const __grid_constant__ GrAggArgs a) {
+  extern __shared__ __align__(16) unsigned char gr_smem[];
+  uint64_t* cells = reinterpret_cast<uint64_t*>(gr_smem);                          // [n_cells][kGrKeys]
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(cells + (size_t)a.n_cells * kGrKeys);  // [kGrKeys]
+  __shared__ uint32_t s_part;
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_part = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const uint32_t item = s_part;
+    if (item >= a.P * a.S) break;
+    const uint32_t p = item / a.S, slice = item - p * a.S;
+    const uint32_t np = min(a.cur[p], a.cap);
+    const uint32_t per = ((np + a.S - 1) / a.S + 3) & ~3u, r0 = min(np, slice * per), n = min(np, r0 + per) - r0;
+    if (n == 0) continue;
+    for (uint32_t i = tid; i < kGrKeys; i += kGrAggThreads) cnt[i] = 0;
+#pragma unroll 1
+    for (int c = 0; c < a.n_cells; c++) {
+      const uint64_t id = cell_identity(a.cell_op[c]);
+      for (uint32_t i = tid; i < kGrKeys; i += kGrAggThreads) cells[(size_t)c * kGrKeys + i] = id;
+    }
+    __syncthreads();
+    const uint32_t* dd = a.d + (uint64_t)p * a.cap + r0;
+    const uint64_t* vv = a.v + (uint64_t)p * a.cap + r0;
+    for (uint32_t i0 = 0; i0 < n; i0 += kGrAggThreads * 8) {
+      uint32_t k[8]; uint64_t x[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t i = i0 + j * kGrAggThreads + tid;
+        k[j] = i < n ? dd[i] & (kGrKeys - 1) : 0xFFFFFFFFu;
+        x[j] = i < n ? ld_stream_u64(vv + i) : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) if (k[j] != 0xFFFFFFFFu) atomicAdd(&cnt[k[j]], 1u);
+#pragma unroll 1
+      for (int c = 0; c < a.n_cells; c++) {
+        const int op = a.cell_op[c];
+        uint64_t* cc = cells + (size_t)c * kGrKeys;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (k[j] == 0xFFFFFFFFu) continue;
+          bool valid;
+          const uint64_t e = cell_encode(op, x[j], valid);
+          if (valid) cell_atomic_shared(op, cc + k[j], e);
+        }
+      }
+    }
+    __syncthreads();
+    if (a.S > 1) {  // several CTAs per range: this one's partial groups go into the global direct table; gr_emit_kernel writes the output
+      const uint64_t slots = (uint64_t)a.P << kGrKeysLog2;
+      for (uint32_t i = tid; i < kGrKeys; i += kGrAggThreads) {
+        const uint32_t cn = cnt[i];
+        if (!cn) continue;
+        const uint64_t g = ((uint64_t)p << kGrKeysLog2) + i;
+        atomicAdd(a.m_cnt + g, (unsigned long long)cn);
+#pragma unroll 1
+        for (int c = 0; c < a.n_cells; c++) cell_atomic_global(a.cell_op[c], a.m_cells + (uint64_t)c * slots + g, cells[(size_t)c * kGrKeys + i]);
+      }
+      continue;
+    }
+    // every non-empty slot is a group: its key is the range's first key plus the slot
+    for (uint32_t i0 = 0; i0 < kGrKeys; i0 += kGrAggThreads) {
+      const uint32_t i = i0 + tid;
+      const uint32_t cn = cnt[i];
+      const uint32_t m = __ballot_sync(0xffffffffu, cn != 0);
+      if (m == 0) continue;
+      unsigned long long g0 = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) g0 = atomicAdd(a.out_n, (unsigned long long)__popc(m));
+      g0 = __shfl_sync(0xffffffffu, g0, leader);
+      if (cn) {
+        const unsigned long long g = g0 + __popc(m & ((1u << lane) - 1));
+        if (g < a.out_cap) {
+          uint64_t cv[kMaxCells];
+#pragma unroll
+          for (int c = 0; c < kMaxCells; c++) cv[c] = c < a.n_cells ? cells[(size_t)c * kGrKeys + i] : 0;
+          emit_group(a.out, a.out_keys, a.out_aggs, a.out_cap, g, a.rmin + (int64_t)(((uint64_t)p << kGrKeysLog2) + i), cn, cv);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gr_merge_init_kernel(GrAggArgs a) {
+  const uint64_t slots = (uint64_t)a.P << kGrKeysLog2;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < slots; i += (uint64_t)gridDim.x * blockDim.x) {
+    a.m_cnt[i] = 0;
+    for (int c = 0; c < a.n_cells; c++) a.m_cells[(uint64_t)c * slots + i] = cell_identity(a.cell_op[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256) gr_emit_kernel(GrAggArgs a) {
+  const uint64_t slots = (uint64_t)a.P << kGrKeysLog2;
+  const int lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x; i0 < slots; i0 += stride) {   // whole warps stay together for the ballot
+    const uint64_t i = i0 + threadIdx.x;
+    const unsigned long long cn = i < slots ? a.m_cnt[i] : 0ULL;
+    const uint32_t m = __ballot_sync(0xffffffffu, cn != 0);
+    if (m == 0) continue;
+    unsigned long long g0 = 0;
+    const int leader = __ffs(m) - 1;
+    if (lane == leader) g0 = atomicAdd(a.out_n, (unsigned long long)__popc(m));
+    g0 = __shfl_sync(0xffffffffu, g0, leader);
+    if (cn) {
+      const unsigned long long g = g0 + __popc(m & ((1u << lane) - 1));
+      if (g < a.out_cap) {
+        uint64_t cv[kMaxCells];
+#pragma unroll
+        for (int c = 0; c < kMaxCells; c++) cv[c] = c < a.n_cells ? a.m_cells[(uint64_t)c * slots + i] : 0;
+        emit_group(a.out, a.out_keys, a.out_aggs, a.out_cap, g, a.rmin + (int64_t)i, cn, cv);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- table init / extraction
 __global__ void __launch_bounds__(256) gb_init_kernel(GbParams p) {
   const uint64_t n = p.g_cap + 1, stride = (uint64_t)gridDim.x * blockDim.x;
@@ -902,6 +1144,84 @@ static olap_status run_partitioned(olap_ctx* ctx, GbParams& p, uint64_t n_groups
   return OLAP_OK;
 }
 
+olap_status key_min_max(olap_ctx* ctx, const uint64_t* keys, uint64_t n, cudaStream_t s, int64_t* mn, int64_t* mx);  // join.cu
+
+static uint32_t gr_region_cap(uint64_t n, uint64_t parts) {
+  const uint64_t mean = (n + parts - 1) / parts;
+  return (uint32_t)((mean + mean / 4 + 2048 + 3) & ~3ULL);
+}
+
+// *flags_out: 0 = the groups are in the output; bit kGrFlag* set = nothing usable was produced (region overflow: skewed keys;
+// out of range: the remembered min / max was stale) and the caller takes another regime / refreshes the range
+static olap_status run_dense_range(olap_ctx* ctx, const GbParams& p, int64_t rmin, uint64_t rrange, Scratch& sc, cudaStream_t s, uint32_t* flags_out) {
+  const uint64_t P = (rrange + kGrKeys - 1) >> kGrKeysLog2;
+  const bool two = P > (uint64_t)kGrThreads;
+  const uint64_t C = two ? (P + kGrThreads - 1) / kGrThreads : 0;   // coarse regions of 256 ranges each
+  const uint64_t PP = ((two ? C * kGrThreads : P) + 255) / 256 * 256 + 256;
+  const uint32_t cap = gr_region_cap(p.n, P), cap1 = two ? gr_region_cap(p.n, C) : 0;
+  if (P * cap >= 0xFFFFFFFFULL || (two && C * cap1 >= 0xFFFFFFFFULL)) { *flags_out = 1u << kGrFlagOverflow; return OLAP_OK; }
+  uint32_t *d1 = nullptr, *d2 = nullptr, *ctl = nullptr;
+  uint64_t *v1 = nullptr, *v2 = nullptr;
+  const uint64_t ctl_words = PP + (two ? ((C + 255) / 256 * 256 + 256) : 0) + kGrFlagWords + 4;
+  OLAP_TRY(sc.get<uint32_t>(P * cap, &d2));
+  OLAP_TRY(sc.get<uint64_t>(P * cap, &v2));
+  if (two) { OLAP_TRY(sc.get<uint32_t>(C * cap1, &d1)); OLAP_TRY(sc.get<uint64_t>(C * cap1, &v1)); }
+  OLAP_TRY(sc.get<uint32_t>(ctl_words, &ctl));
+  OLAP_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
+  uint32_t *cur2 = ctl, *cur1 = ctl + PP, *flags = ctl + ctl_words - kGrFlagWords - 4, *ticket = flags + kGrFlagWords;
+  const size_t smem = (size_t)kGrTile * 12;
+  OLAP_CUDA(cudaFuncSetAttribute(gr_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OLAP_CUDA(cudaFuncSetAttribute(gr_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GrPartArgs a;
+  memset(&a, 0, sizeof(a));
+  a.keys = p.keys; a.vals = p.n_vcols ? p.vcol[0] : nullptr; a.n = p.n; a.rmin = (uint64_t)rmin; a.rrange = rrange; a.flags = flags;
+  const uint64_t tiles0 = (p.n + kGrTile - 1) / kGrTile;
+  const unsigned grid0 = capped_grid(tiles0, (uint64_t)ctx->sm_count * 3);
+  if (!two) {
+    a.shift = kGrKeysLog2; a.cap = cap; a.cursor = cur2; a.out_d = d2; a.out_v = v2;
+    gr_part_kernel<false><<<grid0, kGrThreads, smem, s>>>(a);
+    count_launch(ctx, 2);
+  } else {
+    a.shift = kGrKeysLog2 + 8; a.cap = cap1; a.cursor = cur1; a.out_d = d1; a.out_v = v1;
+    gr_part_kernel<false><<<grid0, kGrThreads, smem, s>>>(a);
+    phase_mark(ctx, s, "partition_coarse");
+    GrPartArgs f;
+    memset(&f, 0, sizeof(f));
+    f.in_d = d1; f.in_v = v1; f.reg_cur = cur1; f.reg_cap = cap1; f.n_reg = (uint32_t)C; f.reg_parts = kGrThreads;
+    f.shift = kGrKeysLog2; f.cap = cap; f.cursor = cur2; f.out_d = d2; f.out_v = v2; f.flags = flags;
+    const uint64_t tiles1 = (uint64_t)((cap1 + kGrTile - 1) / kGrTile) * C;
+    gr_part_kernel<true><<<capped_grid(tiles1, (uint64_t)ctx->sm_count * 3), kGrThreads, smem, s>>>(f);
+    count_launch(ctx, 3);
+  }
+  phase_mark(ctx, s, "partition");
+  GrAggArgs g;
+  memset(&g, 0, sizeof(g));
+  g.d = d2; g.v = v2; g.cur = cur2; g.cap = cap; g.P = (uint32_t)P; g.ticket = ticket;
+  g.n_cells = p.n_cells;
+  for (int c = 0; c < kMaxCells; c++) g.cell_op[c] = p.cell_op[c];
+  g.out = p.out; g.out_keys = p.out_keys; g.out_aggs = p.out_aggs; g.out_cap = p.out_cap; g.out_n = p.out_n; g.rmin = rmin;
+  const size_t asmem = (size_t)kGrKeys * (4 + 8 * (size_t)p.n_cells);
+  OLAP_CUDA(cudaFuncSetAttribute(gr_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+  const uint64_t ctas = (uint64_t)ctx->sm_count * 2;
+  g.S = P >= ctas ? 1u : (uint32_t)((ctas + P - 1) / P);
+  if (g.S > 1) {
+    const uint64_t slots = P << kGrKeysLog2;
+    OLAP_TRY(sc.get<unsigned long long>(slots, &g.m_cnt));
+    OLAP_TRY(sc.get<uint64_t>(slots * std::max(p.n_cells, 1), &g.m_cells));
+    gr_merge_init_kernel<<<capped_grid((slots + 255) / 256, (uint64_t)ctx->sm_count * 8), 256, 0, s>>>(g);
+  }
+  gr_agg_kernel<<<capped_grid(P * g.S, ctas), kGrAggThreads, asmem, s>>>(g);
+  if (g.S > 1) gr_emit_kernel<<<capped_grid(((P << kGrKeysLog2) + 255) / 256, (uint64_t)ctx->sm_count * 8), 256, 0, s>>>(g);
+  count_launch(ctx, 3);
+  OLAP_CUDA(cudaGetLastError());
+  uint32_t hf[kGrFlagWords];
+  OLAP_CUDA(cudaMemcpyAsync(hf, flags, sizeof(hf), cudaMemcpyDeviceToHost, s));
+  OLAP_CUDA(cudaStreamSynchronize(s));
+  *flags_out = 0;
+  for (int i = 0; i < kGrFlagWords; i++) if (hf[i]) *flags_out |= 1u << i;
+  return OLAP_OK;
+}
+
 }  // namespace olap
 
 using namespace olap;
@@ -950,6 +1270,7 @@ static olap_status group_by_impl(olap_ctx* ctx, const int64_t* keys, const olap_
   const uint64_t tile = (uint64_t)kGbThreads * kGbRows;
   const uint64_t tiles = (n_rows + tile - 1) / tile;
   uint64_t n_groups = 0;
+  bool dense_failed = false;
   for (int attempt = 0;; attempt++) {
     Scratch tsc(ctx, s);
     // regime
@@ -958,14 +1279,24 @@ static olap_status group_by_impl(olap_ctx* ctx, const int64_t* keys, const olap_
     if (need < 16) need = 16;
     // up to 96 KB: two CTAs per SM; up to 200 KB: one CTA per SM, still ahead of the partitioned regime's extra pass
     const bool shared = keys && attempt == 0 && (need + 1) * sbytes + 16 <= 200 * 1024;
-    const bool partitioned = keys && attempt == 0 && !shared && n_rows >= (1u << 20) && p.n_vcols <= 4;  // the partitioner carries <= 4 payload columns
+    // dense keys (key range <= 16 x the hint, <= 2^28): direct-address tables over key ranges, no hashing (run_dense_range)
+    bool dense = false;
+    int64_t dmin = 0; uint64_t drange = 0;
+    if (keys && attempt == 0 && !dense_failed && !shared && !any_prog && p.terms.n == 0 && p.n_vcols <= 1 && n_rows >= (1u << 20) &&
+        getenv("OLAP_GB_DENSE") == nullptr) {
+      int64_t mn, mx;
+      OLAP_TRY(key_min_max(ctx, (const uint64_t*)keys, n_rows, s, &mn, &mx));
+      const uint64_t span = (uint64_t)mx - (uint64_t)mn;
+      if (mx >= mn && span < (1ULL << 28) && span + 1 <= 16 * std::max<uint64_t>(n_groups_hint, 1)) { dense = true; dmin = mn; drange = span + 1; }
+    }
+    const bool partitioned = keys && attempt == 0 && !shared && !dense && n_rows >= (1u << 20) && p.n_vcols <= 4;  // the partitioner carries <= 4 payload columns
     if (any_prog && partitioned) {
       set_error("computed aggregate inputs are fused in the no-key / shared / global regimes only; materialise them for %llu groups",
                 (unsigned long long)n_groups_hint);
       return OLAP_ERR_UNSUPPORTED;
     }
     // global table: the spill target of the shared/partitioned regimes (small), or the whole table
-    uint64_t gh = (shared || partitioned) ? std::min<uint64_t>(n_groups_hint, 4096) : n_groups_hint;
+    uint64_t gh = (shared || partitioned || dense) ? std::min<uint64_t>(n_groups_hint, 4096) : n_groups_hint;
     p.g_cap = keys ? pow2_at_least(std::max<uint64_t>(2 * gh, 1024)) : 1;
     const uint64_t n1 = p.g_cap + 1;
     OLAP_TRY(tsc.get<uint64_t>(n1, &p.g_keys));
@@ -999,6 +1330,15 @@ static olap_status group_by_impl(olap_ctx* ctx, const int64_t* keys, const olap_
           });
         }
         count_launch(ctx);
+      } else if (dense) {
+        uint32_t df = 0;
+        OLAP_TRY(run_dense_range(ctx, p, dmin, drange, tsc, s, &df));
+        if (df) {  // skewed keys overflowed a range's region, or the remembered key range was stale: redo without this regime
+          if (df & (1u << kGrFlagOutOfRange)) ctx->shard_key_stats.erase(keys);
+          else dense_failed = true;
+          attempt = -1;
+          continue;
+        }
       } else if (partitioned) {
         OLAP_TRY(run_partitioned(ctx, p, n_groups_hint, tsc, s));
       } else {

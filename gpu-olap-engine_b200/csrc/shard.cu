@@ -19,7 +19,7 @@
 // "comp").  The only cross-rank synchronisation is "every rank's shuffle of chunk k has finished": stream events inside one
 // process (olap_sharded_hash_join_i64), or a collective of the host language between the per-phase calls (sharded.py: NCCL).
 //
-// Skew (Zipf): heavy-hitter keys are agreed on by all ranks (olap_shard_hot_*), their build rows are replicated (a <= 1024-entry
+// Skew (Zipf): heavy-hitter keys are agreed on by all ranks (olap_shard_hot_*), their build rows are replicated (a <= 4096-entry
 // table), and probe rows carrying them never leave their source rank: the shuffle kernel joins them on the spot.
 #include "common.cuh"
 #include "djoin.cuh"
@@ -35,7 +35,7 @@ using namespace olap;
 constexpr int kShardMaxWorld = 8;
 constexpr uint32_t kShardRegions = 256;       // regions per slab side (>= world * Q)
 constexpr uint32_t kShardSlackPct = 30;       // words reserved per side above the rows it can receive
-constexpr uint32_t kHotCand = 4096;           // heavy-hitter candidates a rank reports
+constexpr uint32_t kHotCand = 16384;          // heavy-hitter candidates a rank reports
 
 struct olap_shard {
   olap_ctx* ctx = nullptr;
@@ -44,10 +44,11 @@ struct olap_shard {
   int chunks = 1;
   // slab layout (identical on every rank): [build regions][probe chunk 0 regions] ... [counts: u32 x 256 x (1 + chunks)]
   uint64_t words_b = 0, words_p = 0, off_counts = 0, off_sync = 0, slab_bytes = 0;
-  uint32_t epoch = 0;           // barriers passed so far (olap_shard_barrier)
+  uint32_t epoch = 0, epoch_waited = 0;   // signals sent / waits issued so far (olap_shard_signal / _wait)
   void* slabs[kShardMaxWorld] = {};
   void* own_slab_alloc = nullptr;
   bool ce_mode = true;          // copy-engine exchange through a local outbox (else: TMA stores from the shuffle kernel)
+  cudaEvent_t ce_fork = nullptr, ce_join[8] = {};
   uint64_t* outbox = nullptr;   // ce: [build regions][probe chunk regions ...], laid out like a slab
   // geometry of the current join
   bool planned = false;
@@ -111,18 +112,27 @@ __global__ void shard_pairs_to_global_kernel(const olap_pair* __restrict__ pairs
   }
 }
 
-// Cross-GPU barrier on a stream: one warp tells every peer "my work queued before this kernel is done" (a release store of the
-// epoch into the peer's slab) and waits until every peer has said the same (acquire loads of its own words).  32 threads and a
-// handful of registers, so it is resident next to anything -- an NCCL all-reduce used as the barrier could not start while the
-// join kernel held the SM's registers and stalled the shuffle stream for the length of a join (2 ms per group).
-// One process per GPU only: ranks that share a GPU must not spin on each other (the one-process driver uses stream events).
-__global__ void shard_barrier_kernel(uint32_t epoch, uint32_t rank, uint32_t world, uint32_t* p0, uint32_t* p1, uint32_t* p2, uint32_t* p3, uint32_t* p4,
-                                     uint32_t* p5, uint32_t* p6, uint32_t* p7, uint32_t* mine, uint32_t* local_flags) {
+// Cross-GPU synchronisation through the slabs, in two halves that may sit on different streams:
+//   signal  one warp tells every peer "my work queued on this stream before this kernel is done" (a release store of the epoch
+//           into the peer's slab);
+//   wait    one warp spins until every peer has said so for the same epoch (acquire loads of its own words).
+// The scatter stream only ever signals -- it never waits for a peer, so copies of chunk k + 1 follow those of chunk k back to
+// back -- and the stream that consumes a chunk waits.  32 threads and a handful of registers: resident next to anything (an NCCL
+// all-reduce used as the barrier could not start while the join kernel held the SM's registers and stalled the shuffle stream
+// for the length of a join, 2 ms per group).  One process per GPU only: ranks that share a GPU must not spin on each other (the
+// one-process driver uses stream events).
+__global__ void shard_signal_kernel(uint32_t epoch, uint32_t rank, uint32_t world, uint32_t* p0, uint32_t* p1, uint32_t* p2, uint32_t* p3, uint32_t* p4,
+                                    uint32_t* p5, uint32_t* p6, uint32_t* p7) {
   uint32_t* peers[8] = {p0, p1, p2, p3, p4, p5, p6, p7};
   const uint32_t t = threadIdx.x;
   if (t < world) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers[t] + rank), "r"(epoch) : "memory");
+  }
+}
+__global__ void shard_wait_kernel(uint32_t epoch, uint32_t world, uint32_t* mine, uint32_t* local_flags) {
+  const uint32_t t = threadIdx.x;
+  if (t < world) {
     const long long t0 = clock64();
     for (;;) {
       uint32_t v;
@@ -137,9 +147,9 @@ __global__ void shard_barrier_kernel(uint32_t epoch, uint32_t rank, uint32_t wor
 
 extern "C" {
 
-// "every rank's work queued on `stream` before this call has completed" -- the BARRIER of the per-phase protocol, for groups
-// with one process per GPU.  Every rank calls it the same number of times, in the same order.
-olap_status olap_shard_barrier(olap_shard* sh, void* stream) {
+// "my work queued on `stream` before this call has completed", told to every rank.  Every rank issues the same sequence of
+// signals; olap_shard_wait number n returns once every rank's signal number n has arrived.
+olap_status olap_shard_signal(olap_shard* sh, void* stream) {
   OLAP_REQUIRE(sh && sh->slabs[0], "olap_shard_attach first");
   olap_ctx* ctx = sh->ctx;
   std::lock_guard<std::mutex> g(ctx->mu);
@@ -147,11 +157,28 @@ olap_status olap_shard_barrier(olap_shard* sh, void* stream) {
   uint32_t* p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int r = 0; r < sh->world; r++) p[r] = sh->sync_words(r);
   sh->epoch++;
-  shard_barrier_kernel<<<1, 32, 0, ctx->stream_of(stream)>>>(sh->epoch, (uint32_t)sh->rank, (uint32_t)sh->world, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7],
-                                                             sh->sync_words(sh->rank), sh->flags(0));
+  shard_signal_kernel<<<1, 32, 0, ctx->stream_of(stream)>>>(sh->epoch, (uint32_t)sh->rank, (uint32_t)sh->world, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]);
   count_launch(ctx);
   OLAP_CUDA(cudaGetLastError());
   return OLAP_OK;
+}
+
+olap_status olap_shard_wait(olap_shard* sh, void* stream) {
+  OLAP_REQUIRE(sh && sh->slabs[0], "olap_shard_attach first");
+  olap_ctx* ctx = sh->ctx;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  sh->epoch_waited++;
+  shard_wait_kernel<<<1, 32, 0, ctx->stream_of(stream)>>>(sh->epoch_waited, (uint32_t)sh->world, sh->sync_words(sh->rank), sh->flags(0));
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
+
+// the BARRIER of the per-phase protocol on one stream: signal, then wait
+olap_status olap_shard_barrier(olap_shard* sh, void* stream) {
+  OLAP_TRY(olap_shard_signal(sh, stream));
+  return olap_shard_wait(sh, stream);
 }
 
 olap_status olap_shard_create(olap_ctx* ctx, int32_t rank, int32_t world, uint64_t build_rows_cap, uint64_t probe_rows_cap, int32_t probe_chunks,
@@ -180,7 +207,7 @@ olap_status olap_shard_create(olap_ctx* ctx, int32_t rank, int32_t world, uint64
   }
   olap_status st = pool_alloc(ctx, sh->local_words * 4, ctx->streams[0], (void**)&sh->local);
   if (st == OLAP_OK && sh->ce_mode && world > 1) st = pool_alloc(ctx, (sh->words_b + sh->words_p * probe_chunks) * 8, ctx->streams[0], (void**)&sh->outbox);
-  if (st == OLAP_OK) st = pool_alloc(ctx, ((uint64_t)6 * hot_table_slots() + 2 * (1u << 18) + 2 * kHotCand + 16) * 4, ctx->streams[0], (void**)&sh->hot);
+  if (st == OLAP_OK) st = pool_alloc(ctx, ((uint64_t)6 * hot_table_slots() + 2 * (uint64_t)hot_sample_slots() + 2 * kHotCand + 16) * 4, ctx->streams[0], (void**)&sh->hot);
   if (st != OLAP_OK) { delete sh; return st; }
   *out = sh;
   return OLAP_OK;
@@ -197,7 +224,7 @@ olap_status olap_shard_attach(olap_shard* sh, void* const* peer_slabs) {
   OLAP_CUDA(cudaSetDevice(ctx->device));
   OLAP_CUDA(cudaMemsetAsync(sh->sync_words(sh->rank), 0, 64, ctx->streams[0]));
   OLAP_CUDA(cudaStreamSynchronize(ctx->streams[0]));
-  sh->epoch = 0;
+  sh->epoch = 0; sh->epoch_waited = 0;
   return OLAP_OK;
 }
 
@@ -211,6 +238,7 @@ olap_status olap_shard_destroy(olap_shard* sh) {
     if (sh->built) { dj_probe_end(sh->pg, ctx->streams[0]); dj_build_free(sh->dj, ctx->streams[0]); }
     if (sh->local) pool_free(ctx, sh->local, ctx->streams[0]);
     if (sh->outbox) pool_free(ctx, sh->outbox, ctx->streams[0]);
+    if (sh->ce_fork) { cudaEventDestroy(sh->ce_fork); for (auto e : sh->ce_join) if (e) cudaEventDestroy(e); }
     if (sh->hot) pool_free(ctx, sh->hot, ctx->streams[0]);
     if (sh->own_slab_alloc) cudaFree(sh->own_slab_alloc);
   }
@@ -320,13 +348,25 @@ olap_status olap_shard_send(olap_shard* sh, int32_t side, int32_t chunk, void* s
   OLAP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream_of(stream);
   const uint32_t cap = side ? sh->pcap : sh->bcap;
-  if (sh->ce_mode) {
+  if (sh->ce_mode && sh->world > 1) {
+    // one copy per peer, spread over the context's spare streams so that several copy engines work at once (a single stream's
+    // copies run one after the other: 447 GB/s per direction at 4 GPUs); s waits for all of them before the counts go out
     const uint64_t* ob = side ? sh->outbox_p(chunk) : sh->outbox_b();
     const uint64_t block = (uint64_t)sh->Q * cap;
+    const size_t ns = ctx->streams.size();
+    const int lanes = ns > 3 ? (int)std::min<size_t>(ns - 3, (size_t)sh->world - 1) : 0;
+    if (!sh->ce_fork) { OLAP_CUDA(cudaEventCreateWithFlags(&sh->ce_fork, cudaEventDisableTiming)); for (auto& e : sh->ce_join) OLAP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+    if (lanes) OLAP_CUDA(cudaEventRecord(sh->ce_fork, s));
+    for (int l = 0; l < lanes; l++) OLAP_CUDA(cudaStreamWaitEvent(ctx->streams[3 + l], sh->ce_fork, 0));
     for (int k = 1; k < sh->world; k++) {
       const int r = (sh->rank + k) % sh->world;   // every rank starts with a different peer
       uint64_t* dst = (side ? sh->regions_p(r, chunk) : sh->regions_b(r)) + (uint64_t)sh->rank * block;
-      OLAP_CUDA(cudaMemcpyAsync(dst, ob + (uint64_t)r * block, block * 8, cudaMemcpyDeviceToDevice, s));
+      cudaStream_t cs = lanes ? ctx->streams[3 + (k - 1) % lanes] : s;
+      OLAP_CUDA(cudaMemcpyAsync(dst, ob + (uint64_t)r * block, block * 8, cudaMemcpyDeviceToDevice, cs));
+    }
+    for (int l = 0; l < lanes; l++) {
+      OLAP_CUDA(cudaEventRecord(sh->ce_join[l], ctx->streams[3 + l]));
+      OLAP_CUDA(cudaStreamWaitEvent(s, sh->ce_join[l], 0));
     }
   }
   uint32_t* counts[kShardMaxWorld];
@@ -350,7 +390,7 @@ olap_status olap_shard_build(olap_shard* sh, void* stream) {
   sh->built = true;
   OLAP_CUDA(cudaMemcpyAsync(sh->flags(1), sh->dj.bctl + sh->dj.PP, kFlagWords * 4, cudaMemcpyDeviceToDevice, s));   // the build side's flags
   // rows this rank receives per chunk: its slice's share of the domain of every source's chunk; with heavy hitters pulled out the
-  // warm keys still load single key ranges unevenly, so the ranges get twice the room (hot = 2: 100 % slack)
+  // warm keys still load single key ranges unevenly, so the ranges get three times the room (hot = 2: 200 % slack)
   const double share = std::min(1.0, (double)sh->slice / (double)sh->grange);
   const uint64_t per_chunk = (uint64_t)((double)sh->chunk_cap * sh->world * share) + 1;
   return dj_probe_begin(sh->dj, per_chunk * (uint64_t)std::max(sh->group, sh->last_group), sh->hot_on ? 2 : 0, s, &sh->pg);
@@ -445,9 +485,9 @@ olap_status olap_shard_sent_rows(olap_shard* sh, uint64_t* host_rows_per_dest /*
 
 // ---- heavy hitters (Zipf-skewed probe keys).  With olap_shard_plan(hot = 1) the order of a join is:
 //   olap_shard_hot_candidates (every rank, its probe shard)  ->  the host language gathers the lists, sums the counts per key,
-//   keeps the <= 1024 most frequent  ->  olap_shard_hot_set (same keys on every rank)
+//   keeps the <= 4096 most frequent  ->  olap_shard_hot_set (same keys on every rank)
 //   scatter + BARRIER + olap_shard_build (build side, as before)
-//   olap_shard_hot_resolve -> element-wise MAX of the 2048 x u64 table over the ranks -> olap_shard_hot_finalize
+//   olap_shard_hot_resolve -> element-wise MAX of the 8192 x u64 table over the ranks -> olap_shard_hot_finalize
 //   probe scatters: rows carrying a hot key stay on their rank; pair {hot slot, local probe row} goes to hot_pairs, the slot's
 //   build row is (merged[slot] - 1) = source rank << 32 | source row.
 // keys are passed as (key - global_min + 1) in u32, the form the tables hold.
@@ -475,7 +515,7 @@ olap_status olap_shard_hot_candidates(olap_shard* sh, const int64_t* probe_keys,
 
 olap_status olap_shard_hot_set(olap_shard* sh, const uint32_t* keys_plus1, uint32_t n_keys, void* stream) {
   OLAP_REQUIRE(sh && sh->planned && (n_keys == 0 || keys_plus1), "olap_shard_plan first");
-  OLAP_REQUIRE(n_keys <= hot_table_slots() / 2, "at most 1024 hot keys");
+  OLAP_REQUIRE(n_keys <= hot_table_slots() / 2, "at most 4096 hot keys");
   // the table is built here, sequentially over the SORTED keys: every rank ends up with the same slot for the same key
   std::vector<uint32_t> keys(keys_plus1, keys_plus1 + n_keys), tab(hot_table_slots(), 0);
   std::sort(keys.begin(), keys.end());
@@ -495,7 +535,7 @@ olap_status olap_shard_hot_set(olap_shard* sh, const uint32_t* keys_plus1, uint3
   return OLAP_OK;
 }
 
-// after olap_shard_build.  out_dptr: 2048 x u64 on the device, to be MAX-reduced over the ranks by the caller
+// after olap_shard_build.  out_dptr: 8192 x u64 on the device, to be MAX-reduced over the ranks by the caller
 olap_status olap_shard_hot_resolve(olap_shard* sh, uint64_t* out_dptr, void* stream) {
   OLAP_REQUIRE(sh && sh->planned && sh->built && out_dptr, "olap_shard_build first");
   olap_ctx* ctx = sh->ctx;
@@ -518,7 +558,7 @@ olap_status olap_shard_hot_finalize(olap_shard* sh, const uint64_t* merged_dptr,
 }
 
 // the merged hot table of the current join: host_merged[slot] = 0, or (source rank << 32 | source row) + 1 of the slot's build row
-olap_status olap_shard_hot_table(olap_shard* sh, uint64_t* host_merged /* [2048] */, void* stream) {
+olap_status olap_shard_hot_table(olap_shard* sh, uint64_t* host_merged /* [8192] */, void* stream) {
   OLAP_REQUIRE(sh && host_merged, "NULL argument");
   olap_ctx* ctx = sh->ctx;
   std::lock_guard<std::mutex> g(ctx->mu);
@@ -548,7 +588,7 @@ olap_status olap_shard_ctx_create_all(int32_t n_ranks, const int32_t* devices, u
   for (int r = 0; r < n_ranks; r++) { out_ctxs[r] = nullptr; out_shards[r] = nullptr; }
   olap_status st = OLAP_OK;
   for (int r = 0; r < n_ranks && st == OLAP_OK; r++) {
-    st = olap_ctx_create(devices[r], max_gpu_memory, 4, &out_ctxs[r]);
+    st = olap_ctx_create(devices[r], max_gpu_memory, 8, &out_ctxs[r]);
     if (st == OLAP_OK) st = olap_shard_create(out_ctxs[r], r, n_ranks, build_rows_cap, probe_rows_cap, probe_chunks, &out_shards[r]);
   }
   void* slabs[kShardMaxWorld] = {};

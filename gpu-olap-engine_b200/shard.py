@@ -18,6 +18,7 @@ import numpy as np
 from . import _lib
 from .core import Context
 
+HOT_SLOTS = 8192      # open-addressing slots of the heavy-hitter table (csrc/djoin.cu kHotSlots): at most half of them hold a key
 FLAG_NAMES = ["region overflow (skewed keys)", "build key outside the planned range", "repeated build key", "-"]
 
 
@@ -71,7 +72,7 @@ class ShardGroup:
 
     def hot_pairs_to_global(self, r, hot_pairs, n_pairs, build_row_offsets, probe_row_offsets):
         """Global (left, right) row ids of rank r's heavy-hitter pairs (numpy uint64)."""
-        tab = (C.c_uint64 * 2048)()
+        tab = (C.c_uint64 * HOT_SLOTS)()
         _lib.check(self.lib.olap_shard_hot_table(self.shards[r], tab, None))
         tab = np.ctypeslib.as_array(tab).astype(np.uint64)
         pr = hot_pairs.to_numpy(2 * n_pairs).reshape(-1, 2).astype(np.uint64)
@@ -140,6 +141,15 @@ class RangeShardedJoin:
         else:
             _lib.check(self.lib.olap_shard_barrier(self.handle, self.comm.cuda_stream))
 
+    def _phase_done(self):
+        """After a scatter + send on comm: let the peers know, and make comp wait for all of them -- comm itself goes on."""
+        if self.nccl_barrier:
+            self._barrier()
+            ev = self.torch.cuda.Event(); ev.record(self.comm); self.comp.wait_event(ev)
+        else:
+            _lib.check(self.lib.olap_shard_signal(self.handle, self.comm.cuda_stream))
+            _lib.check(self.lib.olap_shard_wait(self.handle, self.comp.cuda_stream))
+
     def _scatter(self, side, chunk, ptr, n, row_base):
         """Partition kernel on `part`, then -- ordered behind it -- the peer copies (ce mode) and the count publication on `comm`."""
         torch, lib, h = self.torch, self.lib, self.handle
@@ -167,11 +177,11 @@ class RangeShardedJoin:
 
     def _hot_keys(self, probe, npb, stream):
         """The agreed heavy-hitter set of this probe column: every rank samples its shard, the lists are all-gathered, the counts
-        summed per key and the <= 1024 most frequent kept (same result on every rank).  Remembered per (pointer, rows)."""
+        summed per key and the <= 4096 most frequent kept (same result on every rank).  Remembered per (pointer, rows)."""
         key = ("hot", probe.data_ptr(), npb)
         if key not in self._stats:
             torch, dist = self.torch, self.dist
-            cap = 4096
+            cap = 16384
             hk = (C.c_uint32 * cap)(); hc = (C.c_uint32 * cap)(); hn = C.c_uint32()
             _lib.check(self.lib.olap_shard_hot_candidates(self.handle, probe.data_ptr() if npb else None, npb, hk, hc, cap, C.byref(hn), stream))
             mine = torch.zeros(2 * cap + 1, dtype=torch.int64, device=self.device)
@@ -188,7 +198,7 @@ class RangeShardedJoin:
                 m = int(allc[r, 0])
                 for k, c in zip(allc[r, 1:1 + m], allc[r, 1 + cap:1 + cap + m]):
                     freq[int(k)] = freq.get(int(k), 0) + int(c)
-            top = sorted(freq.items(), key=lambda kv: (-kv[1], kv[0]))[:1024]
+            top = sorted(freq.items(), key=lambda kv: (-kv[1], kv[0]))[:HOT_SLOTS // 2]
             self._stats[key] = np.array(sorted(k for k, _ in top), dtype=np.uint32)
         return self._stats[key]
 
@@ -223,13 +233,11 @@ class RangeShardedJoin:
         mark("comm: entry barrier done", comm)
         self._scatter(0, 0, build.data_ptr(), nb, 0)
         mark("comm: build sent", comm)
-        self._barrier()
-        mark("comm: build barrier done", comm)
-        ev = torch.cuda.Event(); ev.record(comm); comp.wait_event(ev)
+        self._phase_done()
         _lib.check(lib.olap_shard_build(h, comp.cuda_stream))
         mark("comp: build partitioned", comp)
         if hot:   # the hot keys' build rows: resolved by their owners, MAX-reduced, back to every rank before the probe side moves
-            glob = torch.empty(2048, dtype=torch.int64, device=self.device)
+            glob = torch.empty(HOT_SLOTS, dtype=torch.int64, device=self.device)
             _lib.check(lib.olap_shard_hot_resolve(h, glob.data_ptr(), comp.cuda_stream))
             ev = torch.cuda.Event(); ev.record(comp); part.wait_event(ev)
             with torch.cuda.stream(part):
@@ -242,9 +250,7 @@ class RangeShardedJoin:
             lo = min(k * cc, npb); hi = min(lo + cc, npb)
             self._scatter(1, k, probe.data_ptr() + 8 * lo, hi - lo, lo)
             mark(f"comm: chunk {k} sent", comm)
-            self._barrier()
-            mark(f"comm: chunk {k} barrier done", comm)
-            ev = torch.cuda.Event(); ev.record(comm); comp.wait_event(ev)
+            self._phase_done()
             _lib.check(lib.olap_shard_probe(h, k, pairs.data_ptr(), max_matches, comp.cuda_stream))
             mark(f"comp: chunk {k} done", comp)
         cnt = C.c_uint64(); hcnt = C.c_uint64(); fl = (C.c_uint32 * 4)()

@@ -223,6 +223,10 @@ OLAP_API olap_status olap_shard_attach(olap_shard* shard, void* const* peer_slab
 /* BARRIER for groups with one process per GPU: a one-warp kernel on `stream` that signals every peer through its slab and waits for
  * every peer's signal.  Every rank calls it the same number of times in the same order.  Not for ranks that share a GPU.       */
 OLAP_API olap_status olap_shard_barrier(olap_shard* shard, void* stream);
+/* the two halves of the barrier, for different streams: the scatter stream signals ("everything queued here before is done") and
+ * goes on without waiting for anybody; the stream that consumes the chunk waits.  Wait number n matches every rank's signal n.  */
+OLAP_API olap_status olap_shard_signal(olap_shard* shard, void* stream);
+OLAP_API olap_status olap_shard_wait(olap_shard* shard, void* stream);
 OLAP_API olap_status olap_shard_key_range(olap_shard* shard, const int64_t* keys, uint64_t n_rows, int64_t* out_min, int64_t* out_max, void* stream);
 OLAP_API olap_status olap_shard_plan(olap_shard* shard, int64_t global_min, int64_t global_max, uint64_t global_build_rows, int32_t hot, void* stream);
 OLAP_API olap_status olap_shard_scatter(olap_shard* shard, int32_t side, int32_t chunk, const int64_t* keys, uint64_t n_rows, uint32_t row_base,
@@ -236,15 +240,15 @@ OLAP_API olap_status olap_shard_finish(olap_shard* shard, uint64_t* host_count, 
                                        void* stream);
 /* Heavy hitters (Zipf-skewed probe keys), olap_shard_plan(hot = 1).  Order within a join:
  *   olap_shard_hot_candidates on every rank (samples its probe shard; keys as key - global_min + 1 in u32, with sample counts)
- *   -> the host language gathers the lists, sums the counts per key, keeps the <= 1024 most frequent -> olap_shard_hot_set
+ *   -> the host language gathers the lists, sums the counts per key, keeps the <= 4096 most frequent -> olap_shard_hot_set
  *   build side as before (scatter, BARRIER, olap_shard_build)
- *   olap_shard_hot_resolve (2048 x u64 on the device) -> element-wise MAX over the ranks -> olap_shard_hot_finalize
+ *   olap_shard_hot_resolve (8192 x u64 on the device) -> element-wise MAX over the ranks -> olap_shard_hot_finalize
  *   probe scatters: a row carrying a hot key never leaves its rank; its pair {hot slot, local probe row} goes to hot_pairs and the
  *   slot's build row is merged[slot] - 1 = (source rank << 32 | source row).                                                    */
 OLAP_API olap_status olap_shard_hot_candidates(olap_shard* shard, const int64_t* probe_keys, uint64_t n_rows, uint32_t* host_keys_plus1,
                                                uint32_t* host_counts, uint32_t capacity, uint32_t* host_n, void* stream);
 OLAP_API olap_status olap_shard_hot_set(olap_shard* shard, const uint32_t* keys_plus1, uint32_t n_keys, void* stream);
-OLAP_API olap_status olap_shard_hot_resolve(olap_shard* shard, uint64_t* out_dptr /* 2048 x u64 */, void* stream);
+OLAP_API olap_status olap_shard_hot_resolve(olap_shard* shard, uint64_t* out_dptr /* 8192 x u64 */, void* stream);
 OLAP_API olap_status olap_shard_hot_finalize(olap_shard* shard, const uint64_t* merged_dptr, olap_pair* hot_pairs, uint64_t max_hot_pairs, void* stream);
 OLAP_API olap_status olap_shard_pairs_to_global(olap_shard* shard, const olap_pair* pairs, uint64_t n_pairs, const uint64_t* build_row_offsets_dptr,
                                                 const uint64_t* probe_row_offsets_dptr, uint64_t* out_left, uint64_t* out_right, void* stream);
@@ -261,7 +265,7 @@ OLAP_API olap_status olap_sharded_hash_join_i64(olap_shard* const* shards, int32
                                                 const int64_t* const* probe_keys, const uint64_t* n_probe, olap_pair* const* out_pairs,
                                                 const uint64_t* max_matches, uint64_t* host_counts, olap_pair* const* hot_pairs,
                                                 const uint64_t* max_hot_pairs, uint64_t* host_hot_counts);
-OLAP_API olap_status olap_shard_hot_table(olap_shard* shard, uint64_t* host_merged /* [2048] */, void* stream);
+OLAP_API olap_status olap_shard_hot_table(olap_shard* shard, uint64_t* host_merged /* [8192] */, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Aggregation.  Replaces AggregateParams/AggregateSpec/AggregateKernel::aggregate

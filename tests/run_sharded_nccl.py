@@ -18,7 +18,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ctx = g.Context(local, 0, 8)
+    ctx = g.Context(local, 0, 12)
     ops = sharded.DeviceOps(ctx)
     torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.lib.olap_ctx_stream(ctx.handle, 0), device=ops.device))
     dev = ops.device

@@ -82,7 +82,7 @@ def zipf_keys(rng, n, keys_by_rank, s):
 
 
 @pytest.mark.timeout(900)
-@pytest.mark.parametrize("world,s", [(2, 1.0), (4, 1.5), (4, 0.5)])
+@pytest.mark.parametrize("world,s", [(2, 1.0), (4, 1.5), (4, 0.5), (8, 1.0)])
 def test_range_sharded_join_zipf_heavy_hitters_stay_on_their_rank(world, s):
     import gpu_olap_engine_b200 as g
     from gpu_olap_engine_b200.shard import ShardGroup
