@@ -339,11 +339,6 @@ def bench_single(ctx, g, args, local_rank, peak, peak_kind):
     # every pair of the last timed step, checked on the device: each probe row exactly once, equal keys
     verify_pairs(torch, dbuild, dprobe, pairs, nb, npb, cnt)
 
-    if args.skip_e2e or args.skip_cpu:
-        clocks = sampler.stop()
-        print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": ms_step, "phases_ms": phases, "gpu_launches": int(launches),
-                          "clocks": clocks}))
-        return 0
 
     # ---- the general path: sparse build keys (2^27 unique keys of a 2^33 domain) take hash partitions + bucket tables
     general = None
@@ -360,6 +355,13 @@ def bench_single(ctx, g, args, local_rank, peak, peak_kind):
                    "kernels": kernel_rooflines(gph, GENERAL_PHASE_BYTES, nb, npb, gcnt, peak, {}),
                    "job_roofline_frac": (8.0 * rows + 8.0 * gcnt) / (gms * 1e-3) / 1e9 / peak}
         del gb_, gp_
+
+    if args.skip_e2e or args.skip_cpu:   # profiling runs (ncu launch lists): the device-timed legs only, not a bench line
+        group_by = None if args.skip_groupby else bench_group_by(ctx, g, args, torch, stream, peak, peak_kind)
+        clocks = sampler.stop()
+        print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": ms_step, "phases_ms": phases, "gpu_launches": int(launches),
+                          "value_general": general, "group_by": group_by, "clocks": clocks}))
+        return 0
 
     # ---- e2e: host (pinned) buffers through the C-ABI, copies inside the timed region
     hb, hp, hout = C.c_void_p(), C.c_void_p(), C.c_void_p()
