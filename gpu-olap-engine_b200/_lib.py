@@ -66,6 +66,7 @@ SIGNATURES = {
     "olap_join_build_create": (i32, [vp, vp, u64, i32, vp, pvp]),
     "olap_join_probe": (i32, [vp, vp, u64, u32, vp, u64, vp, pu64, vp]),
     "olap_join_build_destroy": (i32, [vp]),
+    "olap_join_unmatched_rows": (i32, [vp, vp, u64, i32, u64, vp, vp, pu64, vp]),
     "olap_choose_join_strategy": (i32, [u64]),
     "olap_radix_partition_i64": (i32, [vp, vp, vp, u64, i32, vp, vp, vp, vp]),
     "olap_partition_of": (u32, [i64, i32]),

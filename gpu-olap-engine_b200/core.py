@@ -218,6 +218,14 @@ class Context:
         return out
 
     # ------------------------------------------------------------------ join
+    def join_unmatched_rows(self, pairs, n_pairs: int, side: int, n_rows: int, stream=None) -> np.ndarray:
+        """Row ids of one join side (0 = left / build, 1 = right / probe) that appear in no pair, ascending -- what Left / Right /
+        Full joins append NULL-extended (logical_plan.rs:52-58)."""
+        out = self.alloc(max(n_rows, 1), np.uint32)
+        cnt = C.c_uint64()
+        check(self.lib.olap_join_unmatched_rows(self.handle, _ptr(pairs), n_pairs, side, n_rows, out.ptr, None, C.byref(cnt), stream))
+        return out.to_numpy(cnt.value)
+
     def hash_join_i64(self, build_keys, n_build: int, probe_keys, n_probe: int, max_matches: Optional[int] = None,
                       strategy: int = JOIN_AUTO, out_pairs=None, want_pairs: bool = True, stream=None):
         """JoinKernel::join analogue.  Returns (count, pairs DeviceBuffer of uint32[2*k])."""

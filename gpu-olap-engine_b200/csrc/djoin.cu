@@ -28,7 +28,18 @@ constexpr int kRRows = 16;                        // rows per thread per tile
 constexpr int kRTile = kRThreads * kRRows;        // 4096 rows ranked / staged per CTA iteration
 constexpr int kRFineBits = 6;                     // second level: every coarse region is split into 64 ranges of 2^15 keys
 constexpr uint32_t kRMaxParts = 256u << kRFineBits;
-constexpr int kHotSlots = 8192;                   // open-addressing slots of the heavy-hitter table (<= 4096 keys, 32 KB of shared memory)
+constexpr int kHotSlots = 8192;                   // slots of the heavy-hitter table (32 KB of shared memory)
+// The table is 2048 BUCKETS of 4 slots; a key lives in bucket b1(key), or -- only when that one was full -- in bucket b2(key).  A
+// lookup is one 16-byte shared-memory load and four compares, plus the same again for the rare row whose first bucket is full: no
+// probing chain, no loop, no divergence.  At most a quarter of the slots hold a key (2048 keys: a bucket holds Poisson(1) of them, 2 %
+// are full).  What this replaces -- linear probing over 8192 slots, half full -- measured on rpart_kernel<raw, hot, peer> at Zipf 1.0
+// (profiles/r02_ncu_zipf_rpart_before.txt): 356 thread instructions per row against 60 without heavy hitters, a third of them in the
+// one-lane-at-a-time tail of the probing loop (8.7 iterations per warp and row slot, 3.7 lanes active), 3.8 ms per 2^27-row chunk
+// against 0.5 ms.  The keys given up (ranks 2049..4096 of a Zipf(1) distribution over 2^31 rows carry 3 % of the probe rows) travel
+// the normal way.
+constexpr int kHotBucketBits = 11;
+constexpr uint32_t kHotMaxKeys = kHotSlots / 4;
+static_assert(kHotSlots == 4 << kHotBucketBits, "2048 buckets of 4 slots");
 constexpr uint32_t kHotSampleSlots = 1u << 19;    // counting table of the sampling pass
 
 // Why two levels (scratch/part_bench.cu on a B200, 2^29 rows, 16 B/row of traffic): ONE pass to 4096 partitions is bound by its
@@ -71,56 +82,57 @@ struct RPartArgs {
 __device__ __forceinline__ uint32_t peer_part(const RPartArgs& a, uint32_t d) { return (uint32_t)(((uint64_t)(d >> kRShift) * a.peer_mf) >> 32); }
 __device__ __forceinline__ uint32_t peer_dest(const RPartArgs& a, uint32_t part) { return (part * a.peer_mq) >> 24; }
 
-__device__ __forceinline__ uint32_t hot_slot_of(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - 13); }
-static_assert(kHotSlots == 8192, "hot_slot_of shifts for 2^13 slots");
+__host__ __device__ __forceinline__ uint32_t hot_b1(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - kHotBucketBits); }
+__host__ __device__ __forceinline__ uint32_t hot_b2(uint32_t d) { return ((d ^ 0x5BD1E995u) * 0x85EBCA6Bu) >> (32 - kHotBucketBits); }
 
-// CTAs per SM: 4 for raw keys (64 registers); the region passes keep the carried id next to offset and rank -- under a 64-register
-// cap ptxas serialises their 16 loads (2.18 ms instead of 1.35 ms for 2^29 rows) -- so they run 3 per SM with 80 registers
-// Heavy-hitter lookup of a thread's R rows at once (linear probing, table at most half full).  state[k]: 0 = dead row, 1 = live row
-// still to be looked up; on return a live row is 2 (not a heavy hitter) or 0x80000000 | slot (heavy hitter).  The first rounds probe
-// all rows together -- independent shared-memory loads in flight -- because a row-by-row probing loop left every load's latency
-// exposed (3.3 ms instead of 1.0 ms per 2^27-row chunk at Zipf 1.0); the rare long chains are finished one by one.
+// slot of `want` (= offset + 1) in a bucket's four keys, or ~0
+__device__ __forceinline__ uint32_t hot_match(const uint4& b, uint32_t want, uint32_t slot0) {
+  return b.x == want ? slot0 : b.y == want ? slot0 + 1 : b.z == want ? slot0 + 2 : b.w == want ? slot0 + 3 : 0xFFFFFFFFu;
+}
+
+// Heavy-hitter lookup of a thread's R rows.  state[k]: 0 = dead row, 1 = live row to be looked up; on return a live row is 2 (not
+// a heavy hitter) or 0x80000000 | slot (heavy hitter).  hotk: the table in shared memory, 16-byte aligned.  Four rows at a time:
+// their bucket loads are in flight together, and four buckets are all the registers hold.
 template <int R>
 __device__ __forceinline__ uint32_t hot_lookup(const uint32_t* hotk, const uint32_t (&d)[R], uint32_t (&state)[R]) {
-  uint32_t slot[R];
-#pragma unroll
-  for (int k = 0; k < R; k++) slot[k] = hot_slot_of(d[k]);
+  static_assert(R % 4 == 0, "rows are looked up four at a time");
+  const uint4* hk4 = reinterpret_cast<const uint4*>(hotk);
   uint32_t nhot = 0;
 #pragma unroll
-  for (int round = 0; round < 3; round++) {
-    uint32_t hk[R];
+  for (int k0 = 0; k0 < R; k0 += 4) {
+    uint4 b[4];
 #pragma unroll
-    for (int k = 0; k < R; k++) hk[k] = state[k] == 1u ? hotk[slot[k]] : 0u;
+    for (int j = 0; j < 4; j++) b[j] = hk4[hot_b1(d[k0 + j])];
 #pragma unroll
-    for (int k = 0; k < R; k++) {
+    for (int j = 0; j < 4; j++) {
+      const int k = k0 + j;
       if (state[k] != 1u) continue;
-      if (hk[k] == 0u) state[k] = 2u;
-      else if (hk[k] == d[k] + 1u) { state[k] = 0x80000000u | slot[k]; nhot++; }
-      else slot[k] = (slot[k] + 1) & (kHotSlots - 1);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < R; k++) {
-    while (state[k] == 1u) {
-      const uint32_t h = hotk[slot[k]];
-      if (h == 0u) state[k] = 2u;
-      else if (h == d[k] + 1u) { state[k] = 0x80000000u | slot[k]; nhot++; }
-      else slot[k] = (slot[k] + 1) & (kHotSlots - 1);
+      const uint32_t want = d[k] + 1u;
+      uint32_t hit = hot_match(b[j], want, hot_b1(d[k]) << 2);
+      if (hit == 0xFFFFFFFFu && b[j].w != 0u) {  // the first bucket is full (slots fill in order): the key may live in its second one
+        const uint32_t b2 = hot_b2(d[k]);
+        hit = hot_match(hk4[b2], want, b2 << 2);
+      }
+      if (hit != 0xFFFFFFFFu) { state[k] = 0x80000000u | hit; nhot++; }
+      else state[k] = 2u;
     }
   }
   return nhot;
 }
 
-// Stage position of a heavy-hitter row: the hot rows of a warp instruction reserve their slots with ONE shared-memory atomic
-// (a per-row atomic on the single counter serialised the whole CTA: 38 % of the rows are hot at Zipf 1.0).  All 32 lanes call it.
-__device__ __forceinline__ uint32_t hot_stage_slot(uint32_t* counter, bool is_hot) {
-  const uint32_t m = __ballot_sync(0xffffffffu, is_hot);
-  if (m == 0) return 0;
-  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m) << 16) >> 16;
-  base = __shfl_sync(0xffffffffu, base, leader);
-  return base + __popc(m & ((1u << lane) - 1));
+// Stage positions of a thread's heavy-hitter rows: the warp scans its per-thread counts and reserves the warp's slots with ONE
+// shared-memory atomic per tile (it was a ballot + atomic per row slot: 75 instructions per row in the scatter phase; a per-row
+// atomic on the single counter serialised the whole CTA before that -- 38 % of the rows are hot at Zipf 1.0).  The counter ends up
+// holding the tile's number of hot rows.  All 32 lanes call it; returns the thread's first slot.
+__device__ __forceinline__ uint32_t hot_stage_base(uint32_t* counter, uint32_t nhot) {
+  const int lane = threadIdx.x & 31;
+  uint32_t incl = nhot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  uint32_t wbase = 0;
+  if (lane == 31 && incl) wbase = atomicAdd(counter, incl);
+  wbase = __shfl_sync(0xffffffffu, wbase, 31);
+  return wbase + incl - nhot;
 }
 
 template <int INPUT, bool HOT, bool PEER = false>
@@ -196,11 +208,8 @@ __global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) 
       }
     }
     if (INPUT == kInRaw && oob && a.oob_is_error) a.flags[kFlagOutOfRange] = 1;
-    if (HOT) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) nhot += __shfl_xor_sync(0xffffffffu, nhot, o);
-      if (lane == 0 && nhot) atomicAdd(&s_hot[par], nhot);
-    }
+    uint32_t hbase = 0;   // HOT: this thread's first slot among the tile's heavy-hitter rows
+    if (HOT) hbase = hot_stage_base(&s_hot[par], nhot);
     __syncthreads();
 
     // phase 2: exclusive scan of the tile histogram (one partition per thread); every non-empty (tile, partition) run is
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) 
     if (tid == 0) {
       s_over[par ^ 1] = 0; s_hot[par ^ 1] = 0;  // the previous tile is done with them, the next one starts after a barrier
       if (HOT) {  // the tile's heavy-hitter pairs are reserved in the output now; the round trip is over by the time they are written
-        const uint32_t nh = s_hot[par] & 0xFFFFu;
+        const uint32_t nh = s_hot[par];
         if (nh) s_hotbase = atomicAdd(a.count, (unsigned long long)nh);
       }
     }
@@ -240,12 +249,10 @@ __global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) 
 #pragma unroll
     for (int k = 0; k < R; k++) {
       const bool is_hot = HOT && rk[k] != kREmpty && (rk[k] & 0x80000000u);
-      uint32_t hslot = 0;
-      if (HOT) hslot = hot_stage_slot(&s_hot[par], is_hot);
       if (rk[k] == kREmpty) continue;
       const uint32_t id = INPUT == kInRegionsCarry ? (uint32_t)key[k] : idb + (uint32_t)(row0 + (uint64_t)k * kRThreads + tid);
       if (is_hot) {
-        stage[kRTile - 1 - hslot] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (rk[k] & (kHotSlots - 1)));
+        stage[kRTile - 1 - hbase++] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (rk[k] & (kHotSlots - 1)));
       } else {
         stage[cnt[(PEER ? peer_part(a, d[k]) : d[k] >> a.shift) - pbase] + rk[k]] = ((uint64_t)d[k] << 32) | id;
       }
@@ -276,7 +283,7 @@ __global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) 
       }
     }
     if (HOT) {
-      const uint32_t nh = s_hot[par] & 0xFFFFu;
+      const uint32_t nh = s_hot[par];
       if (nh) {
         const unsigned long long base = s_hotbase;
         for (uint32_t i = tid; i < nh; i += kRThreads) {
@@ -391,7 +398,7 @@ __global__ void __maxnreg__(48) djoin_shared_kernel(const __grid_constant__ DJoi
 
 // ------------------------------------------------------------------------------------------- heavy hitters
 // Sample the probe keys, count the samples per key in a small global table, keep the keys seen at least `min_count` times (at
-// most kHotSlots / 2 of them).  All on the device: no host round trip.
+// most kHotMaxKeys of them).  All on the device: no host round trip.
 struct HotArgs {
   const uint64_t* keys; uint64_t n; uint64_t stride; uint32_t n_samples;
   uint64_t rmin, rrange;
@@ -416,7 +423,7 @@ __global__ void hot_sample_kernel(HotArgs h) {
   }
 }
 
-// one CTA: raise the threshold until at most kHotSlots / 2 keys qualify, then build the open-addressing hot table
+// one CTA: raise the threshold until at most kHotMaxKeys keys qualify, then build the open-addressing hot table
 __global__ void __launch_bounds__(1024) hot_select_kernel(HotArgs h) {
   __shared__ uint32_t s_cnt;
   __shared__ uint32_t s_thr;
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__(1024) hot_select_kernel(HotArgs h) {
     for (uint32_t i = threadIdx.x; i < h.tab_slots; i += blockDim.x) mine += h.tab_key[i] && h.tab_cnt[i] >= thr;
     if (mine) atomicAdd(&s_cnt, mine);
     __syncthreads();
-    if (threadIdx.x == 0) s_thr = s_cnt <= kHotSlots / 2 ? 0 : thr + (thr + 1) / 2;
+    if (threadIdx.x == 0) s_thr = s_cnt <= kHotMaxKeys ? 0 : thr + (thr + 1) / 2;
     __syncthreads();
     if (s_thr == 0) break;
     thr = s_thr;
@@ -437,9 +444,14 @@ __global__ void __launch_bounds__(1024) hot_select_kernel(HotArgs h) {
   for (uint32_t i = threadIdx.x; i < h.tab_slots; i += blockDim.x) {
     const uint32_t k = h.tab_key[i];
     if (k && h.tab_cnt[i] >= thr) {
-      uint32_t s = hot_slot_of(k - 1);
-      while (atomicCAS(&h.hot_keys[s], 0u, k) != 0) s = (s + 1) & (kHotSlots - 1);
-      atomicAdd(h.hot_n, 1u);
+      // first free slot of bucket b1, else of bucket b2 (slots are taken in order and never freed, so a bucket whose last slot is
+      // taken is full); a key that finds both full is simply not a heavy hitter
+      bool placed = false;
+      for (int t = 0; t < 2 && !placed; t++) {
+        const uint32_t b = t ? hot_b2(k - 1) : hot_b1(k - 1);
+        for (int j = 0; j < 4 && !placed; j++) placed = atomicCAS(&h.hot_keys[4 * b + j], 0u, k) == 0u;
+      }
+      if (placed) atomicAdd(h.hot_n, 1u);
     }
   }
 }
@@ -490,10 +502,13 @@ static olap_status launch_rpart_t(olap_ctx* ctx, const RPartArgs& a, unsigned gr
 static olap_status launch_rpart(olap_ctx* ctx, const RPartArgs& a, int input, unsigned grid_limit, cudaStream_t s) {
   const uint64_t tiles = input == kInRaw ? (a.n + kRTile - 1) / kRTile : (uint64_t)((a.reg_cap + kRTile - 1) / kRTile) * a.n_reg;
   if (!tiles) return OLAP_OK;
-  uint64_t grid = (uint64_t)ctx->sm_count * (input == kInRaw ? 4 : 3);
+  const bool hot = a.hot_keys != nullptr, peer = a.peer_out[0] != nullptr, shared = grid_limit != 0;
+  // one wave of resident CTAs (the tile loop strides by the grid): 4 per SM for raw keys, 3 for the region passes and for the
+  // heavy-hitter variant (__launch_bounds__ above) -- launched with 4 per SM, a quarter of its CTAs ran as a second wave at a third
+  // of the occupancy
+  uint64_t grid = (uint64_t)ctx->sm_count * ((input == kInRaw && !hot) ? 4 : 3);
   if (grid_limit && grid > grid_limit) grid = grid_limit;
   if (grid > tiles) grid = tiles;
-  const bool hot = a.hot_keys != nullptr, peer = a.peer_out[0] != nullptr, shared = grid_limit != 0;
   if (input == kInRaw && peer) return hot ? launch_rpart_t<kInRaw, true, true>(ctx, a, (unsigned)grid, shared, s) : launch_rpart_t<kInRaw, false, true>(ctx, a, (unsigned)grid, shared, s);
   if (input == kInRaw) return hot ? launch_rpart_t<kInRaw, true>(ctx, a, (unsigned)grid, shared, s) : launch_rpart_t<kInRaw, false>(ctx, a, (unsigned)grid, shared, s);
   if (input == kInRegionsCarry) return launch_rpart_t<kInRegionsCarry, false>(ctx, a, (unsigned)grid, shared, s);
@@ -712,7 +727,7 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* stage0 = reinterpret_cast<uint64_t*>(smem_raw);           // [2][kShufStage]
   __shared__ uint32_t cnt[kRThreads];
-  __shared__ uint32_t hotk[HOT ? kHotSlots : 1];
+  __shared__ __align__(16) uint32_t hotk[HOT ? kHotSlots : 4];
   __shared__ uint32_t s_warp[NW];
   __shared__ uint32_t s_hot[2];
   __shared__ unsigned long long s_hotbase;
@@ -756,11 +771,8 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
     if (HOT) nhot = hot_lookup<R>(hotk, d, pr);
 #pragma unroll
     for (int k = 0; k < R; k++) pr[k] = (pr[k] == 1u || pr[k] == 2u) ? 0u : (pr[k] == 0u ? kREmpty : pr[k]);   // 0 = live, to be ranked below
-    if (HOT) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) nhot += __shfl_xor_sync(0xffffffffu, nhot, o);
-      if (lane == 0 && nhot) atomicAdd(&s_hot[par], nhot);
-    }
+    uint32_t hbase = 0;
+    if (HOT) hbase = hot_stage_base(&s_hot[par], nhot);
     uint32_t rank[R];
 #pragma unroll
     for (int k = 0; k < R; k++) rank[k] = pr[k] == 0u ? atomicAdd(&cnt[peer_part(a, d[k])], 1u) : 0u;
@@ -785,7 +797,7 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
     if (tid == 0) {
       s_hot[par ^ 1] = 0;
       if (HOT) {
-        const uint32_t nh = s_hot[par] & 0xFFFFu;
+        const uint32_t nh = s_hot[par];
         if (nh) s_hotbase = atomicAdd(a.count, (unsigned long long)nh);
       }
     }
@@ -807,12 +819,10 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
 #pragma unroll
     for (int k = 0; k < R; k++) {
       const bool is_hot = HOT && pr[k] != kREmpty && (pr[k] & 0x80000000u);
-      uint32_t hslot = 0;
-      if (HOT) hslot = hot_stage_slot(&s_hot[par], is_hot);
       if (pr[k] == kREmpty) continue;
       const uint32_t id = a.id_base + (uint32_t)(row0 + (uint64_t)k * kRThreads + tid);
       if (is_hot) {
-        stage[kShufStage - 1 - hslot] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (pr[k] & (kHotSlots - 1)));
+        stage[kShufStage - 1 - hbase++] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (pr[k] & (kHotSlots - 1)));
       } else {
         const uint32_t part = pr[k] >> 16;
         const uint32_t dl = d[k] - peer_dest(a, part) * (a.peer_q * a.peer_subw);
@@ -832,7 +842,7 @@ __global__ void __maxnreg__(96) shuffle_kernel(const __grid_constant__ RPartArgs
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     cnt[tid] = 0;
     if (HOT) {
-      const uint32_t nh = s_hot[par] & 0xFFFFu;
+      const uint32_t nh = s_hot[par];
       if (nh) {
         const unsigned long long base = s_hotbase;
         for (uint32_t i = tid; i < nh; i += kRThreads) {
@@ -909,7 +919,24 @@ olap_status range_shuffle_publish(olap_ctx* ctx, const uint32_t* cursor, uint32_
 
 // ------------------------------------------------------------------------------------------- heavy hitters across ranks
 uint32_t hot_table_slots() { return kHotSlots; }
-uint32_t hot_slot_host(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - 13); }
+uint32_t hot_max_keys() { return kHotMaxKeys; }
+// Host-side build of the same table, sequentially over the caller's (sorted) keys so that every rank ends up with the same slot for
+// the same key.  keys_plus1: offset + 1; tab: hot_table_slots() zeroed words.  Returns the keys placed.
+uint32_t hot_table_build_host(const uint32_t* keys_plus1, uint32_t n, uint32_t* tab) {
+  uint32_t placed = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t k = keys_plus1[i];
+    if (k == 0 || k == 0xFFFFFFFFu) continue;
+    bool done = false;
+    for (int t = 0; t < 2 && !done; t++) {
+      const uint32_t b = t ? hot_b2(k - 1) : hot_b1(k - 1);
+      for (int j = 0; j < 4 && !done; j++)
+        if (tab[4 * b + j] == 0) { tab[4 * b + j] = k; done = true; }
+    }
+    placed += done;
+  }
+  return placed;
+}
 uint32_t hot_sample_slots() { return kHotSampleSlots; }
 
 // (offset + 1, sample count) of every sampled key seen at least min_count times -> list (at most cap entries)

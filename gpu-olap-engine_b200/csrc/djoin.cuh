@@ -47,7 +47,8 @@ void dj_probe_end(DJProbe& p, cudaStream_t s);
 // heavy-hitter table handed to a pass over raw probe keys: rows whose key is in it are joined on the spot
 struct HotRef { const uint32_t* hot_keys = nullptr; const uint32_t* hot_ids = nullptr; olap_pair* pairs = nullptr; uint64_t max_matches = 0; unsigned long long* count = nullptr; };
 uint32_t hot_table_slots();
-uint32_t hot_slot_host(uint32_t d);
+uint32_t hot_max_keys();   // at most a quarter of the slots hold a key
+uint32_t hot_table_build_host(const uint32_t* keys_plus1, uint32_t n, uint32_t* tab);
 uint32_t hot_sample_slots();
 olap_status hot_candidates(olap_ctx* ctx, const uint64_t* keys, uint64_t n, int64_t gmin, uint64_t grange, uint32_t* scratch, uint32_t cap,
                            uint32_t** out_key, uint32_t** out_cnt, uint32_t** out_n, cudaStream_t s);

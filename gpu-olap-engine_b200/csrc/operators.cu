@@ -37,6 +37,11 @@ struct Col {
   BufPtr buf;
   uint64_t off = 0;     // first row inside buf: the batches of a consolidated table are views into one allocation per column
   uint64_t* data() const { return (uint64_t*)buf->p + off; }
+  // optional validity, one byte per row, 1 = valid (column_buffer.rs:37-41).  Set by olap_register_batch for columns that arrive
+  // with nulls and by outer joins for the NULL-extended side; carried by scans, exported as an Arrow bitmap.  Every other operator
+  // reads a null as the 0 / 0.0 stored in its place (record_batch_convert.rs:103, :108) and emits non-null columns.
+  BufPtr valid;
+  uint8_t* validity() const { return valid ? (uint8_t*)valid->p : nullptr; }
 };
 struct Batch { std::vector<Col> cols; uint64_t n = 0; };
 using Batches = std::vector<Batch>;
@@ -59,6 +64,12 @@ __global__ void __launch_bounds__(256) gather_pairs_kernel(const uint64_t* __res
                                                            uint64_t n, uint64_t* __restrict__ out) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, st = (uint64_t)gridDim.x * blockDim.x;
   for (; i < n; i += st) out[i] = __ldg(col + ld_stream_u32(pairs + 2 * i + side));
+}
+// flags[pairs[i].side] = 1: the rows of one join side that found a partner (8-byte flags: the ordered selection pass reads them
+// as an Int64 column)
+__global__ void __launch_bounds__(256) mark_pairs_kernel(const uint32_t* __restrict__ pairs, int side, uint64_t n, uint64_t* __restrict__ flags) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, st = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += st) flags[ld_stream_u32(pairs + 2 * i + side)] = 1;
 }
 // out[i] = col[i * stride]: an evenly spaced sample of a column
 __global__ void __launch_bounds__(256) sample_kernel(const uint64_t* __restrict__ col, uint64_t stride, uint64_t m, uint64_t* __restrict__ out) {
@@ -292,6 +303,12 @@ static olap_status exec_projection(olap_ctx* ctx, const olap_plan* p, Batches* o
       OLAP_TRY(eval_expr(ctx, e, b, &v));
       OLAP_TRY(materialise(ctx, v, b.n, &m));
       Col c; c.name = expr_name(e); c.type = m.type; c.buf = m.buf; c.off = m.off;
+      if (e->kind == EXPR_COLUMN) {  // a column passed through keeps its validity (resolved like eval_expr: name first, then index)
+        const Col* src = nullptr;
+        for (const Col& x : b.cols) if (x.name == e->text) { src = &x; break; }
+        if (!src && e->index < b.cols.size()) src = &b.cols[e->index];
+        if (src) c.valid = src->valid;
+      }
       o.cols.push_back(c);
     }
     out->push_back(o);
@@ -361,7 +378,8 @@ static olap_status exec_hash_join(olap_ctx* ctx, const olap_plan* p, Batches* ou
   OLAP_TRY(exec(ctx, p->in, &left));
   OLAP_TRY(exec(ctx, p->right, &right));
   if (left.empty() || right.empty()) return OLAP_OK;  // executor.rs:231-233
-  if (p->join_type != OLAP_JOIN_INNER) { set_error("only INNER joins execute (README.md:410-411)"); return OLAP_ERR_UNSUPPORTED; }
+  const int jt = p->join_type;
+  if (jt < OLAP_JOIN_INNER || jt > OLAP_JOIN_FULL) { set_error("unknown join type %d (logical_plan.rs:52-58)", jt); return OLAP_ERR_BAD_ARG; }
   if (p->lkeys.empty() || p->rkeys.empty()) { set_error("hash join needs one key expression per side"); return OLAP_ERR_BAD_ARG; }
   uint64_t nl = 0, nr = 0;
   for (const Batch& b : left) nl += b.n;
@@ -384,13 +402,36 @@ static olap_status exec_hash_join(olap_ctx* ctx, const olap_plan* p, Batches* ou
     OLAP_TRY(st);
     break;
   }
-  Batch o; o.n = count;
+  // Left / Right / Full (logical_plan.rs:52-58): the preserved side's rows without a partner follow the inner pairs, in row
+  // order -- unmatched left rows first, then unmatched right rows -- with the other side's columns NULL (value 0, validity 0)
+  uint64_t ul = 0, ur = 0;
+  BufPtr lsel, rsel;
+  if (jt == OLAP_JOIN_LEFT || jt == OLAP_JOIN_FULL) {
+    OLAP_TRY(new_buf(ctx, std::max<uint64_t>(nl, 1) * 4, &lsel));
+    OLAP_TRY(olap_join_unmatched_rows(ctx, (const olap_pair*)pairs->p, count, 0, nl, (uint32_t*)lsel->p, nullptr, &ul, nullptr));
+  }
+  if (jt == OLAP_JOIN_RIGHT || jt == OLAP_JOIN_FULL) {
+    OLAP_TRY(new_buf(ctx, std::max<uint64_t>(nr, 1) * 4, &rsel));
+    OLAP_TRY(olap_join_unmatched_rows(ctx, (const olap_pair*)pairs->p, count, 1, nr, (uint32_t*)rsel->p, nullptr, &ur, nullptr));
+  }
+  const uint64_t total = count + ul + ur;
+  cudaStream_t s0 = ctx->streams[0];
+  Batch o; o.n = total;
   for (int side = 0; side < 2; side++) {
     const Batch& S = side ? R : L;
+    const uint64_t own = side ? ur : ul, own_at = side ? count + ul : count;      // this side's unmatched rows and where they go
+    const uint64_t null_n = side ? ul : ur, null_at = side ? count : count + ul;  // rows where this side is NULL
     for (const Col& c : S.cols) {  // left columns, then right columns, gathered by the row-id pairs
       Col oc; oc.name = c.name; oc.type = c.type;
-      OLAP_TRY(new_buf(ctx, count * 8, &oc.buf));
-      if (count) { gather_pairs_kernel<<<small_grid(ctx, count), 256, 0, ctx->streams[0]>>>(c.data(), (const uint32_t*)pairs->p, side, count, oc.data()); count_launch(ctx); }
+      OLAP_TRY(new_buf(ctx, std::max<uint64_t>(total, 1) * 8, &oc.buf));
+      if (count) { gather_pairs_kernel<<<small_grid(ctx, count), 256, 0, s0>>>(c.data(), (const uint32_t*)pairs->p, side, count, oc.data()); count_launch(ctx); }
+      if (own) OLAP_TRY(olap_gather_8b(ctx, c.data(), (const uint32_t*)(side ? rsel : lsel)->p, own, oc.data() + own_at, nullptr));
+      if (null_n) {
+        OLAP_CUDA(cudaMemsetAsync(oc.data() + null_at, 0, null_n * 8, s0));
+        OLAP_TRY(new_buf(ctx, total, &oc.valid));
+        OLAP_CUDA(cudaMemsetAsync(oc.validity(), 1, total, s0));
+        OLAP_CUDA(cudaMemsetAsync(oc.validity() + null_at, 0, null_n, s0));
+      }
       o.cols.push_back(oc);
     }
   }
@@ -719,8 +760,49 @@ olap_plan* olap_plan_aggregate(olap_plan* input, olap_expr* const* group_by, int
 }
 void olap_plan_free(olap_plan* p) { delete p; }
 
+// Rows of one join side that appear in no pair, ascending: mark the partners, then the ordered selection pass of the filter
+// (filter.cu) over the flags.  Composed of public calls, so no context lock is held here.
+olap_status olap_join_unmatched_rows(olap_ctx* ctx, const olap_pair* pairs, uint64_t n_pairs, int32_t side, uint64_t n_rows, uint32_t* out_row_ids,
+                                     uint64_t* out_count_dptr, uint64_t* host_count, void* stream) {
+  OLAP_REQUIRE(ctx, "ctx is NULL");
+  OLAP_REQUIRE(side == 0 || side == 1, "side is 0 (left / build rows) or 1 (right / probe rows)");
+  OLAP_REQUIRE(n_pairs == 0 || pairs, "pairs is NULL");
+  OLAP_REQUIRE(n_rows < 0xFFFFFFFFULL, "row ids are u32");
+  OLAP_REQUIRE(n_rows == 0 || out_row_ids, "out_row_ids is NULL");
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream_of(stream);
+  if (n_rows == 0) {
+    if (out_count_dptr) OLAP_CUDA(cudaMemsetAsync(out_count_dptr, 0, 8, s));
+    if (host_count) { *host_count = 0; OLAP_CUDA(cudaStreamSynchronize(s)); }
+    return OLAP_OK;
+  }
+  void* flags = nullptr;
+  OLAP_TRY(olap_pool_alloc(ctx, n_rows * 8, stream, &flags));
+  olap_status st = OLAP_OK;
+  cudaError_t e = cudaMemsetAsync(flags, 0, n_rows * 8, s);
+  if (e == cudaSuccess && n_pairs) {
+    mark_pairs_kernel<<<small_grid(ctx, n_pairs), 256, 0, s>>>((const uint32_t*)pairs, side, n_pairs, (uint64_t*)flags);
+    count_launch(ctx);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) st = cuda_fail(e, "marking the matched rows", __FILE__, __LINE__);
+  if (st == OLAP_OK) st = olap_filter_i64(ctx, (const int64_t*)flags, n_rows, OLAP_EQ, 0, nullptr, out_row_ids, out_count_dptr, host_count, stream);
+  olap_pool_free(ctx, flags, stream);   // stream-ordered: behind the selection pass
+  return st;
+}
+
+static olap_status register_batch_impl(olap_ctx* ctx, const char* table_name, ArrowArray* batch, ArrowSchema* schema);
+
 olap_status olap_register_batch(olap_ctx* ctx, const char* table_name, ArrowArray* batch, ArrowSchema* schema) {
   OLAP_REQUIRE(ctx && table_name && batch && schema, "NULL argument");
+  const olap_status st = register_batch_impl(ctx, table_name, batch, schema);
+  // the array is consumed whatever happened: the copies above were synchronised (or never started), so the producer may free it
+  if (st != OLAP_OK) cudaStreamSynchronize(ctx->streams[0]);
+  if (batch->release) batch->release(batch);
+  return st;
+}
+
+static olap_status register_batch_impl(olap_ctx* ctx, const char* table_name, ArrowArray* batch, ArrowSchema* schema) {
   OLAP_REQUIRE(schema->format && strcmp(schema->format, "+s") == 0, "a RecordBatch is a struct-typed ArrowArray (format \"+s\")");
   OLAP_REQUIRE(batch->n_children == schema->n_children, "array/schema children mismatch");
   Batch b; b.n = (uint64_t)batch->length;
@@ -734,11 +816,13 @@ olap_status olap_register_batch(olap_ctx* ctx, const char* table_name, ArrowArra
     const int st = src_type_of(s->format);
     if (st >= 0) {
       c.type = st >= OLAP_SRC_F32 ? OLAP_F64 : OLAP_I64;
-      OLAP_TRY(olap_column_upload(ctx, a->buffers[1], b.n, st, validity, (uint64_t)a->offset, c.buf->p, nullptr, nullptr));
+      if (validity && b.n) OLAP_TRY(new_buf(ctx, b.n, &c.valid));
+      OLAP_TRY(olap_column_upload(ctx, a->buffers[1], b.n, st, validity, (uint64_t)a->offset, c.buf->p, c.validity(), nullptr));
     } else if (s->format && (strcmp(s->format, "u") == 0 || strcmp(s->format, "U") == 0)) {
       // Utf8 -> FNV-1a-64 as i64, nulls -> 0 (record_batch_convert.rs:93-97, :112-121); hashed on the host: strings are not on the hot path
       c.type = OLAP_I64;
       std::vector<int64_t> h(b.n);
+      std::vector<uint8_t> hv(validity ? b.n : 0);
       const bool large = s->format[0] == 'U';
       const uint8_t* data = (const uint8_t*)a->buffers[2];
       for (uint64_t r = 0; r < b.n; r++) {
@@ -747,8 +831,13 @@ olap_status olap_register_batch(olap_ctx* ctx, const char* table_name, ArrowArra
         int64_t o0 = large ? ((const int64_t*)a->buffers[1])[idx] : ((const int32_t*)a->buffers[1])[idx];
         int64_t o1 = large ? ((const int64_t*)a->buffers[1])[idx + 1] : ((const int32_t*)a->buffers[1])[idx + 1];
         h[r] = valid ? (int64_t)fnv1a64(data + o0, (uint64_t)(o1 - o0)) : 0;
+        if (validity) hv[r] = valid ? 1 : 0;
       }
       OLAP_TRY(olap_memcpy_h2d(ctx, c.buf->p, h.data(), b.n * 8, nullptr));
+      if (validity && b.n) {
+        OLAP_TRY(new_buf(ctx, b.n, &c.valid));
+        OLAP_TRY(olap_memcpy_h2d(ctx, c.valid->p, hv.data(), b.n, nullptr));
+      }
       OLAP_TRY(olap_stream_synchronize(ctx, nullptr));
     } else {
       set_error("Unsupported column type for GPU conversion: format '%s' (column '%s')", s->format ? s->format : "?", c.name.c_str());
@@ -756,8 +845,7 @@ olap_status olap_register_batch(olap_ctx* ctx, const char* table_name, ArrowArra
     }
     b.cols.push_back(c);
   }
-  OLAP_TRY(olap_stream_synchronize(ctx, nullptr));  // the Arrow buffers may go away once we release the array
-  if (batch->release) batch->release(batch);
+  OLAP_TRY(olap_stream_synchronize(ctx, nullptr));  // the Arrow buffers may go away once the caller releases the array
   Catalog* cat = catalog_of(ctx);
   std::lock_guard<std::mutex> g(cat->mu);
   cat->tables[table_name].push_back(b);
@@ -803,13 +891,25 @@ olap_status olap_result_export(olap_result* r, int32_t i, ArrowArray* out_array,
       if (e != cudaSuccess) { for (void* q : ap->owned) free(q); delete ap; delete sp; return cuda_fail(e, "export copy", __FILE__, __LINE__); }
     }
     ap->bufs[2 * c] = nullptr; ap->bufs[2 * c + 1] = host;
+    int64_t nulls = 0;
+    if (b.cols[c].valid && b.n) {  // byte-per-row validity -> Arrow bitmap (LSB first), packed on the host
+      olap_ctx* ctx = b.cols[c].buf->ctx;
+      std::vector<uint8_t> bytes(b.n);
+      cudaError_t e = cudaMemcpyAsync(bytes.data(), b.cols[c].validity(), b.n, cudaMemcpyDeviceToHost, ctx->streams[0]);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->streams[0]);
+      if (e != cudaSuccess) { for (void* q : ap->owned) free(q); delete ap; delete sp; return cuda_fail(e, "export copy", __FILE__, __LINE__); }
+      uint8_t* bits = (uint8_t*)calloc((b.n + 7) / 8 + 8, 1);
+      ap->owned.push_back(bits);
+      for (uint64_t r = 0; r < b.n; r++) { if (bytes[r]) bits[r >> 3] |= (uint8_t)(1u << (r & 7)); else nulls++; }
+      if (nulls) ap->bufs[2 * c] = bits;
+    }
     ArrowArray& a = ap->children[c];
-    a.length = (int64_t)b.n; a.null_count = 0; a.offset = 0; a.n_buffers = 2; a.n_children = 0;
+    a.length = (int64_t)b.n; a.null_count = nulls; a.offset = 0; a.n_buffers = 2; a.n_children = 0;
     a.buffers = &ap->bufs[2 * c]; a.children = nullptr; a.dictionary = nullptr; a.release = release_child; a.private_data = nullptr;
     ap->child_arrays[c] = &a;
     sp->names[c] = b.cols[c].name;
     ArrowSchema& s = sp->children[c];
-    s.format = b.cols[c].type == OLAP_F64 ? "g" : "l"; s.name = sp->names[c].c_str(); s.metadata = nullptr; s.flags = 0; s.n_children = 0;
+    s.format = b.cols[c].type == OLAP_F64 ? "g" : "l"; s.name = sp->names[c].c_str(); s.metadata = nullptr; s.flags = b.cols[c].valid ? 2 /* ARROW_FLAG_NULLABLE */ : 0; s.n_children = 0;
     s.children = nullptr; s.dictionary = nullptr; s.release = release_child_schema; s.private_data = nullptr;
     sp->ptrs[c] = &s;
   }

@@ -19,7 +19,7 @@
 // "comp").  The only cross-rank synchronisation is "every rank's shuffle of chunk k has finished": stream events inside one
 // process (olap_sharded_hash_join_i64), or a collective of the host language between the per-phase calls (sharded.py: NCCL).
 //
-// Skew (Zipf): heavy-hitter keys are agreed on by all ranks (olap_shard_hot_*), their build rows are replicated (a <= 4096-entry
+// Skew (Zipf): heavy-hitter keys are agreed on by all ranks (olap_shard_hot_*), their build rows are replicated (a <= 2048-entry
 // table), and probe rows carrying them never leave their source rank: the shuffle kernel joins them on the spot.
 #include "common.cuh"
 #include "djoin.cuh"
@@ -485,7 +485,7 @@ olap_status olap_shard_sent_rows(olap_shard* sh, uint64_t* host_rows_per_dest /*
 
 // ---- heavy hitters (Zipf-skewed probe keys).  With olap_shard_plan(hot = 1) the order of a join is:
 //   olap_shard_hot_candidates (every rank, its probe shard)  ->  the host language gathers the lists, sums the counts per key,
-//   keeps the <= 4096 most frequent  ->  olap_shard_hot_set (same keys on every rank)
+//   keeps the <= 2048 most frequent  ->  olap_shard_hot_set (same keys on every rank)
 //   scatter + BARRIER + olap_shard_build (build side, as before)
 //   olap_shard_hot_resolve -> element-wise MAX of the 8192 x u64 table over the ranks -> olap_shard_hot_finalize
 //   probe scatters: rows carrying a hot key stay on their rank; pair {hot slot, local probe row} goes to hot_pairs, the slot's
@@ -515,17 +515,12 @@ olap_status olap_shard_hot_candidates(olap_shard* sh, const int64_t* probe_keys,
 
 olap_status olap_shard_hot_set(olap_shard* sh, const uint32_t* keys_plus1, uint32_t n_keys, void* stream) {
   OLAP_REQUIRE(sh && sh->planned && (n_keys == 0 || keys_plus1), "olap_shard_plan first");
-  OLAP_REQUIRE(n_keys <= hot_table_slots() / 2, "at most 4096 hot keys");
+  OLAP_REQUIRE(n_keys <= hot_max_keys(), "at most 2048 hot keys (a quarter of the table's slots)");
   // the table is built here, sequentially over the SORTED keys: every rank ends up with the same slot for the same key
   std::vector<uint32_t> keys(keys_plus1, keys_plus1 + n_keys), tab(hot_table_slots(), 0);
   std::sort(keys.begin(), keys.end());
   keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-  for (uint32_t k : keys) {
-    if (k == 0 || k == 0xFFFFFFFFu) continue;
-    uint32_t s = hot_slot_host(k - 1);
-    while (tab[s]) s = (s + 1) & (hot_table_slots() - 1);
-    tab[s] = k;
-  }
+  hot_table_build_host(keys.data(), (uint32_t)keys.size(), tab.data());
   olap_ctx* ctx = sh->ctx;
   std::lock_guard<std::mutex> g(ctx->mu);
   OLAP_CUDA(cudaSetDevice(ctx->device));
@@ -656,7 +651,7 @@ olap_status olap_sharded_hash_join_i64(olap_shard* const* shards, int32_t n_rank
     for (auto& kv : freq) byc.emplace_back(kv.second, kv.first);
     std::sort(byc.begin(), byc.end(), [](const std::pair<uint64_t, uint32_t>& a, const std::pair<uint64_t, uint32_t>& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
     std::vector<uint32_t> keys;
-    for (size_t i = 0; i < byc.size() && keys.size() < hot_table_slots() / 2; i++) keys.push_back(byc[i].second);
+    for (size_t i = 0; i < byc.size() && keys.size() < hot_max_keys(); i++) keys.push_back(byc[i].second);
     for (int r = 0; r < W; r++) OLAP_TRY(olap_shard_hot_set(shards[r], keys.data(), (uint32_t)keys.size(), comm[r]));
   }
   const int K = shards[0]->chunks;

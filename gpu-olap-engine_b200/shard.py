@@ -18,7 +18,8 @@ import numpy as np
 from . import _lib
 from .core import Context
 
-HOT_SLOTS = 8192      # open-addressing slots of the heavy-hitter table (csrc/djoin.cu kHotSlots): at most half of them hold a key
+HOT_SLOTS = 8192      # open-addressing slots of the heavy-hitter table (csrc/djoin.cu kHotSlots)
+HOT_MAX_KEYS = HOT_SLOTS // 4   # at most a quarter of them hold a key (kHotMaxKeys): short probe chains for the rows that are NOT hot
 FLAG_NAMES = ["region overflow (skewed keys)", "build key outside the planned range", "repeated build key", "-"]
 
 
@@ -177,7 +178,7 @@ class RangeShardedJoin:
 
     def _hot_keys(self, probe, npb, stream):
         """The agreed heavy-hitter set of this probe column: every rank samples its shard, the lists are all-gathered, the counts
-        summed per key and the <= 4096 most frequent kept (same result on every rank).  Remembered per (pointer, rows)."""
+        summed per key and the <= 2048 most frequent kept (same result on every rank).  Remembered per (pointer, rows)."""
         key = ("hot", probe.data_ptr(), npb)
         if key not in self._stats:
             torch, dist = self.torch, self.dist
@@ -198,7 +199,7 @@ class RangeShardedJoin:
                 m = int(allc[r, 0])
                 for k, c in zip(allc[r, 1:1 + m], allc[r, 1 + cap:1 + cap + m]):
                     freq[int(k)] = freq.get(int(k), 0) + int(c)
-            top = sorted(freq.items(), key=lambda kv: (-kv[1], kv[0]))[:HOT_SLOTS // 2]
+            top = sorted(freq.items(), key=lambda kv: (-kv[1], kv[0]))[:HOT_MAX_KEYS]
             self._stats[key] = np.array(sorted(k for k, _ in top), dtype=np.uint32)
         return self._stats[key]
 

@@ -696,6 +696,10 @@ def bench_sharded_join(ctx, args, rank, world, local_rank, peak, peak_kind, Cloc
                        "peak_nominal_gbs": 900.0, "peak_measured_gbs": 770.0,
                        "floor_ms_per_join_at_measured_peak": bytes_out / 770e9 * 1e3,
                        "note": "8 bytes leave the rank per row whose key another rank owns; inside the step the shuffle of chunk k+1 overlaps the local join of chunk k"},
+            "skew_note": (None if zipf <= 0 else
+                          "Zipf: the timed steps run WITH heavy-hitter handling (hot keys agreed across ranks and remembered per probe column, their build rows replicated, "
+                          "hot probe rows joined on their source rank inside the shuffle pass); the shuffle-alone / local-alone figures below are taken with it switched off "
+                          "(every row travels), so `hidden_ms` and the NVLink rate are not comparable with the step -- compare ms_per_step with the uniform run"),
             "overlap": {"shuffle_alone_ms": shuffle_ms, "local_alone_ms": local_ms, "step_ms": ms_step,
                         "hidden_ms": shuffle_ms + local_ms - ms_step,
                         "note": "shuffle = both sides scattered; local = second partition level + shared-memory join of all chunks; hidden = how much of their sum the step does not pay"},

@@ -152,6 +152,12 @@ OLAP_API olap_status olap_join_probe(olap_join_build* build, const int64_t* prob
                                      olap_pair* out_pairs, uint64_t max_matches, uint64_t* out_count_dptr, uint64_t* host_count,
                                      void* stream);
 OLAP_API olap_status olap_join_build_destroy(olap_join_build* build);
+/* Outer joins (JoinType::{Left, Right, Full}, gpu-olap-core/src/logical_plan.rs:52-58; the reference never executes them,
+ * README.md:410-411): the row ids of one side that appear in NO pair, in ascending row order.  side 0 = left / build rows,
+ * 1 = right / probe rows; n_rows = rows of that side; out_row_ids holds up to n_rows u32.  The operator layer appends these rows,
+ * NULL-extended, behind the inner pairs.  Asynchronous unless host_count is given.                                          */
+OLAP_API olap_status olap_join_unmatched_rows(olap_ctx* ctx, const olap_pair* pairs, uint64_t n_pairs, int32_t side, uint64_t n_rows,
+                                              uint32_t* out_row_ids, uint64_t* out_count_dptr, uint64_t* host_count, void* stream);
 /* JoinKernel::choose_strategy (join_kernel.rs:71-77) */
 OLAP_API int32_t olap_choose_join_strategy(uint64_t n_build);
 
@@ -240,7 +246,7 @@ OLAP_API olap_status olap_shard_finish(olap_shard* shard, uint64_t* host_count, 
                                        void* stream);
 /* Heavy hitters (Zipf-skewed probe keys), olap_shard_plan(hot = 1).  Order within a join:
  *   olap_shard_hot_candidates on every rank (samples its probe shard; keys as key - global_min + 1 in u32, with sample counts)
- *   -> the host language gathers the lists, sums the counts per key, keeps the <= 4096 most frequent -> olap_shard_hot_set
+ *   -> the host language gathers the lists, sums the counts per key, keeps the <= 2048 most frequent -> olap_shard_hot_set
  *   build side as before (scatter, BARRIER, olap_shard_build)
  *   olap_shard_hot_resolve (8192 x u64 on the device) -> element-wise MAX over the ranks -> olap_shard_hot_finalize
  *   probe scatters: a row carrying a hot key never leaves its rank; its pair {hot slot, local probe row} goes to hot_pairs and the
@@ -337,7 +343,9 @@ typedef struct olap_expr olap_expr;
 typedef struct olap_plan olap_plan;
 typedef struct olap_result olap_result;
 
-/* JoinType, gpu-olap-core/src/logical_plan.rs:52-58; only Inner executes (README.md:410-411) */
+/* JoinType, gpu-olap-core/src/logical_plan.rs:52-58.  The reference executes none of them (README.md:410-411 lists the outer
+ * ones as missing); here Left / Right / Full append the unmatched rows of the preserved side(s) behind the inner pairs, the other
+ * side's columns NULL there (Arrow validity bitmaps in the exported batch).                                                    */
 enum { OLAP_JOIN_INNER = 0, OLAP_JOIN_LEFT = 1, OLAP_JOIN_RIGHT = 2, OLAP_JOIN_FULL = 3 };
 
 /* PhysicalExpr::{Column{index,name}, Literal{value}, BinaryExpr{left,op,right}} (physical_plan.rs:66-75).  Columns
@@ -364,7 +372,9 @@ OLAP_API void olap_plan_free(olap_plan* p);
 
 /* Catalog::get_table_data analogue: import one RecordBatch (struct-typed ArrowArray) into device memory and append
  * it to table_name.  Numeric columns are widened to 8 bytes ON DEVICE, Utf8 becomes FNV-1a-64 as i64, nulls become 0
- * (arrow-interop/src/record_batch_convert.rs:35-130).  The array is released after the copy.                   */
+ * (arrow-interop/src/record_batch_convert.rs:35-130) and the column keeps a byte-per-row validity (:37-41) that scans carry and
+ * olap_result_export turns back into an Arrow bitmap; filters, projections, joins and aggregates read a null as 0 / 0.0 like the
+ * reference does (:103, :108).  The array is released in every case, also when the call fails.                              */
 OLAP_API olap_status olap_register_batch(olap_ctx* ctx, const char* table_name, struct ArrowArray* batch, struct ArrowSchema* schema);
 OLAP_API olap_status olap_drop_table(olap_ctx* ctx, const char* table_name);
 

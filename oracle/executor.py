@@ -1,7 +1,10 @@
 """CPU restatement of GpuExecutor::execute (gpu-olap-core/src/executor.rs:37-355) over numpy columns, built from the
 oracle's primitives.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Stubs are completed per SURVEY.md 8(c).
 
-A batch is (names, [np.ndarray int64|float64], n_rows); tables is {name: [pyarrow.RecordBatch]}."""
+A batch is (names, [np.ndarray int64|float64], n_rows, valids); valids[i] is None (no nulls) or a uint8 array, 1 = valid
+(column_buffer.rs:37-41; buffer_to_array puts the nulls back, record_batch_convert.rs:161-170).  Scans carry validity, outer joins
+produce it; filters, expressions, join keys and aggregates read a null as the 0 stored in its place (:103, :108) and emit
+non-null columns, as take_int64 / eval_expr do (executor.rs:496-507, :377-409).  tables is {name: [pyarrow.RecordBatch]}."""
 from __future__ import annotations
 
 import numpy as np
@@ -13,16 +16,21 @@ _CMP = {"=": O.EQ, "==": O.EQ, "!=": O.NE, "<>": O.NE, ">": O.GT, ">=": O.GE, "<
 
 def _widen_batch(rb):
     import pyarrow as pa
-    names, cols = [], []
+    names, cols, valids = [], [], []
     for f, c in zip(rb.schema, rb.columns):
         names.append(f.name)
+        valid = None if c.null_count == 0 else np.array([v is not None for v in c.to_pylist()], np.uint8)
+        valids.append(valid)
         if pa.types.is_string(f.type) or pa.types.is_large_string(f.type):   # record_batch_convert.rs:93-97, :112-121
             cols.append(np.array([0 if v is None else np.uint64(O.fnv1a64(v.encode())).astype(np.int64) for v in c.to_pylist()], np.int64))
         else:
-            valid = None if c.null_count == 0 else np.array([v is not None for v in c.to_pylist()], np.uint8)
             raw = np.asarray(c.fill_null(0)) if c.null_count else c.to_numpy(zero_copy_only=False)
             cols.append(O.widen_column(np.ascontiguousarray(raw), validity=valid))
-    return names, cols, rb.num_rows
+    return names, cols, rb.num_rows, valids
+
+
+def _valids(b):
+    return b[3] if len(b) > 3 and b[3] is not None else [None] * len(b[1])
 
 
 def expr_name(e):                                     # executor.rs:529-537
@@ -35,7 +43,7 @@ def expr_name(e):                                     # executor.rs:529-537
 
 
 def eval_expr(e, batch):                              # executor.rs:377-441
-    names, cols, n = batch
+    names, cols, n = batch[:3]
     k = type(e).__name__
     if k == "Column":
         if e.name in names:
@@ -82,11 +90,11 @@ def execute(plan, tables):
             fields = list(plan.schema)
             names = [f.name for f in fields]
             cols = [np.empty(0, np.float64 if pa.types.is_floating(f.type) else np.int64) for f in fields]
-            out = [(names, cols, 0)]
+            out = [(names, cols, 0, [None] * len(cols))]
         else:
             out = [_widen_batch(rb) for rb in rbs]
         if plan.projection is not None:
-            out = [([b[0][i] for i in plan.projection], [b[1][i] for i in plan.projection], b[2]) for b in out]
+            out = [([b[0][i] for i in plan.projection], [b[1][i] for i in plan.projection], b[2], [_valids(b)[i] for i in plan.projection]) for b in out]
         return out
     if k == "GpuFilter":
         out = []
@@ -96,7 +104,13 @@ def execute(plan, tables):
                 out.append((b[0], [O.take(c, idx) for c in b[1]], len(idx)))
         return out
     if k == "GpuProjection":
-        return [([expr_name(e) for e in plan.exprs], [eval_expr(e, b) for e in plan.exprs], b[2]) for b in execute(plan.input, tables)]
+        def passthrough(e, b):                        # a bare column keeps its validity
+            if type(e).__name__ != "Column":
+                return None
+            v = _valids(b)
+            return v[b[0].index(e.name)] if e.name in b[0] else (v[e.index] if e.index < len(v) else None)
+        return [([expr_name(e) for e in plan.exprs], [eval_expr(e, b) for e in plan.exprs], b[2], [passthrough(e, b) for e in plan.exprs])
+                for b in execute(plan.input, tables)]
     if k == "GpuHashJoin":
         left, right = execute(plan.left, tables), execute(plan.right, tables)
         if not left or not right:                     # executor.rs:231-233
@@ -107,8 +121,19 @@ def execute(plan, tables):
         names = left[0][0] + right[0][0]
         lcols = [np.concatenate([b[1][i] for b in left]) for i in range(len(left[0][0]))]
         rcols = [np.concatenate([b[1][i] for b in right]) for i in range(len(right[0][0]))]
-        cols = [c[pairs[:, 0]] for c in lcols] + [c[pairs[:, 1]] for c in rcols]
-        return [(names, cols, cnt)]
+        jt = int(getattr(plan, "join_type", 0))      # JoinType (logical_plan.rs:52-58): 0 Inner, 1 Left, 2 Right, 3 Full
+        # outer joins (never executed by the reference; SQL semantics): the preserved side's rows without a partner follow the inner
+        # pairs in row order -- unmatched left rows, then unmatched right rows -- with the other side NULL (value 0, validity 0)
+        ul = np.setdiff1d(np.arange(len(lk)), pairs[:, 0]) if jt in (1, 3) else np.empty(0, np.int64)
+        ur = np.setdiff1d(np.arange(len(rk)), pairs[:, 1]) if jt in (2, 3) else np.empty(0, np.int64)
+        cols, valids = [], []
+        for c in lcols:
+            cols.append(np.concatenate([c[pairs[:, 0]], c[ul], np.zeros(len(ur), c.dtype)]))
+            valids.append(np.concatenate([np.ones(cnt + len(ul), np.uint8), np.zeros(len(ur), np.uint8)]) if len(ur) else None)
+        for c in rcols:
+            cols.append(np.concatenate([c[pairs[:, 1]], np.zeros(len(ul), c.dtype), c[ur]]))
+            valids.append(np.concatenate([np.ones(cnt, np.uint8), np.zeros(len(ul), np.uint8), np.ones(len(ur), np.uint8)]) if len(ul) else None)
+        return [(names, cols, cnt + len(ul) + len(ur), valids)]
     if k == "GpuAggregate":
         inp = execute(plan.input, tables)
         names_of = {0: "SUM", 1: "COUNT", 2: "MIN", 3: "MAX", 4: "AVG"}

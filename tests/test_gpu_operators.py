@@ -34,15 +34,22 @@ def run_both(ex, plan, tables, sort_by=None, exact=True):
     got = ex.execute(plan)
     exp = OX.execute(plan, tables)
     assert len(got) == len(exp)
-    for g_rb, (names, cols, n) in zip(got, exp):
+    for g_rb, eb in zip(got, exp):
+        names, cols, n = eb[:3]
+        evalid = [np.ones(n, np.uint8) if v is None else v for v in (eb[3] if len(eb) > 3 else [None] * len(cols))]
         assert g_rb.num_rows == n and g_rb.schema.names == names
-        gcols = [g_rb.column(i).to_numpy(zero_copy_only=False) for i in range(g_rb.num_columns)]
+        # a NULL is exported as a cleared validity bit over the value 0 (record_batch_convert.rs:103, :108, :161-170)
+        gvalid = [np.asarray(g_rb.column(i).is_valid()).astype(np.uint8) for i in range(g_rb.num_columns)]
+        gcols = [g_rb.column(i).fill_null(0).to_numpy(zero_copy_only=False) for i in range(g_rb.num_columns)]
         if sort_by is not None and n:
             keys = [names.index(s) for s in sort_by]
-            go = np.lexsort([gcols[k] for k in reversed(keys)]); eo = np.lexsort([cols[k] for k in reversed(keys)])
+            go = np.lexsort([x for k in reversed(keys) for x in (gcols[k], gvalid[k])])
+            eo = np.lexsort([x for k in reversed(keys) for x in (cols[k], evalid[k])])
             gcols = [c[go] for c in gcols]; cols = [c[eo] for c in cols]
-        for name, gc, ec in zip(names, gcols, cols):
+            gvalid = [v[go] for v in gvalid]; evalid = [v[eo] for v in evalid]
+        for name, gc, ec, gv, ev in zip(names, gcols, cols, gvalid, evalid):
             assert gc.dtype == ec.dtype, name
+            assert (gv == ev).all(), f"{name}: validity"
             assert (gc == ec).all() if exact else np.allclose(gc, ec, rtol=1e-12, atol=0), name
     return got
 
@@ -145,13 +152,69 @@ def test_hash_join_c1b_shape_materialised(ex):
     assert ex.execute(g.GpuHashJoin(g.GpuTableScan("customers"), empty, [col("id")], [col("cust")])) == []   # executor.rs:231-233
 
 
+@pytest.mark.parametrize("jt", ["Left", "Right", "Full"])
+def test_outer_joins_append_null_extended_rows(ex, jt):
+    # JoinType::{Left, Right, Full} (logical_plan.rs:52-58): unmatched rows of the preserved side(s), the other side NULL
+    import gpu_olap_engine_b200 as g
+    nb, npb = 5000, 40000
+    left = pa.table({"id": O.gen_perm_i64(nb, 2, 3 * nb), "w": O.gen_dyadic_f64(nb, 9, 1 << 10)})            # a third of the key domain
+    right = pa.table({"cust": O.gen_uniform_i64(npb, 22, 4 * nb), "amount": O.gen_uniform_i64(npb, 23, 10000)})  # some keys match nothing
+    tables = {"customers": left.to_batches(max_chunksize=2000), "orders": right.to_batches(max_chunksize=15000)}
+    plan = g.GpuHashJoin(g.GpuTableScan("customers"), g.GpuTableScan("orders"), [col("id")], [col("cust")], getattr(g.JoinType, jt))
+    got = run_both(ex, plan, tables, sort_by=["cust", "amount", "id", "w"])
+    rb = got[0]
+    lk, rk = left["id"].to_numpy(), right["cust"].to_numpy()
+    inner = int(np.isin(rk, lk).sum())                      # unique build keys: one pair per matching probe row
+    ul = int((~np.isin(lk, rk)).sum()) if jt in ("Left", "Full") else 0
+    ur = int((~np.isin(rk, lk)).sum()) if jt in ("Right", "Full") else 0
+    assert ul + ur > 0 and rb.num_rows == inner + ul + ur
+    assert rb.column("cust").null_count == ul and rb.column("amount").null_count == ul
+    assert rb.column("id").null_count == ur and rb.column("w").null_count == ur
+    # the unmatched rows come behind the inner pairs, in row order
+    if ul:
+        tail = rb.column("id").to_numpy(zero_copy_only=False)[inner:inner + ul].astype(np.int64)
+        assert (tail == lk[~np.isin(lk, rk)]).all()
+    if ur:
+        tail = rb.column("cust").to_numpy(zero_copy_only=False)[inner + ul:].astype(np.int64)
+        assert (tail == rk[~np.isin(rk, lk)]).all()
+
+
+def test_outer_joins_edge_cases(ex):
+    import gpu_olap_engine_b200 as g
+    # duplicates on both sides, nothing matches at all, everything matches
+    l = pa.table({"a": np.array([1, 1, 2, 3, 7], np.int64), "x": np.arange(5, dtype=np.int64)})
+    r = pa.table({"b": np.array([1, 2, 2, 9], np.int64), "y": np.arange(4, dtype=np.float64)})
+    for jt in (g.JoinType.Inner, g.JoinType.Left, g.JoinType.Right, g.JoinType.Full):
+        plan = g.GpuHashJoin(g.GpuTableScan("l"), g.GpuTableScan("r"), [col("a")], [col("b")], jt)
+        got = run_both(ex, plan, {"l": l.to_batches(), "r": r.to_batches()}, sort_by=["a", "x", "b", "y"])
+        assert got[0].num_rows == {0: 4, 1: 6, 2: 5, 3: 7}[int(jt)]
+    disjoint = pa.table({"b": np.array([100, 200], np.int64), "y": np.array([0.5, 1.5])})
+    full = run_both(ex, g.GpuHashJoin(g.GpuTableScan("l"), g.GpuTableScan("r"), [col("a")], [col("b")], g.JoinType.Full),
+                    {"l": l.to_batches(), "r": disjoint.to_batches()}, sort_by=["a", "x", "b", "y"])
+    assert full[0].num_rows == 7 and full[0].column("a").null_count == 2 and full[0].column("y").null_count == 5
+    same = run_both(ex, g.GpuHashJoin(g.GpuTableScan("l"), g.GpuTableScan("l"), [col("a")], [col("a")], g.JoinType.Full),
+                    {"l": l.to_batches()}, sort_by=["a", "x"])
+    assert same[0].num_rows == 7 and all(same[0].column(i).null_count == 0 for i in range(4))
+    # the kernel seam under it: rows of a side that appear in no pair, ascending
+    pairs = ex.ctx.upload_raw(np.array([[0, 3], [2, 3], [2, 0]], np.uint32).reshape(-1))
+    assert ex.ctx.join_unmatched_rows(pairs, 3, 0, 5).tolist() == [1, 3, 4] and ex.ctx.join_unmatched_rows(pairs, 3, 1, 4).tolist() == [1, 2]
+    assert ex.ctx.join_unmatched_rows(None, 0, 1, 3).tolist() == [0, 1, 2] and ex.ctx.join_unmatched_rows(pairs, 3, 0, 0).tolist() == []
+
+
 def test_arrow_import_layout_rules(ex):
     # record_batch_convert.rs:35-130: widening, u64 reinterpretation, nulls -> 0, Utf8 -> FNV-1a
     import gpu_olap_engine_b200 as g
     rb = pa.record_batch({"i8": pa.array([1, None, -3], pa.int8()), "u64": pa.array([2**64 - 1, 5, None], pa.uint64()),
                           "f32": pa.array([1.5, None, -2.25], pa.float32()), "s": pa.array(["a", None, "foobar"])})
     got = run_both(ex, g.GpuTableScan("mixed"), {"mixed": [rb]})
-    assert got[0].column("i8").to_pylist() == [1, 0, -3] and got[0].column("u64").to_pylist() == [-1, 5, 0]
+    # nulls: the value slot holds 0 (:103, :108), the validity byte brings the NULL back on the way out (buffer_to_array, :161-170)
+    assert got[0].column("i8").to_pylist() == [1, None, -3] and got[0].column("u64").to_pylist() == [-1, 5, None]
+    assert got[0].column("i8").fill_null(0).to_pylist() == [1, 0, -3] and got[0].column("f32").to_pylist() == [1.5, None, -2.25]
+    # ... and every operator downstream reads the 0: filters / expressions emit non-null columns (take_int64, executor.rs:496-507)
+    kept = run_both(ex, g.GpuFilter(g.GpuTableScan("mixed"), g.BinaryExpr(col("i8"), ">=", lit(0))), {"mixed": [rb]})
+    assert kept[0].column("i8").to_pylist() == [1, 0] and kept[0].column("i8").null_count == 0
+    proj = run_both(ex, g.GpuProjection(g.GpuTableScan("mixed"), [col("u64"), g.BinaryExpr(col("i8"), "+", lit(1))]), {"mixed": [rb]})
+    assert proj[0].column(0).to_pylist() == [-1, 5, None] and proj[0].column(1).to_pylist() == [2, 1, -2]
     assert got[0].column("s").to_pylist()[2] == np.uint64(0x85944171f73967e8).astype(np.int64)
     sl = pa.record_batch({"a": pa.array(range(100), pa.int16())}).slice(10, 50)     # non-zero Arrow offset
     run_both(ex, g.GpuTableScan("sliced"), {"sliced": [sl]})
@@ -164,8 +227,6 @@ def test_operator_errors(ex):
         ex.execute(g.GpuProjection(g.GpuTableScan("sales"), [g.Column(99, "nope")]))
     with pytest.raises(g.OlapError, match="Cannot parse literal"):
         ex.execute(g.GpuProjection(g.GpuTableScan("sales"), [lit("abc")]))
-    with pytest.raises(g.OlapError, match="INNER"):
-        ex.execute(g.GpuHashJoin(g.GpuTableScan("sales"), g.GpuTableScan("sales"), [col("k")], [col("k")], g.JoinType.Left))
     with pytest.raises(g.OlapError, match="not registered"):
         ex.execute(g.GpuTableScan("missing"))
 
