@@ -340,6 +340,44 @@ def bench_single(ctx, g, args, local_rank, peak, peak_kind):
     verify_pairs(torch, dbuild, dprobe, pairs, nb, npb, cnt)
 
 
+    # ---- BASELINE config 2 names "int64 keys + int64 payload": the same join followed by the materialisation of both sides' payload
+    # columns in pair order (what execute_hash_join's output RecordBatch holds, executor.rs:255-264) -- late materialisation, random
+    # 8-byte gathers by the row-id pairs
+    payload = None
+    if not args.skip_payload:
+        pb, pp = ctx.generate(nb, 0, 91, 1 << 40), ctx.generate(npb, 0, 92, 1 << 40)
+        ob, op_ = ctx.alloc(npb, np.int64), ctx.alloc(npb, np.int64)
+
+        def pstep():
+            c, _ = ctx.hash_join_i64(dbuild, nb, dprobe, npb, max_matches=npb, strategy=g.JOIN_RADIX, out_pairs=pairs)
+            g._lib.check(ctx.lib.olap_join_gather_8b(ctx.handle, pb.ptr, pairs.ptr, 0, c, ob.ptr, None))
+            g._lib.check(ctx.lib.olap_join_gather_8b(ctx.handle, pp.ptr, pairs.ptr, 1, c, op_.ptr, None))
+            return c
+        for _ in range(2):
+            pc = pstep()
+        psteps = max(2, args.steps // 2)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record(stream)
+        for _ in range(psteps):
+            pc = pstep()
+        e1.record(stream); torch.cuda.synchronize()
+        pms = e0.elapsed_time(e1) / psteps
+        # every gathered value checked on the device: out_build[i] == payload_build[left_i], out_probe[i] == payload_probe[right_i]
+        pr = dev_view(torch, pairs, 2 * pc, "<u4").view(torch.int32).view(-1, 2)
+        pbv, ppv, obv, opv = dev_view(torch, pb, nb), dev_view(torch, pp, npb), dev_view(torch, ob, npb), dev_view(torch, op_, npb)
+        for a in range(0, pc, 1 << 26):
+            l = pr[a:a + (1 << 26), 0].to(torch.int64) & 0xFFFFFFFF
+            r = pr[a:a + (1 << 26), 1].to(torch.int64) & 0xFFFFFFFF
+            assert bool((obv[a:a + (1 << 26)] == pbv[l]).all()) and bool((opv[a:a + (1 << 26)] == ppv[r]).all()), "payload materialisation check failed"
+        in_bytes, pair_bytes, out_bytes = 16.0 * rows, 8.0 * pc, 16.0 * pc
+        payload = {"value": rows / (pms * 1e-3), "unit": "rows/s", "ms_per_step": pms, "steps": psteps, "join_ms": ms_step, "materialise_ms": pms - ms_step,
+                   "workload": "the same join + both int64 payload columns gathered into pair order (2 x 2^%d values, every one verified)" % args.log2_probe,
+                   "job_roofline_survey": {"algorithmic_bytes": in_bytes + pair_bytes, "frac": (in_bytes + pair_bytes) / (pms * 1e-3) / 1e9 / peak,
+                                           "note": "SURVEY 8(d) C2: 16 B x rows in (keys + payloads) + 8 B x pairs out = 15.03 GB"},
+                   "job_roofline_materialised": {"algorithmic_bytes": in_bytes + pair_bytes + out_bytes, "frac": (in_bytes + pair_bytes + out_bytes) / (pms * 1e-3) / 1e9 / peak,
+                                                 "note": "... + the two materialised payload columns (16 B x pairs)"}}
+        del pb, pp, ob, op_
+
     # ---- the general path: sparse build keys (2^27 unique keys of a 2^33 domain) take hash partitions + bucket tables
     general = None
     if not args.skip_general:
@@ -360,7 +398,7 @@ def bench_single(ctx, g, args, local_rank, peak, peak_kind):
         group_by = None if args.skip_groupby else bench_group_by(ctx, g, args, torch, stream, peak, peak_kind)
         clocks = sampler.stop()
         print(json.dumps({"profiling_run": True, "value": value, "ms_per_step": ms_step, "phases_ms": phases, "gpu_launches": int(launches),
-                          "value_general": general, "group_by": group_by, "clocks": clocks}))
+                          "value_with_payload": payload, "value_general": general, "group_by": group_by, "clocks": clocks}))
         return 0
 
     # ---- e2e: host (pinned) buffers through the C-ABI, copies inside the timed region
@@ -469,6 +507,7 @@ def bench_single(ctx, g, args, local_rank, peak, peak_kind):
                          "frac": job_bytes / (ms_step * 1e-3) / 1e9 / peak,
                          "note": "keys read once + pairs written once; SURVEY 8(d)'s 15.03 GB also counts payload columns the join never touches"},
         "phases_ms": phases,
+        "value_with_payload": payload,
         "value_general": general,
         "group_by": group_by,
         "cpu_baseline": {"value": cpu_rps, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
@@ -510,6 +549,7 @@ def main():
     ap.add_argument("--cpu-log2-gb-rows", type=int, default=26)
     ap.add_argument("--skip-groupby", action="store_true")
     ap.add_argument("--skip-general", action="store_true")
+    ap.add_argument("--skip-payload", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: omit the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: omit the CPU baseline leg")
     args = ap.parse_args()

@@ -66,6 +66,7 @@ SIGNATURES = {
     "olap_join_build_create": (i32, [vp, vp, u64, i32, vp, pvp]),
     "olap_join_probe": (i32, [vp, vp, u64, u32, vp, u64, vp, pu64, vp]),
     "olap_join_build_destroy": (i32, [vp]),
+    "olap_join_gather_8b": (i32, [vp, vp, vp, i32, u64, vp, vp]),
     "olap_join_unmatched_rows": (i32, [vp, vp, u64, i32, u64, vp, vp, pu64, vp]),
     "olap_choose_join_strategy": (i32, [u64]),
     "olap_radix_partition_i64": (i32, [vp, vp, vp, u64, i32, vp, vp, vp, vp]),
@@ -101,6 +102,7 @@ SIGNATURES = {
     "olap_shard_hot_table": (i32, [vp, pu64, vp]),
     "olap_group_by_i64": (i32, [vp, vp, C.POINTER(AggSpec), i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_group_by_prog_i64": (i32, [vp, vp, C.POINTER(AggSpec), vp, i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
+    "olap_sharded_group_by_i64": (i32, [pvp, i32, pvp, pvp, i32, pu64, u64, pvp, pvp, pu64, pu64]),
     "olap_agg_identity": (i64, [i32]),
     "olap_compute_launch_params": (None, [u64, C.POINTER(u32), C.POINTER(u32)]),
     "olap_expr_column": (vp, [u64, C.c_char_p]),

@@ -60,9 +60,22 @@ __global__ void __launch_bounds__(256) fill_kernel(uint64_t* out, uint64_t n, ui
   for (; i < n; i += st) out[i] = v;
 }
 // out[i] = col[pairs[2 * i + side]]: materialises one join output column from the row-id pairs
+// Four pairs per thread and iteration: the four row ids are loaded first, then the four gathers are in flight together (one
+// dependent load chain per value left the DRAM latency of every gather exposed).
 __global__ void __launch_bounds__(256) gather_pairs_kernel(const uint64_t* __restrict__ col, const uint32_t* __restrict__ pairs, int side,
                                                            uint64_t n, uint64_t* __restrict__ out) {
-  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, st = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t st = (uint64_t)gridDim.x * blockDim.x;
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  for (; i + 3 * st < n; i += 4 * st) {
+    uint32_t id[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) id[k] = ld_stream_u32(pairs + 2 * (i + k * st) + side);
+    uint64_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = __ldg(col + id[k]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[i + k * st] = v[k];
+  }
   for (; i < n; i += st) out[i] = __ldg(col + ld_stream_u32(pairs + 2 * i + side));
 }
 // flags[pairs[i].side] = 1: the rows of one join side that found a partner (8-byte flags: the ordered selection pass reads them
@@ -759,6 +772,19 @@ olap_plan* olap_plan_aggregate(olap_plan* input, olap_expr* const* group_by, int
   return p;
 }
 void olap_plan_free(olap_plan* p) { delete p; }
+
+olap_status olap_join_gather_8b(olap_ctx* ctx, const void* col, const olap_pair* pairs, int32_t side, uint64_t n_pairs, void* out, void* stream) {
+  OLAP_REQUIRE(ctx && (side == 0 || side == 1), "ctx is NULL / side is 0 (left) or 1 (right)");
+  OLAP_REQUIRE(n_pairs == 0 || (col && pairs && out), "NULL pointer");
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  if (n_pairs == 0) return OLAP_OK;
+  const uint64_t blocks = (n_pairs + 1023) / 1024, cap = (uint64_t)ctx->sm_count * 16;
+  gather_pairs_kernel<<<(unsigned)std::min<uint64_t>(blocks, cap), 256, 0, ctx->stream_of(stream)>>>((const uint64_t*)col, (const uint32_t*)pairs, side, n_pairs,
+                                                                                                     (uint64_t*)out);
+  count_launch(ctx);
+  OLAP_CUDA(cudaGetLastError());
+  return OLAP_OK;
+}
 
 // Rows of one join side that appear in no pair, ascending: mark the partners, then the ordered selection pass of the filter
 // (filter.cu) over the flags.  Composed of public calls, so no context lock is held here.

@@ -71,6 +71,30 @@ class ShardGroup:
             return [int(c) for c in counts], [int(c) for c in hot_counts]
         return [int(c) for c in counts]
 
+    def group_by(self, keys, n_rows, aggs, n_groups_hint: int, out_capacity=None):
+        """GROUP BY over all ranks' rows (olap_sharded_group_by_i64): keys[r] = rank r's key column, aggs[r] = [(func, values, value_type)]
+        with the same functions / types on every rank.  Returns per rank (n_groups, keys ndarray, [typed ndarray per aggregate]) -- rank r
+        holds the groups whose key it owns (olap_shuffle_dest_of); the union over the ranks is the result."""
+        from .core import typed_agg_results
+        n = self.n
+        na = len(aggs[0])
+        caps = [int(c) for c in (out_capacity if out_capacity is not None else [max(int(n_groups_hint), 1)] * n)]
+        spec_arrays = [(_lib.AggSpec * na)(*[_lib.AggSpec(v.ptr if v is not None else None, int(f), int(t)) for f, v, t in aggs[r]]) for r in range(n)]
+        ok = [self.ctxs[r].alloc(max(caps[r], 1), np.int64) for r in range(n)]
+        oa = [self.ctxs[r].alloc(na * max(caps[r], 1), np.uint64) for r in range(n)]
+        ctxs = (C.c_void_p * n)(*[c.handle for c in self.ctxs])
+        kp = (C.c_void_p * n)(*[k.ptr if k is not None else None for k in keys])
+        sp = (C.c_void_p * n)(*[C.addressof(a) for a in spec_arrays])
+        okp = (C.c_void_p * n)(*[b.ptr for b in ok]); oap = (C.c_void_p * n)(*[b.ptr for b in oa])
+        g = (C.c_uint64 * n)()
+        _lib.check(self.lib.olap_sharded_group_by_i64(ctxs, n, kp, sp, na, (C.c_uint64 * n)(*[int(x) for x in n_rows]), int(n_groups_hint), okp, oap,
+                                                      (C.c_uint64 * n)(*caps), g))
+        out = []
+        for r in range(n):
+            ng = int(g[r])
+            out.append((ng, ok[r].to_numpy(ng), typed_agg_results(oa[r].to_numpy(), max(caps[r], 1), ng, aggs[r])))
+        return out
+
     def hot_pairs_to_global(self, r, hot_pairs, n_pairs, build_row_offsets, probe_row_offsets):
         """Global (left, right) row ids of rank r's heavy-hitter pairs (numpy uint64)."""
         tab = (C.c_uint64 * HOT_SLOTS)()

@@ -152,6 +152,11 @@ OLAP_API olap_status olap_join_probe(olap_join_build* build, const int64_t* prob
                                      olap_pair* out_pairs, uint64_t max_matches, uint64_t* out_count_dptr, uint64_t* host_count,
                                      void* stream);
 OLAP_API olap_status olap_join_build_destroy(olap_join_build* build);
+/* Join output materialisation (the RecordBatch execute_hash_join promises and never builds, executor.rs:255-264): out[i] =
+ * col[pairs[i].left_row] (side 0) or col[pairs[i].right_row] (side 1) for any 8-byte column -- the payload columns of both sides in
+ * pair order.  Random 8-byte gathers: a 32-byte DRAM sector per value once the column is larger than the L2.                  */
+OLAP_API olap_status olap_join_gather_8b(olap_ctx* ctx, const void* col, const olap_pair* pairs, int32_t side, uint64_t n_pairs, void* out,
+                                         void* stream);
 /* Outer joins (JoinType::{Left, Right, Full}, gpu-olap-core/src/logical_plan.rs:52-58; the reference never executes them,
  * README.md:410-411): the row ids of one side that appear in NO pair, in ascending row order.  side 0 = left / build rows,
  * 1 = right / probe rows; n_rows = rows of that side; out_row_ids holds up to n_rows u32.  The operator layer appends these rows,
@@ -316,6 +321,20 @@ OLAP_API olap_status olap_group_by_prog_i64(olap_ctx* ctx, const int64_t* keys, 
 OLAP_API int64_t olap_agg_identity(int32_t func);
 /* compute_launch_params (filter_kernel.rs:75-79, aggregate_kernel.rs:127-131), without the u32 truncation bug */
 OLAP_API void olap_compute_launch_params(uint64_t n_rows, uint32_t* grid, uint32_t* block);
+
+/* GROUP BY across the GPUs of one box, one process driving all ranks (SURVEY.md 8(b) "multi-GPU", 8(e); no reference analogue,
+ * README.md:414).  ctxs[r] is rank r's context (olap_ctx_create / olap_shard_ctx_create_all; the devices may repeat), keys[r] /
+ * specs[r][n_aggs] / n_rows[r] its rows -- every rank passes the same aggregates (function, value type), each over its own column.
+ * Local pre-aggregation into partials (AVG travels as sum + count, aggregate_kernel.rs:22-23; every COUNT / AVG shares one row
+ * count), the partial rows go to the rank that owns their key (olap_shuffle_dest_of(key, log2 n_ranks)) with one peer copy per
+ * (source, owner, column), the owner merges and finalises.  Rank r's out_keys[r] / out_aggs[r] (agg-major, stride out_capacity[r],
+ * typed like olap_group_by_i64's) receive the host_n_groups[r] groups it owns; the union over the ranks is the result.  n_ranks is
+ * 1, 2, 4 or 8.  OLAP_ERR_CAPACITY when some rank owns more groups than its out_capacity (host_n_groups is exact for every rank).
+ * Synchronous: the results are complete on return.                                                                          */
+OLAP_API olap_status olap_sharded_group_by_i64(olap_ctx* const* ctxs, int32_t n_ranks, const int64_t* const* keys,
+                                               const olap_agg_spec* const* specs, int32_t n_aggs, const uint64_t* n_rows,
+                                               uint64_t n_groups_hint, int64_t* const* out_keys, void* const* out_aggs,
+                                               const uint64_t* out_capacity, uint64_t* host_n_groups);
 
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -199,6 +199,15 @@ def test_outer_joins_edge_cases(ex):
     pairs = ex.ctx.upload_raw(np.array([[0, 3], [2, 3], [2, 0]], np.uint32).reshape(-1))
     assert ex.ctx.join_unmatched_rows(pairs, 3, 0, 5).tolist() == [1, 3, 4] and ex.ctx.join_unmatched_rows(pairs, 3, 1, 4).tolist() == [1, 2]
     assert ex.ctx.join_unmatched_rows(None, 0, 1, 3).tolist() == [0, 1, 2] and ex.ctx.join_unmatched_rows(pairs, 3, 0, 0).tolist() == []
+    # ... and the materialisation of a payload column in pair order (olap_join_gather_8b), both sides, odd sizes
+    rng = np.random.default_rng(3)
+    for n_pairs in (3, 1000, 262_147):
+        pr = rng.integers(0, 5000, (n_pairs, 2)).astype(np.uint32)
+        colv = rng.integers(-2**62, 2**62, 5000).astype(np.int64)
+        dpairs, dcol, dout = ex.ctx.upload_raw(pr.reshape(-1)), ex.ctx.upload_raw(colv), ex.ctx.alloc(n_pairs, np.int64)
+        for side in (0, 1):
+            g._lib.check(ex.ctx.lib.olap_join_gather_8b(ex.ctx.handle, dcol.ptr, dpairs.ptr, side, n_pairs, dout.ptr, None))
+            assert (dout.to_numpy() == colv[pr[:, side]]).all()
 
 
 def test_arrow_import_layout_rules(ex):

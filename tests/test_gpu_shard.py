@@ -114,3 +114,60 @@ def test_range_sharded_join_zipf_heavy_hitters_stay_on_their_rank(world, s):
             l, rt = grp.hot_pairs_to_global(r, hot[r], hot_counts[r], boff, poff); got.append(np.stack([l, rt], 1))
         got = np.concatenate(got).astype(np.uint32)
         assert (O.sort_pairs(got) == O.sort_pairs(exp_pairs)).all()
+
+
+# ------------------------------------------------------------------------------------------------- sharded GROUP BY (C ABI)
+def _sharded_group_by(world, key_shards, vi_shards, vf_shards, funcs, hint, out_capacity=None):
+    import gpu_olap_engine_b200 as g
+    from gpu_olap_engine_b200.shard import ShardGroup
+    with ShardGroup([0] * world, 1024, 1024, 1) as grp:
+        dk = [grp.ctxs[r].upload_raw(key_shards[r]) if len(key_shards[r]) else None for r in range(world)]
+        di = [grp.ctxs[r].upload_raw(vi_shards[r]) if len(vi_shards[r]) else None for r in range(world)]
+        df = [grp.ctxs[r].upload_raw(vf_shards[r]) if len(vf_shards[r]) else None for r in range(world)]
+        aggs = [[(f, (df[r] if t == g.F64 else di[r]), t) for f, t in funcs] for r in range(world)]
+        return grp.group_by(dk, [len(k) for k in key_shards], aggs, hint, out_capacity)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world,G", [(1, 300), (2, 1000), (4, 50_000), (8, 7)])
+def test_sharded_group_by_in_process(world, G):
+    # olap_sharded_group_by_i64: local partials -> owner rank by key hash -> merge; == the oracle's group-by over all rows
+    import gpu_olap_engine_b200 as g
+    rng = np.random.default_rng(world * 1000 + G)
+    sizes = [int(x) for x in rng.integers(50_000, 400_000, world)]
+    if world >= 4:
+        sizes[1] = 0                                                        # a rank without rows
+    keys = [rng.integers(-G // 2, G - G // 2, n).astype(np.int64) for n in sizes]
+    vi = [rng.integers(-(1 << 20), 1 << 20, n).astype(np.int64) for n in sizes]
+    vf = [(rng.integers(0, 1 << 20, n) / 1024.0).astype(np.float64) for n in sizes]     # dyadic: sums are order-independent
+    funcs = [(g.SUM, g.I64), (g.COUNT, g.I64), (g.MIN, g.I64), (g.MAX, g.F64), (g.AVG, g.I64), (g.AVG, g.F64), (g.SUM, g.F64), (g.COUNT, g.F64)]
+    res = _sharded_group_by(world, keys, vi, vf, funcs, G)
+    ak, ai, af = np.concatenate(keys), np.concatenate(vi), np.concatenate(vf)
+    ek, er = O.group_by_i64(ak, [af if t == g.F64 else ai for _, t in funcs], [f for f, _ in funcs])
+    lib = g.load()
+    bits = world.bit_length() - 1
+    got_k = np.concatenate([r[1] for r in res])
+    assert len(got_k) == len(ek) and len(np.unique(got_k)) == len(got_k)                 # every group on exactly one rank
+    for r, (ng, k, cols) in enumerate(res):
+        assert all(lib.olap_shuffle_dest_of(int(x), bits) == r for x in k[:200])          # ... the rank that owns its key
+    order = np.argsort(got_k)
+    assert (got_k[order] == ek).all()
+    for i, (f, t) in enumerate(funcs):
+        got = np.concatenate([r[2][i] for r in res])[order]
+        if f == g.AVG:
+            assert np.allclose(got, er[i], rtol=1e-12, atol=0), i
+        else:
+            assert got.dtype == er[i].dtype and (got == er[i]).all(), i
+
+
+def test_sharded_group_by_capacity_and_errors():
+    import gpu_olap_engine_b200 as g
+    rng = np.random.default_rng(5)
+    keys = [rng.integers(0, 5000, 100_000).astype(np.int64) for _ in range(2)]
+    vi = [rng.integers(0, 100, 100_000).astype(np.int64) for _ in range(2)]
+    with pytest.raises(g.OlapError) as ei:                                   # 5000 groups over 2 ranks do not fit 100 slots each
+        _sharded_group_by(2, keys, vi, vi, [(g.SUM, g.I64)], 5000, out_capacity=[100, 100])
+    assert ei.value.status == 6
+    with pytest.raises(g.OlapError) as ei:
+        _sharded_group_by(1, keys[:1], vi[:1], vi[:1], [(g.SUM, g.I64)] * 16, 5000)
+    assert ei.value.status == 1
