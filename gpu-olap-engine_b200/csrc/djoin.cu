@@ -135,12 +135,15 @@ __device__ __forceinline__ uint32_t hot_stage_base(uint32_t* counter, uint32_t n
   return wbase + incl - nhot;
 }
 
-template <int INPUT, bool HOT, bool PEER = false>
-__global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) rpart_kernel(const __grid_constant__ RPartArgs a) {
+// ROWS: rows per thread and tile.  16 (4096-row tiles) is the shape every variant has; 8 halves the registers held across the tile's
+// barriers -- more CTAs per SM to fill the gaps between the phases -- and is instantiated for the plain variants (see launch_rpart).
+template <int INPUT, bool HOT, bool PEER = false, int ROWS = kRRows>
+__global__ void __launch_bounds__(kRThreads, ROWS == 8 ? (INPUT == kInRaw ? 6 : 5) : ((INPUT == kInRaw && !HOT) ? 4 : 3)) rpart_kernel(const __grid_constant__ RPartArgs a) {
+  constexpr int kTile = kRThreads * ROWS;
   static_assert(!PEER || INPUT == kInRaw, "the shuffle reads raw keys");
   __shared__ uint64_t* s_optr[PEER ? kRThreads : 1];                   // PEER: where staged row i of partition j goes = s_optr[j] + i
-  constexpr int R = kRRows, NW = kRThreads / 32;
-  __shared__ __align__(16) uint64_t stage[kRTile];                    // rows in partition order (32 KB)
+  constexpr int R = ROWS, NW = kRThreads / 32;
+  __shared__ __align__(16) uint64_t stage[kTile];                    // rows in partition order (32 KB)
   __shared__ uint32_t cnt[kRThreads];                                 // tile histogram, then exclusive offsets
   __shared__ uint32_t gbase[kRThreads];                               // global position of staged row i = gbase[part] + i
   extern __shared__ __align__(16) uint32_t hotk[];                    // HOT: the hot keys (32 KB, dynamic); their build rows are read through L1
@@ -156,18 +159,18 @@ __global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) 
   if (tid == 0) { s_over[0] = s_over[1] = 0; s_hot[0] = s_hot[1] = 0; }
   __syncthreads();
 
-  const uint32_t tiles_per_reg = INPUT == kInRaw ? 1u : (a.reg_cap + kRTile - 1) / kRTile;
-  const uint32_t tiles = INPUT == kInRaw ? (uint32_t)((a.n + kRTile - 1) / kRTile) : tiles_per_reg * a.n_reg;
+  const uint32_t tiles_per_reg = INPUT == kInRaw ? 1u : (a.reg_cap + kTile - 1) / kTile;
+  const uint32_t tiles = INPUT == kInRaw ? (uint32_t)((a.n + kTile - 1) / kTile) : tiles_per_reg * a.n_reg;
   int par = 1;
   for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const uint64_t* src = a.in;
-    uint64_t n = a.n, row0 = (uint64_t)t * kRTile;
+    uint64_t n = a.n, row0 = (uint64_t)t * kTile;
     uint32_t pbase = 0, idb = a.id_base;
     if (INPUT != kInRaw) {
       const uint32_t g = t / tiles_per_reg;
       src = a.in + (uint64_t)g * a.reg_cap;
       n = min(a.reg_cur[g], a.reg_cap);
-      row0 = (uint64_t)(t - g * tiles_per_reg) * kRTile;
+      row0 = (uint64_t)(t - g * tiles_per_reg) * kTile;
       pbase = (g % a.reg_q) * a.reg_parts;
       idb = a.id_base + g * a.reg_cap;
       if (row0 >= n) continue;  // uniform over the CTA
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) 
       if (rk[k] == kREmpty) continue;
       const uint32_t id = INPUT == kInRegionsCarry ? (uint32_t)key[k] : idb + (uint32_t)(row0 + (uint64_t)k * kRThreads + tid);
       if (is_hot) {
-        stage[kRTile - 1 - hbase++] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (rk[k] & (kHotSlots - 1)));
+        stage[kTile - 1 - hbase++] = ((uint64_t)id << 32) | __ldg(a.hot_ids + (rk[k] & (kHotSlots - 1)));
       } else {
         stage[cnt[(PEER ? peer_part(a, d[k]) : d[k] >> a.shift) - pbase] + rk[k]] = ((uint64_t)d[k] << 32) | id;
       }
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(kRThreads, (INPUT == kInRaw && !HOT) ? 4 : 3) 
       if (nh) {
         const unsigned long long base = s_hotbase;
         for (uint32_t i = tid; i < nh; i += kRThreads) {
-          const uint64_t v = stage[kRTile - 1 - i];  // {probe row : hi, build row : lo}
+          const uint64_t v = stage[kTile - 1 - i];  // {probe row : hi, build row : lo}
           if (a.pairs && base + i < a.max_matches) a.pairs[base + i] = olap_pair{(uint32_t)v, (uint32_t)(v >> 32)};
         }
       }
@@ -488,27 +491,39 @@ static cudaError_t set_carveout(K kernel, bool shared) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, shared ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
 }
 
-template <int INPUT, bool HOT, bool PEER = false>
+template <int INPUT, bool HOT, bool PEER = false, int ROWS = kRRows>
 static olap_status launch_rpart_t(olap_ctx* ctx, const RPartArgs& a, unsigned grid, bool shared, cudaStream_t s) {
-  OLAP_CUDA(set_carveout(rpart_kernel<INPUT, HOT, PEER>, shared));
+  OLAP_CUDA((set_carveout(rpart_kernel<INPUT, HOT, PEER, ROWS>, shared)));
   const size_t dyn = HOT ? (size_t)kHotSlots * 4 : 0;
-  if (HOT) OLAP_CUDA((cudaFuncSetAttribute(rpart_kernel<INPUT, HOT, PEER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)));
-  rpart_kernel<INPUT, HOT, PEER><<<grid, kRThreads, dyn, s>>>(a);
+  if (HOT) OLAP_CUDA((cudaFuncSetAttribute(rpart_kernel<INPUT, HOT, PEER, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)));
+  rpart_kernel<INPUT, HOT, PEER, ROWS><<<grid, kRThreads, dyn, s>>>(a);
   count_launch(ctx);
   return OLAP_OK;
 }
 
 // grid_limit: CTAs to use at most (0 = fill the GPU); the multi-GPU path runs this next to a shuffle kernel
 static olap_status launch_rpart(olap_ctx* ctx, const RPartArgs& a, int input, unsigned grid_limit, cudaStream_t s) {
-  const uint64_t tiles = input == kInRaw ? (a.n + kRTile - 1) / kRTile : (uint64_t)((a.reg_cap + kRTile - 1) / kRTile) * a.n_reg;
-  if (!tiles) return OLAP_OK;
   const bool hot = a.hot_keys != nullptr, peer = a.peer_out[0] != nullptr, shared = grid_limit != 0;
+  // tile shape: 8 rows per thread for the plain variants when OLAP_RPART_ROWS=8.  A/B knob kept for the record: unlike the group-by's
+  // two-column partition pass (groupby.cu, where 5 CTAs per SM gain a fifth), these one-column passes do not profit -- C2 on a B200:
+  // coarse probe pass 1.65 ms at 16 rows (4 CTAs per SM, 64 registers) vs 1.80 ms at 8 rows (6 CTAs, 40 registers), second level
+  // 1.78 vs 1.79 ms: twice the run reservations and 8-row runs cost what the extra occupancy buys.  16 is the default.
+  static const int rows_env = [] { const char* v = getenv("OLAP_RPART_ROWS"); return v && *v ? atoi(v) : 16; }();
+  const bool r8 = rows_env == 8 && !hot && !peer && !shared;
+  const uint64_t tile = (uint64_t)kRThreads * (r8 ? 8 : kRRows);
+  const uint64_t tiles = input == kInRaw ? (a.n + tile - 1) / tile : (uint64_t)((a.reg_cap + tile - 1) / tile) * a.n_reg;
+  if (!tiles) return OLAP_OK;
   // one wave of resident CTAs (the tile loop strides by the grid): 4 per SM for raw keys, 3 for the region passes and for the
   // heavy-hitter variant (__launch_bounds__ above) -- launched with 4 per SM, a quarter of its CTAs ran as a second wave at a third
   // of the occupancy
-  uint64_t grid = (uint64_t)ctx->sm_count * ((input == kInRaw && !hot) ? 4 : 3);
+  uint64_t grid = (uint64_t)ctx->sm_count * (r8 ? (input == kInRaw ? 6 : 5) : ((input == kInRaw && !hot) ? 4 : 3));
   if (grid_limit && grid > grid_limit) grid = grid_limit;
   if (grid > tiles) grid = tiles;
+  if (r8) {
+    if (input == kInRaw) return launch_rpart_t<kInRaw, false, false, 8>(ctx, a, (unsigned)grid, shared, s);
+    if (input == kInRegionsCarry) return launch_rpart_t<kInRegionsCarry, false, false, 8>(ctx, a, (unsigned)grid, shared, s);
+    return launch_rpart_t<kInRegionsPos, false, false, 8>(ctx, a, (unsigned)grid, shared, s);
+  }
   if (input == kInRaw && peer) return hot ? launch_rpart_t<kInRaw, true, true>(ctx, a, (unsigned)grid, shared, s) : launch_rpart_t<kInRaw, false, true>(ctx, a, (unsigned)grid, shared, s);
   if (input == kInRaw) return hot ? launch_rpart_t<kInRaw, true>(ctx, a, (unsigned)grid, shared, s) : launch_rpart_t<kInRaw, false>(ctx, a, (unsigned)grid, shared, s);
   if (input == kInRegionsCarry) return launch_rpart_t<kInRegionsCarry, false>(ctx, a, (unsigned)grid, shared, s);

@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_part_smem_kernel(GbParams p) {
 // 10^6 30 ms, 10^8 57 ms (per-partition L2 tables, L2-atomic bound).
 constexpr int kGrKeysLog2 = 12;
 constexpr uint32_t kGrKeys = 1u << kGrKeysLog2;
-constexpr int kGrThreads = 256, kGrRows = 16, kGrTile = kGrThreads * kGrRows;
+constexpr int kGrThreads = 256;   // rows per thread and tile (ROWS): 16 at 3 CTAs per SM, or 8 at 5 CTAs per SM -- see launch_gr_part
 enum { kGrFlagOverflow = 0, kGrFlagOutOfRange = 1, kGrFlagWords = 4 };
 
 struct GrPartArgs {
@@ -756,9 +756,9 @@ struct GrPartArgs {
   uint32_t* cursor; uint32_t* out_d; uint64_t* out_v; uint32_t* flags;
 };
 
-template <bool REGIONS>
-__global__ void __launch_bounds__(kGrThreads, 3) gr_part_kernel(const __grid_constant__ GrPartArgs a) {
-  constexpr int R = kGrRows, NW = kGrThreads / 32;
+template <bool REGIONS, int ROWS>
+__global__ void __launch_bounds__(kGrThreads, ROWS == 16 ? 3 : 5) gr_part_kernel(const __grid_constant__ GrPartArgs a) {
+  constexpr int R = ROWS, NW = kGrThreads / 32, kGrTile = kGrThreads * ROWS;
   extern __shared__ __align__(16) unsigned char gr_smem[];
   uint64_t* stage_v = reinterpret_cast<uint64_t*>(gr_smem);               // [kGrTile]
   uint32_t* stage_d = reinterpret_cast<uint32_t*>(stage_v + kGrTile);     // [kGrTile]
@@ -1169,28 +1169,48 @@ static olap_status run_dense_range(olap_ctx* ctx, const GbParams& p, int64_t rmi
   OLAP_TRY(sc.get<uint32_t>(ctl_words, &ctl));
   OLAP_CUDA(cudaMemsetAsync(ctl, 0, ctl_words * 4, s));
   uint32_t *cur2 = ctl, *cur1 = ctl + PP, *flags = ctl + ctl_words - kGrFlagWords - 4, *ticket = flags + kGrFlagWords;
-  const size_t smem = (size_t)kGrTile * 12;
-  OLAP_CUDA(cudaFuncSetAttribute(gr_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  OLAP_CUDA(cudaFuncSetAttribute(gr_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // Tile shape of the partition passes.  ncu on the 16-rows-per-thread kernel (profiles/r02_ncu_groupby_details.txt: 2^30 rows,
+  // G = 1e5) shows a latency-bound pass -- 3.6 TB/s, L1TEX 40 % busy, issue 27 %, 37 % of the warp slots occupied (80 registers: 3
+  // CTAs per SM) -- whose phases (load, rank, scan, stage, write-out) are separated by barriers, so only other CTAs fill the gaps.
+  // 8 rows per thread halve the registers held across the barriers (48: 5 CTAs per SM).  Measured on 2^30 rows (B200): a pass that
+  // fans out to few partitions gains a fifth (3 partitions 8.9 -> 7.1 ms, 25: 8.2 -> 6.7, 96: 8.5 -> 7.1); one that fans out to ~250
+  // loses (8.7 -> 9.3, second level 6.8 -> 9.2 ms) because a 2048-row tile leaves 8-row runs and twice the run reservations.  So the
+  // shape follows the pass's fan-out; OLAP_GR_ROWS = 8 / 16 forces one.
+  const char* rv = getenv("OLAP_GR_ROWS");
+  const int forced_rows = rv && *rv ? atoi(rv) : 0;
+  auto launch_gr_part = [&](bool regions, const GrPartArgs& ga, uint64_t fan_out, uint64_t n_tiles_of_4096) -> cudaError_t {
+    const bool r8 = forced_rows ? forced_rows == 8 : fan_out <= 128;
+    const size_t smem = (size_t)kGrThreads * (r8 ? 8 : 16) * 12;
+    const unsigned grid = capped_grid(n_tiles_of_4096 * (r8 ? 2 : 1), (uint64_t)ctx->sm_count * (r8 ? 5 : 3));
+#define GR_LAUNCH(REG, RW)                                                                                                        \
+  {                                                                                                                               \
+    cudaError_t e = cudaFuncSetAttribute(gr_part_kernel<REG, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    if (e != cudaSuccess) return e;                                                                                               \
+    gr_part_kernel<REG, RW><<<grid, kGrThreads, smem, s>>>(ga);                                                                   \
+  }
+    if (regions) { if (r8) GR_LAUNCH(true, 8) else GR_LAUNCH(true, 16) }
+    else { if (r8) GR_LAUNCH(false, 8) else GR_LAUNCH(false, 16) }
+#undef GR_LAUNCH
+    return cudaGetLastError();
+  };
   GrPartArgs a;
   memset(&a, 0, sizeof(a));
   a.keys = p.keys; a.vals = p.n_vcols ? p.vcol[0] : nullptr; a.n = p.n; a.rmin = (uint64_t)rmin; a.rrange = rrange; a.flags = flags;
-  const uint64_t tiles0 = (p.n + kGrTile - 1) / kGrTile;
-  const unsigned grid0 = capped_grid(tiles0, (uint64_t)ctx->sm_count * 3);
+  const uint64_t tiles0 = (p.n + 4095) / 4096;
   if (!two) {
     a.shift = kGrKeysLog2; a.cap = cap; a.cursor = cur2; a.out_d = d2; a.out_v = v2;
-    gr_part_kernel<false><<<grid0, kGrThreads, smem, s>>>(a);
+    OLAP_CUDA(launch_gr_part(false, a, P, tiles0));
     count_launch(ctx, 2);
   } else {
     a.shift = kGrKeysLog2 + 8; a.cap = cap1; a.cursor = cur1; a.out_d = d1; a.out_v = v1;
-    gr_part_kernel<false><<<grid0, kGrThreads, smem, s>>>(a);
+    OLAP_CUDA(launch_gr_part(false, a, C, tiles0));
     phase_mark(ctx, s, "partition_coarse");
     GrPartArgs f;
     memset(&f, 0, sizeof(f));
     f.in_d = d1; f.in_v = v1; f.reg_cur = cur1; f.reg_cap = cap1; f.n_reg = (uint32_t)C; f.reg_parts = kGrThreads;
     f.shift = kGrKeysLog2; f.cap = cap; f.cursor = cur2; f.out_d = d2; f.out_v = v2; f.flags = flags;
-    const uint64_t tiles1 = (uint64_t)((cap1 + kGrTile - 1) / kGrTile) * C;
-    gr_part_kernel<true><<<capped_grid(tiles1, (uint64_t)ctx->sm_count * 3), kGrThreads, smem, s>>>(f);
+    const uint64_t tiles1 = (uint64_t)((cap1 + 4095) / 4096) * C;
+    OLAP_CUDA(launch_gr_part(true, f, kGrThreads, tiles1));
     count_launch(ctx, 3);
   }
   phase_mark(ctx, s, "partition");
