@@ -17,7 +17,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--groups", default="1,8,100,1000,10000,100000,1000000,10000000,100000000")
     ap.add_argument("--only", default="groupby,filter,tpch")
-    ap.add_argument("--sf", type=float, default=10.0, help="TPC-H scale factor of the lineitem-shaped table (6,000,379 rows per unit)")
+    ap.add_argument("--sf", type=float, default=100.0, help="TPC-H scale factor of the lineitem-shaped table (6,000,379 rows per unit); BASELINE config 4 is SF100")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -81,25 +81,36 @@ def main():
         bench_tpch(ctx, g, args, peak)
 
 
-def bench_tpch(ctx, g, args, peak):
-    """C4: lineitem-shaped columns, registered once as device-resident batches; Q6 and Q1 as PhysicalPlan
-    trees through olap_execute.  Time = wall clock around execute() (plan lowering, kernels, export of the tiny result)."""
-    import time
+def device_lineitem(ctx, g, n):
+    """lineitem-shaped columns of SURVEY.md 8(d) C4, generated ON THE DEVICE (olap_generate + the projection kernels): SF100 is 600 M
+    rows x 7 columns = 33.6 GB, which a host-side generator + PCIe would turn into minutes of set-up.  {name: (DeviceBuffer, type)}."""
     import numpy as np
-    import pyarrow as pa
-    n = int(6_000_379 * args.sf)
-    rng = np.random.default_rng(7)
-    qty = rng.integers(1, 51, n).astype(np.float64)
-    price = np.round(qty * (900.0 + rng.integers(0, 120001, n) / 100.0) * 100.0) / 100.0
-    cols = {"l_shipdate": rng.integers(8036, 10562, n, dtype=np.int64), "l_quantity": qty, "l_extendedprice": price,
-            "l_discount": rng.integers(0, 11, n) / 100.0, "l_tax": rng.integers(0, 9, n) / 100.0,
-            "l_returnflag": rng.integers(0, 3, n, dtype=np.int64), "l_linestatus": rng.integers(0, 2, n, dtype=np.int64)}
-    ex = g.GpuExecutor(g.EngineConfig(), ctx=ctx)
-    ex.drop_table("lineitem")
-    step = 1 << 24
-    for a in range(0, n, step):
-        ex.register_table("lineitem", pa.record_batch({k: v[a:a + step] for k, v in cols.items()}))
-    del cols, qty, price
+    from gpu_olap_engine_b200._lib import check
+    lib, h = ctx.lib, ctx.handle
+
+    def f64_op(col, op, lit, rhs=None):   # out-of-place (the projection kernels take __restrict__ pointers); the input is dropped
+        out = ctx.alloc(n, np.float64)
+        check(lib.olap_project_f64(h, col.ptr, rhs.ptr if rhs is not None else None, float(lit), op, n, out.ptr, None))
+        ctx.synchronize()
+        return out
+
+    def f64_of_int(seed, domain):            # (u % domain) as f64: kind 2 gives (u % domain) / 1024 exactly, and x 1024 is exact too
+        return f64_op(ctx.generate(n, 2, seed, domain), b"*", 1024.0)
+    days = ctx.generate(n, 0, 70, 2526)
+    shipdate = ctx.alloc(n, np.int64)
+    check(lib.olap_project_i64(h, days.ptr, None, 8036, b"+", n, shipdate.ptr, None))                 # days 8036 .. 10561
+    ctx.synchronize()
+    del days
+    qty = f64_op(f64_of_int(71, 50), b"+", 1.0)                                                       # 1 .. 50
+    price = f64_op(f64_op(f64_op(f64_of_int(72, 120001), b"/", 100.0), b"+", 900.0), b"*", 0.0, rhs=qty)   # (900.00 .. 2100.00) x quantity
+    discount = f64_op(f64_of_int(73, 11), b"/", 100.0)                                                # 0.00 .. 0.10
+    tax = f64_op(f64_of_int(74, 9), b"/", 100.0)                                                      # 0.00 .. 0.08
+    return {"l_shipdate": (shipdate, g.I64), "l_quantity": (qty, g.F64), "l_extendedprice": (price, g.F64), "l_discount": (discount, g.F64),
+            "l_tax": (tax, g.F64), "l_returnflag": (ctx.generate(n, 0, 75, 3), g.I64), "l_linestatus": (ctx.generate(n, 0, 76, 2), g.I64)}
+
+
+def tpch_plans(g):
+    """(Q6, Q1) of BASELINE config 4 as PhysicalPlan trees over a registered "lineitem" table."""
     col = lambda name: g.Column(0, name)
     lit = lambda v: g.Literal(str(v))
     B = g.BinaryExpr
@@ -116,6 +127,20 @@ def bench_tpch(ctx, g, args, peak):
     q1 = g.GpuAggregate(g.GpuFilter(g.GpuTableScan("lineitem"), B(col("l_shipdate"), "<=", lit(10471))), [key],
                         [g.Sum(col("l_quantity")), g.Sum(col("l_extendedprice")), g.Sum(disc_price), g.Sum(charge), g.Avg(col("l_quantity")),
                          g.Avg(col("l_extendedprice")), g.Avg(col("l_discount")), g.Count(col("l_quantity"))])
+    return q6, q1
+
+
+def bench_tpch(ctx, g, args, peak):
+    """C4: lineitem-shaped columns registered once as a device-resident table; Q6 and Q1 as PhysicalPlan trees through
+    olap_execute.  Time = wall clock around execute() (plan lowering, kernels, export of the tiny result)."""
+    import time
+    n = int(6_000_379 * args.sf)
+    ex = g.GpuExecutor(g.EngineConfig(), ctx=ctx)
+    ex.drop_table("lineitem")
+    cols = device_lineitem(ctx, g, n)
+    ex.register_device_table("lineitem", cols, n)
+    del cols
+    q6, q1 = tpch_plans(g)
     for name, plan, ncols in (("TPC-H Q6 shape", q6, 4), ("TPC-H Q1 shape", q1, 7)):
         for _ in range(args.warmup):
             out = ex.execute(plan)

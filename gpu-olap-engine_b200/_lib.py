@@ -102,6 +102,7 @@ SIGNATURES = {
     "olap_shard_hot_table": (i32, [vp, pu64, vp]),
     "olap_group_by_i64": (i32, [vp, vp, C.POINTER(AggSpec), i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_group_by_prog_i64": (i32, [vp, vp, C.POINTER(AggSpec), vp, i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
+    "olap_group_by_expr_i64": (i32, [vp, vp, C.POINTER(AggSpec), vp, i32, u64, u64, C.POINTER(FilterTerm), i32, vp, vp, u64, vp, pu64, vp]),
     "olap_sharded_group_by_i64": (i32, [pvp, i32, pvp, pvp, i32, pu64, u64, pvp, pvp, pu64, pu64]),
     "olap_agg_identity": (i64, [i32]),
     "olap_compute_launch_params": (None, [u64, C.POINTER(u32), C.POINTER(u32)]),
@@ -116,6 +117,7 @@ SIGNATURES = {
     "olap_plan_aggregate": (vp, [vp, pvp, i32, C.POINTER(i32), pvp, i32]),
     "olap_plan_free": (None, [vp]),
     "olap_register_batch": (i32, [vp, C.c_char_p, vp, vp]),
+    "olap_register_device_batch": (i32, [vp, C.c_char_p, i32, C.POINTER(C.c_char_p), C.POINTER(i32), pvp, pvp, u64]),
     "olap_drop_table": (i32, [vp, C.c_char_p]),
     "olap_execute": (i32, [vp, vp, pvp]),
     "olap_result_num_batches": (i32, [vp]),

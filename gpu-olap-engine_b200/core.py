@@ -255,7 +255,7 @@ class Context:
 
     # ------------------------------------------------------------------ aggregate
     def group_by_i64(self, keys, n_rows: int, aggs: Sequence[tuple], n_groups_hint: int, out_capacity: Optional[int] = None,
-                     terms: Optional[Sequence[Term]] = None, stream=None, progs=None):
+                     terms: Optional[Sequence[Term]] = None, stream=None, progs=None, key_prog=None):
         """AggregateKernel::aggregate analogue.  aggs: [(func, values, value_type)].
 
         Returns (n_groups, out_keys DeviceBuffer, out_aggs DeviceBuffer [n_aggs * out_capacity], out_capacity)."""
@@ -266,7 +266,13 @@ class Context:
         oa = self.alloc(max(na, 1) * cap, np.uint64)
         arr, nt = _terms(terms)
         g = C.c_uint64()
-        if progs is None:
+        if key_prog is not None:  # computed Int64 group key (olap_group_by_expr_i64): keys must be None
+            kp = make_prog(key_prog, I64)
+            built = [None if pr is None else make_prog(pr, aggs[i][2]) for i, pr in enumerate(progs or [None] * na)]
+            ptrs = (C.c_void_p * max(na, 1))(*[None if b is None else C.addressof(b) for b in built])
+            check(self.lib.olap_group_by_expr_i64(self.handle, C.addressof(kp), specs, ptrs, na, n_rows, n_groups_hint, arr, nt, ok.ptr, oa.ptr, cap,
+                                                  None, C.byref(g), stream))
+        elif progs is None:
             check(self.lib.olap_group_by_i64(self.handle, _ptr(keys), specs, na, n_rows, n_groups_hint, arr, nt, ok.ptr, oa.ptr, cap,
                                              None, C.byref(g), stream))
         else:  # progs[i]: None, or [("c", column) | ("l", literal) | "+" | "-" | "*" | "/", ...] in reverse Polish notation

@@ -43,6 +43,7 @@ struct GbParams {
   int n_vcols;                             // distinct value columns, each loaded once per row
   const uint64_t* vcol[kMaxVcols];
   ExprProg prog[kMaxVcols];                // prog[q].n > 0: value column q is computed, not loaded
+  ExprProg key_prog;                       // n > 0: the group key is computed from other columns (keys is then a non-NULL sentinel, never read)
   bool prog_vec;                           // the programs' columns are 32-byte aligned
   int n_cells;
   int8_t cell_op[kMaxCells];
@@ -309,7 +310,7 @@ template <int NV, bool KEYED, bool PROG = false>
 __device__ __forceinline__ void load_rows(const GbParams& p, uint64_t row0, uint64_t begin, uint64_t end, uint64_t (&key)[kGbRows],
                                           uint64_t (&v)[kGbRows][NV], bool (&pass)[kGbRows]) {
   if (p.vec && row0 >= begin && row0 + 3 < end) {
-    if (KEYED) { const u64x4 k = ld_stream_u64x4(p.keys + row0); key[0] = k.a; key[1] = k.b; key[2] = k.c; key[3] = k.d; }
+    if (KEYED && !(PROG && p.key_prog.n)) { const u64x4 k = ld_stream_u64x4(p.keys + row0); key[0] = k.a; key[1] = k.b; key[2] = k.c; key[3] = k.d; }
 #pragma unroll
     for (int q = 0; q < NV; q++) {
       if (q < p.n_vcols && (!PROG || p.prog[q].n == 0)) { const u64x4 x = ld_stream_u64x4(p.vcol[q] + row0); v[0][q] = x.a; v[1][q] = x.b; v[2][q] = x.c; v[3][q] = x.d; }
@@ -322,7 +323,7 @@ __device__ __forceinline__ void load_rows(const GbParams& p, uint64_t row0, uint
     for (int j = 0; j < kGbRows; j++) {
       const uint64_t row = row0 + j;
       pass[j] = row >= begin && row < end;
-      key[j] = (KEYED && pass[j]) ? ld_stream_u64(p.keys + row) : 0;
+      key[j] = (KEYED && pass[j] && !(PROG && p.key_prog.n)) ? ld_stream_u64(p.keys + row) : 0;
 #pragma unroll
       for (int q = 0; q < NV; q++) v[j][q] = (pass[j] && q < p.n_vcols && (!PROG || p.prog[q].n == 0)) ? ld_stream_u64(p.vcol[q] + row) : 0;
     }
@@ -335,6 +336,12 @@ __device__ __forceinline__ void load_rows(const GbParams& p, uint64_t row0, uint
 #pragma unroll
       for (int j = 0; j < kGbRows; j++) v[j][q] = r[j];
     }
+  if (PROG && KEYED && p.key_prog.n) {  // computed group key (GROUP BY returnflag * 2 + linestatus): no projection pass, no key column
+    uint64_t r[4];
+    if (p.prog_vec) eval_prog4<true>(p.key_prog, row0, begin, end, r); else eval_prog4<false>(p.key_prog, row0, begin, end, r);
+#pragma unroll
+    for (int j = 0; j < kGbRows; j++) key[j] = r[j];
+  }
   if (p.terms.n) {  // the fused filter: 256-bit loads of the predicate columns, operator switch once per four rows
     bool f[4];
     if (p.terms_vec) eval_quad<true>(p.terms, row0, end, f); else eval_quad<false>(p.terms, row0, end, f);
@@ -1009,6 +1016,23 @@ __global__ void __launch_bounds__(256) gb_extract_kernel(GbParams p, bool emit_e
 }
 
 // ------------------------------------------------------------------------------------------- host driver
+static olap_status convert_prog(const olap_expr_prog* g, bool f64, ExprProg* out) {
+  OLAP_REQUIRE(g->n_ops >= 1 && g->n_ops <= kMaxProgOps, "expression program: 1..OLAP_PROG_MAX_OPS entries");
+  ExprProg& e = *out;
+  e.n = (int8_t)g->n_ops; e.f64 = f64;
+  int depth = 0;
+  for (int k = 0; k < g->n_ops; k++) {
+    const int op = g->op[k];
+    e.op[k] = (int8_t)op; e.col[k] = (const uint64_t*)g->column[k]; e.lit[k] = (uint64_t)g->literal_bits[k];
+    if (op == 'c') { OLAP_REQUIRE(g->column[k], "expression program: NULL column"); depth++; }
+    else if (op == 'l') depth++;
+    else { OLAP_REQUIRE(op == '+' || op == '-' || op == '*' || op == '/', "expression program: unknown op"); OLAP_REQUIRE(depth >= 2, "expression program: stack underflow"); depth--; }
+    OLAP_REQUIRE(depth <= 3, "expression program: stack depth > 3");
+  }
+  OLAP_REQUIRE(depth == 1, "expression program must leave exactly one value");
+  return OLAP_OK;
+}
+
 static olap_status build_cells(const olap_agg_spec* specs, const olap_expr_prog* const* progs, int n_aggs, GbParams* p) {
   OLAP_REQUIRE(n_aggs >= 0 && n_aggs <= 16, "n_aggs must be in [0, 16]");
   OutSpec* o = &p->out;
@@ -1030,21 +1054,7 @@ static olap_status build_cells(const olap_agg_spec* specs, const olap_expr_prog*
       OLAP_REQUIRE(p->n_vcols < kMaxVcols, "more than 6 distinct value columns in one aggregation");
       vc = p->n_vcols++;
       p->vcol[vc] = id;
-      if (g) {
-        OLAP_REQUIRE(g->n_ops >= 1 && g->n_ops <= kMaxProgOps, "expression program: 1..OLAP_PROG_MAX_OPS entries");
-        ExprProg& e = p->prog[vc];
-        e.n = (int8_t)g->n_ops; e.f64 = t == OLAP_F64;
-        int depth = 0;
-        for (int k = 0; k < g->n_ops; k++) {
-          const int op = g->op[k];
-          e.op[k] = (int8_t)op; e.col[k] = (const uint64_t*)g->column[k]; e.lit[k] = (uint64_t)g->literal_bits[k];
-          if (op == 'c') { OLAP_REQUIRE(g->column[k], "expression program: NULL column"); depth++; }
-          else if (op == 'l') depth++;
-          else { OLAP_REQUIRE(op == '+' || op == '-' || op == '*' || op == '/', "expression program: unknown op"); OLAP_REQUIRE(depth >= 2, "expression program: stack underflow"); depth--; }
-          OLAP_REQUIRE(depth <= 3, "expression program: stack depth > 3");
-        }
-        OLAP_REQUIRE(depth == 1, "expression program must leave exactly one value");
-      }
+      if (g) OLAP_TRY(convert_prog(g, t == OLAP_F64, &p->prog[vc]));
     }
     const int8_t op = (f == OLAP_SUM || f == OLAP_AVG) ? (t == OLAP_F64 ? ADD_F64 : ADD_I64)
                       : f == OLAP_MIN ? (t == OLAP_F64 ? MIN_F64 : MIN_I64) : (t == OLAP_F64 ? MAX_F64 : MAX_I64);
@@ -1246,7 +1256,7 @@ static olap_status run_dense_range(olap_ctx* ctx, const GbParams& p, int64_t rmi
 
 using namespace olap;
 
-static olap_status group_by_impl(olap_ctx* ctx, const int64_t* keys, const olap_agg_spec* specs, const olap_expr_prog* const* progs, int32_t n_aggs,
+static olap_status group_by_impl(olap_ctx* ctx, const olap_expr_prog* key_prog, const int64_t* keys, const olap_agg_spec* specs, const olap_expr_prog* const* progs, int32_t n_aggs,
                                  uint64_t n_rows, uint64_t n_groups_hint, const olap_filter_term* terms, int32_t n_terms, int64_t* out_keys,
                                  void* out_aggs, uint64_t out_capacity, uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream) {
   OLAP_REQUIRE(ctx, "ctx is NULL");
@@ -1261,11 +1271,19 @@ static olap_status group_by_impl(olap_ctx* ctx, const int64_t* keys, const olap_
   memset(&p, 0, sizeof(p));
   OLAP_TRY(build_cells(specs, progs, n_aggs, &p));
   OLAP_TRY(pack_terms(terms, n_terms, &p.terms));
+  bool any_prog = false;
+  p.prog_vec = true;
+  if (key_prog) {  // computed Int64 group key: every "keys ?" below reads "grouped ?", and the PROG kernels never load through it
+    OLAP_REQUIRE(!keys, "pass either a key column or a key program");
+    OLAP_TRY(convert_prog(key_prog, false, &p.key_prog));
+    for (int k = 0; k < p.key_prog.n; k++)
+      if (p.key_prog.op[k] == 'c') p.prog_vec = p.prog_vec && (((uintptr_t)p.key_prog.col[k]) & 31) == 0;
+    keys = reinterpret_cast<const int64_t*>(uintptr_t(0x100));
+    any_prog = true;
+  }
   p.keys = (const uint64_t*)keys;
   p.n = n_rows;
   p.vec = (((uintptr_t)keys) & 31) == 0;
-  bool any_prog = false;
-  p.prog_vec = true;
   for (int q = 0; q < p.n_vcols; q++) {
     if (p.prog[q].n == 0) { p.vec = p.vec && (((uintptr_t)p.vcol[q]) & 31) == 0; continue; }
     any_prog = true;
@@ -1397,7 +1415,7 @@ extern "C" olap_status olap_group_by_i64(olap_ctx* ctx, const int64_t* keys, con
                                          uint64_t n_groups_hint, const olap_filter_term* terms, int32_t n_terms, int64_t* out_keys,
                                          void* out_aggs, uint64_t out_capacity, uint64_t* out_n_groups_dptr, uint64_t* host_n_groups,
                                          void* stream) {
-  return group_by_impl(ctx, keys, specs, nullptr, n_aggs, n_rows, n_groups_hint, terms, n_terms, out_keys, out_aggs, out_capacity,
+  return group_by_impl(ctx, nullptr, keys, specs, nullptr, n_aggs, n_rows, n_groups_hint, terms, n_terms, out_keys, out_aggs, out_capacity,
                        out_n_groups_dptr, host_n_groups, stream);
 }
 
@@ -1405,6 +1423,15 @@ extern "C" olap_status olap_group_by_prog_i64(olap_ctx* ctx, const int64_t* keys
                                               int32_t n_aggs, uint64_t n_rows, uint64_t n_groups_hint, const olap_filter_term* terms,
                                               int32_t n_terms, int64_t* out_keys, void* out_aggs, uint64_t out_capacity,
                                               uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream) {
-  return group_by_impl(ctx, keys, specs, progs, n_aggs, n_rows, n_groups_hint, terms, n_terms, out_keys, out_aggs, out_capacity,
+  return group_by_impl(ctx, nullptr, keys, specs, progs, n_aggs, n_rows, n_groups_hint, terms, n_terms, out_keys, out_aggs, out_capacity,
+                       out_n_groups_dptr, host_n_groups, stream);
+}
+
+extern "C" olap_status olap_group_by_expr_i64(olap_ctx* ctx, const olap_expr_prog* key_prog, const olap_agg_spec* specs, const olap_expr_prog* const* progs,
+                                              int32_t n_aggs, uint64_t n_rows, uint64_t n_groups_hint, const olap_filter_term* terms,
+                                              int32_t n_terms, int64_t* out_keys, void* out_aggs, uint64_t out_capacity,
+                                              uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream) {
+  OLAP_REQUIRE(key_prog, "key_prog is NULL (olap_group_by_prog_i64 takes a key column)");
+  return group_by_impl(ctx, key_prog, nullptr, specs, progs, n_aggs, n_rows, n_groups_hint, terms, n_terms, out_keys, out_aggs, out_capacity,
                        out_n_groups_dptr, host_n_groups, stream);
 }

@@ -521,18 +521,36 @@ static bool compile_prog(const olap_expr* e, const Batch& b, olap_expr_prog* g, 
 // Number of groups of a key column, estimated from the distinct keys d among m <= 2^17 evenly spaced rows: for G equally likely
 // groups E[d] = G (1 - exp(-m / G)).  The group-by kernels take it as a hint: too low or too high costs speed (a shared
 // table that spills, or L2 atomics where shared memory would do), never correctness.
-static olap_status estimate_groups(olap_ctx* ctx, const uint64_t* keys, uint64_t n, uint64_t* est) {
+// keys: the key column, or NULL with key_prog: a computed key, whose input columns are sampled at the same rows and the program run
+// on the samples.
+static olap_status estimate_groups(olap_ctx* ctx, const uint64_t* keys, const olap_expr_prog* key_prog, uint64_t n, uint64_t* est) {
   const uint64_t m = std::min<uint64_t>(n, 1u << 17), stride = n / m;  // 2^17 rows resolve cardinalities up to ~10^6 (d/m = 0.94 there) and cost ~50 us
-  BufPtr sk, ok, oa;
-  OLAP_TRY(new_buf(ctx, m * 8, &sk));
+  BufPtr ok, oa;
   OLAP_TRY(new_buf(ctx, m * 8, &ok));
   OLAP_TRY(new_buf(ctx, m * 8, &oa));
-  sample_kernel<<<small_grid(ctx, m), 256, 0, ctx->streams[0]>>>(keys, stride, m, (uint64_t*)sk->p);
-  count_launch(ctx);
-  OLAP_CUDA(cudaGetLastError());
   olap_agg_spec cnt; cnt.values = nullptr; cnt.func = OLAP_COUNT; cnt.value_type = OLAP_I64;
   uint64_t d = 0;
-  OLAP_TRY(olap_group_by_i64(ctx, (const int64_t*)sk->p, &cnt, 1, m, std::min<uint64_t>(m, 1u << 16), nullptr, 0, (int64_t*)ok->p, oa->p, m, nullptr, &d, nullptr));
+  std::vector<BufPtr> samples;
+  auto sample = [&](const uint64_t* col, const uint64_t** out) -> olap_status {
+    BufPtr sk;
+    OLAP_TRY(new_buf(ctx, m * 8, &sk));
+    sample_kernel<<<small_grid(ctx, m), 256, 0, ctx->streams[0]>>>(col, stride, m, (uint64_t*)sk->p);
+    count_launch(ctx);
+    OLAP_CUDA(cudaGetLastError());
+    samples.push_back(sk);
+    *out = (const uint64_t*)sk->p;
+    return OLAP_OK;
+  };
+  if (key_prog) {
+    olap_expr_prog sp = *key_prog;
+    for (int k = 0; k < sp.n_ops; k++)
+      if (sp.op[k] == 'c') { const uint64_t* c = nullptr; OLAP_TRY(sample((const uint64_t*)key_prog->column[k], &c)); sp.column[k] = c; }
+    OLAP_TRY(olap_group_by_expr_i64(ctx, &sp, &cnt, nullptr, 1, m, std::min<uint64_t>(m, 1u << 16), nullptr, 0, (int64_t*)ok->p, oa->p, m, nullptr, &d, nullptr));
+  } else {
+    const uint64_t* sk = nullptr;
+    OLAP_TRY(sample(keys, &sk));
+    OLAP_TRY(olap_group_by_i64(ctx, (const int64_t*)sk, &cnt, 1, m, std::min<uint64_t>(m, 1u << 16), nullptr, 0, (int64_t*)ok->p, oa->p, m, nullptr, &d, nullptr));
+  }
   double g;
   if (m == n) g = (double)d;                        // the sample is the column
   else if ((double)d > 0.98 * (double)m) g = (double)n;  // (almost) every sampled key is new: no information beyond "very many"
@@ -614,26 +632,43 @@ static olap_status exec_aggregate(olap_ctx* ctx, const olap_plan* p, Batches* ou
   specs[na].values = nullptr; specs[na].func = OLAP_COUNT; specs[na].value_type = OLAP_I64;
   const bool grouped = !p->group_by.empty();
   Value key;
-  if (grouped) {
-    if (in.empty() || n == 0) return OLAP_OK;  // grouped aggregation of nothing: no rows
+  // An arithmetic group key (Q1: GROUP BY returnflag * 2 + linestatus) becomes a program of the aggregation kernel like the value
+  // expressions: no projection passes, no key column written and read back.  Keys that do not fit a program, and cardinalities
+  // that need the partitioned regime (which carries plain columns), are materialised as before.
+  olap_expr_prog key_prog;
+  bool key_fused = false;
+  auto materialise_key = [&]() -> olap_status {
+    key_fused = false;
     OLAP_TRY(eval_over_batches(ctx, p->group_by[0], in, n, &key));
     if (key.type != OLAP_I64) { set_error("GROUP BY key must be Int64 (aggregate_kernel.rs:48-49)"); return OLAP_ERR_UNSUPPORTED; }
+    return OLAP_OK;
+  };
+  if (grouped) {
+    if (in.empty() || n == 0) return OLAP_OK;  // grouped aggregation of nothing: no rows
+    int ktype = -1;
+    if (compile_prog(p->group_by[0], in[0], &key_prog, &ktype) && ktype == OLAP_I64) key_fused = true;
+    else OLAP_TRY(materialise_key());
   }
   const int ns = na < 16 ? na + 1 : na;  // the kernel seam takes at most 16 aggregates
   uint64_t hint = 1;
-  if (grouped) OLAP_TRY(estimate_groups(ctx, key.data(), n, &hint));
+  if (grouped) OLAP_TRY(estimate_groups(ctx, key_fused ? nullptr : key.data(), key_fused ? &key_prog : nullptr, n, &hint));
   uint64_t cap = hint, groups = 0;
   BufPtr ok, oa;
   bool refused = false;  // at most one UNSUPPORTED retry
   for (int attempt = 0; attempt < 2; attempt++) {
     OLAP_TRY(new_buf(ctx, cap * 8, &ok));
     OLAP_TRY(new_buf(ctx, (uint64_t)ns * cap * 8, &oa));
-    olap_status st = olap_group_by_prog_i64(ctx, grouped ? (const int64_t*)key.data() : nullptr, specs.data(), progs.data(), ns, n, hint,
-                                            terms.empty() ? nullptr : terms.data(), (int32_t)terms.size(), (int64_t*)ok->p, oa->p, cap, nullptr, &groups,
-                                            nullptr);
+    olap_status st;
+    if (key_fused)
+      st = olap_group_by_expr_i64(ctx, &key_prog, specs.data(), progs.data(), ns, n, hint, terms.empty() ? nullptr : terms.data(), (int32_t)terms.size(),
+                                  (int64_t*)ok->p, oa->p, cap, nullptr, &groups, nullptr);
+    else
+      st = olap_group_by_prog_i64(ctx, grouped ? (const int64_t*)key.data() : nullptr, specs.data(), progs.data(), ns, n, hint,
+                                  terms.empty() ? nullptr : terms.data(), (int32_t)terms.size(), (int64_t*)ok->p, oa->p, cap, nullptr, &groups, nullptr);
     if (st == OLAP_ERR_UNSUPPORTED && !refused) {  // too many groups for the regimes that fuse expressions: materialise them
       refused = true;
       OLAP_TRY(bind_inputs(false));
+      if (key_fused) OLAP_TRY(materialise_key());
       attempt = -1;
       continue;
     }
@@ -651,6 +686,8 @@ static olap_status exec_aggregate(olap_ctx* ctx, const olap_plan* p, Batches* ou
     OLAP_CUDA(cudaMemcpyAsync(host.data(), oa->p, host.size() * 8, cudaMemcpyDeviceToHost, ctx->streams[0]));
     OLAP_CUDA(cudaStreamSynchronize(ctx->streams[0]));
     if (ns > na) passing = host[(size_t)na * cap];
+    else if (!terms.empty())  // 16 user aggregates leave no room for the hidden COUNT: count the rows that pass the fused filter separately
+      OLAP_TRY(olap_filter(ctx, terms.data(), (int32_t)terms.size(), n, nullptr, nullptr, nullptr, &passing, nullptr));
   }
   for (int a = 0; a < na; a++) {
     Col c; c.name = std::string(agg_name(p->agg_funcs[a])) + "(" + expr_name(p->agg_in[a]) + ")";
@@ -872,6 +909,30 @@ static olap_status register_batch_impl(olap_ctx* ctx, const char* table_name, Ar
     b.cols.push_back(c);
   }
   OLAP_TRY(olap_stream_synchronize(ctx, nullptr));  // the Arrow buffers may go away once the caller releases the array
+  Catalog* cat = catalog_of(ctx);
+  std::lock_guard<std::mutex> g(cat->mu);
+  cat->tables[table_name].push_back(b);
+  return OLAP_OK;
+}
+
+olap_status olap_register_device_batch(olap_ctx* ctx, const char* table_name, int32_t n_cols, const char* const* names, const int32_t* types,
+                                       const void* const* columns_dptr, const uint8_t* const* validity_dptr, uint64_t n_rows) {
+  OLAP_REQUIRE(ctx && table_name && n_cols >= 1 && names && types && columns_dptr, "NULL argument");
+  OLAP_CUDA(cudaSetDevice(ctx->device));
+  Batch b; b.n = n_rows;
+  for (int i = 0; i < n_cols; i++) {
+    OLAP_REQUIRE(names[i] && (n_rows == 0 || columns_dptr[i]), "NULL column name / pointer");
+    OLAP_REQUIRE(types[i] == OLAP_I64 || types[i] == OLAP_F64, "column type must be OLAP_I64 or OLAP_F64");
+    Col c; c.name = names[i]; c.type = types[i];
+    OLAP_TRY(new_buf(ctx, std::max<uint64_t>(n_rows, 2) * 8, &c.buf));
+    if (n_rows) OLAP_CUDA(cudaMemcpyAsync(c.buf->p, columns_dptr[i], n_rows * 8, cudaMemcpyDeviceToDevice, ctx->streams[0]));
+    if (validity_dptr && validity_dptr[i] && n_rows) {
+      OLAP_TRY(new_buf(ctx, n_rows, &c.valid));
+      OLAP_CUDA(cudaMemcpyAsync(c.valid->p, validity_dptr[i], n_rows, cudaMemcpyDeviceToDevice, ctx->streams[0]));
+    }
+    b.cols.push_back(c);
+  }
+  OLAP_CUDA(cudaStreamSynchronize(ctx->streams[0]));  // the caller may reuse its buffers on return
   Catalog* cat = catalog_of(ctx);
   std::lock_guard<std::mutex> g(cat->mu);
   cat->tables[table_name].push_back(b);

@@ -52,6 +52,16 @@ class GpuExecutor:
             finally:
                 pa.Schema._import_from_c(c.schema_ptr)  # releases the exported schema
 
+    def register_device_table(self, table_name: str, columns, n_rows: int) -> None:
+        """Append one batch of device-resident columns ({name: (DeviceBuffer, OLAP_I64 | OLAP_F64)}) to ``table_name`` -- copied device
+        to device, no host round trip (olap_register_device_batch)."""
+        names = list(columns)
+        n = len(names)
+        cn = (C.c_char_p * n)(*[x.encode() for x in names])
+        ct = (C.c_int32 * n)(*[int(columns[x][1]) for x in names])
+        cp = (C.c_void_p * n)(*[columns[x][0].ptr for x in names])
+        check(self.lib.olap_register_device_batch(self.ctx.handle, table_name.encode(), n, cn, ct, cp, None, n_rows))
+
     def drop_table(self, table_name: str) -> None:
         check(self.lib.olap_drop_table(self.ctx.handle, table_name.encode()))
 

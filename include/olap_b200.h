@@ -9,11 +9,15 @@
  * Conventions
  *   - "dptr" arguments are device addresses (what the reference passes as u64 in JoinParams/FilterParams/
  *     AggregateParams); all columns are packed little-endian 8-byte values (arrow-interop column_buffer.rs:19-21).
- *   - stream is a cudaStream_t passed as void* (NULL = the context's stream 0).  Calls are asynchronous on that
- *     stream unless a host out-parameter (uint64_t* host_*) is non-NULL, in which case the call synchronises the
- *     stream before returning so the value is valid.
- *   - One olap_ctx per GPU.  Calls on one ctx from several host threads are serialised by an internal mutex;
- *     distinct ctxs are independent.
+ *   - stream is a cudaStream_t passed as void* (NULL = the context's stream 0).  Filters, projections, gathers, uploads,
+ *     copies, partition / shuffle passes and the olap_shard_* phase calls are asynchronous on that stream unless a host
+ *     out-parameter (uint64_t* host_*) is non-NULL, in which case the call synchronises the stream before returning so
+ *     the value is valid.  The join (olap_hash_join_i64, olap_join_build_create, olap_join_probe) and the group-by are
+ *     ADAPTIVE operators: they read a few words back (fast-path flags, partition fill, the group count) to pick or to
+ *     abandon a regime, so they synchronise their stream internally whether or not a host out-parameter is given; on
+ *     return their results are complete in stream order either way.
+ *   - One olap_ctx per GPU.  Calls on one ctx from several host threads are serialised by an internal mutex (internal
+ *     waits included); distinct ctxs are independent, so concurrent queries take one ctx each.
  *   - There is no CPU fallback anywhere behind this header.
  */
 #ifndef OLAP_B200_H
@@ -317,6 +321,14 @@ OLAP_API olap_status olap_group_by_prog_i64(olap_ctx* ctx, const int64_t* keys, 
                                             uint64_t n_groups_hint, const olap_filter_term* terms, int32_t n_terms,
                                             int64_t* out_keys, void* out_aggs, uint64_t out_capacity,
                                             uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream);
+/* ... and a computed GROUP BY key: key_prog (Int64 program, same form) replaces the key column -- "GROUP BY returnflag * 2 +
+ * linestatus" without the projection passes that would write the key column and read it back.  Same regimes and the same
+ * OLAP_ERR_UNSUPPORTED rule as olap_group_by_prog_i64; progs may be NULL.                                             */
+OLAP_API olap_status olap_group_by_expr_i64(olap_ctx* ctx, const olap_expr_prog* key_prog, const olap_agg_spec* specs,
+                                            const olap_expr_prog* const* progs, int32_t n_aggs, uint64_t n_rows,
+                                            uint64_t n_groups_hint, const olap_filter_term* terms, int32_t n_terms,
+                                            int64_t* out_keys, void* out_aggs, uint64_t out_capacity,
+                                            uint64_t* out_n_groups_dptr, uint64_t* host_n_groups, void* stream);
 /* AggFunc::identity_value (aggregate_kernel.rs:27-33) */
 OLAP_API int64_t olap_agg_identity(int32_t func);
 /* compute_launch_params (filter_kernel.rs:75-79, aggregate_kernel.rs:127-131), without the u32 truncation bug */
@@ -395,6 +407,12 @@ OLAP_API void olap_plan_free(olap_plan* p);
  * olap_result_export turns back into an Arrow bitmap; filters, projections, joins and aggregates read a null as 0 / 0.0 like the
  * reference does (:103, :108).  The array is released in every case, also when the call fails.                              */
 OLAP_API olap_status olap_register_batch(olap_ctx* ctx, const char* table_name, struct ArrowArray* batch, struct ArrowSchema* schema);
+/* The same for columns that are ALREADY device-resident (an upstream operator's output, a device-side loader, synthetic data):
+ * n_cols 8-byte columns of n_rows rows each, types[i] = OLAP_I64 / OLAP_F64, are copied device-to-device (stream-ordered, no host
+ * round trip) into one batch appended to table_name.  validity[i] (nullable array; entries nullable): one byte per row, 1 = valid. */
+OLAP_API olap_status olap_register_device_batch(olap_ctx* ctx, const char* table_name, int32_t n_cols, const char* const* names,
+                                                const int32_t* types, const void* const* columns_dptr,
+                                                const uint8_t* const* validity_dptr, uint64_t n_rows);
 OLAP_API olap_status olap_drop_table(olap_ctx* ctx, const char* table_name);
 
 /* executor::execute(plan, config) -> Vec<RecordBatch> (executor.rs:15-24).  Results are exported as Arrow C Data

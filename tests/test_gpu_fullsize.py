@@ -89,3 +89,49 @@ def test_filter_full_size_selection_vector(ctx):
     assert bool(exp[s].all())                                  # cnt distinct passing rows == all passing rows
     del v, exp, s
     torch.cuda.empty_cache()
+
+
+def test_tpch_shapes_2_26_rows_device_resident(ctx):
+    # BASELINE config 4 shapes at 2^26 rows through the operator API (olap_execute) on a device-registered table, against torch's own
+    # reductions over the same device columns: Q6 (5 fused conjuncts, SUM(price * discount)) and Q1 (GROUP BY returnflag * 2 + linestatus
+    # as a fused key program, 8 aggregates over fused value programs).  Integer results exact, f64 sums within 1e-12 relative.
+    import gpu_olap_engine_b200 as g
+    from bench_ops import device_lineitem, tpch_plans
+    n = 1 << 26
+    ex = g.GpuExecutor(g.EngineConfig(), ctx=ctx)
+    ex.drop_table("lineitem")
+    cols = device_lineitem(ctx, g, n)
+    ex.register_device_table("lineitem", cols, n)
+    t = {k: as_torch(b, (n,), "<i8" if ty == g.I64 else "<f8") for k, (b, ty) in cols.items()}
+    q6, q1 = tpch_plans(g)
+    ship, qty, price, disc, tax = t["l_shipdate"], t["l_quantity"], t["l_extendedprice"], t["l_discount"], t["l_tax"]
+    assert int(ship.min()) == 8036 and int(ship.max()) == 10561 and float(qty.min()) == 1.0 and float(qty.max()) == 50.0
+    m6 = (ship >= 8766) & (ship < 9131) & (disc >= 0.05) & (disc <= 0.07) & (qty < 24.0)
+    exp6 = float((price * disc)[m6].sum(dtype=torch.float64))
+    got6 = ex.execute(q6)
+    assert len(got6) == 1 and got6[0].num_rows == 1
+    v6 = got6[0].column(0).to_pylist()[0]
+    assert abs(v6 - exp6) <= 1e-12 * abs(exp6), (v6, exp6)
+    m1 = ship <= 10471
+    key = t["l_returnflag"] * 2 + t["l_linestatus"]
+    got1 = ex.execute(q1)[0]
+    assert got1.num_rows == 6
+    gk = np.asarray(got1.column(0).to_numpy())
+    order = np.argsort(gk)
+    assert gk[order].tolist() == [0, 1, 2, 3, 4, 5]
+    dp = price * (1.0 - disc)
+    ch = dp * (1.0 + tax)
+    # the reference sums are torch.sum over each group's rows (pairwise summation: ~1e-15 relative), not atomics in arbitrary order
+    masks = [m1 & (key == k) for k in range(6)]
+    cnt = torch.stack([m.sum() for m in masks]).to(torch.float64)
+    gsum = lambda x: torch.stack([x[m].sum(dtype=torch.float64) for m in masks])
+    exp = [gsum(qty), gsum(price), gsum(dp), gsum(ch)]
+    exp += [exp[0] / cnt, exp[1] / cnt, gsum(disc) / cnt, cnt]
+    for i, e in enumerate(exp):
+        got = np.asarray(got1.column(1 + i).to_numpy(), dtype=np.float64)[order]
+        ref = e.cpu().numpy()
+        assert np.allclose(got, ref, rtol=1e-12, atol=0), (i, float(np.max(np.abs(got - ref) / np.abs(ref))))
+    assert np.asarray(got1.column(8).to_numpy())[order].astype(np.int64).sum() == int(m1.sum())     # COUNT is exact
+    ex.drop_table("lineitem")
+    del t, cols
+    torch.cuda.empty_cache()

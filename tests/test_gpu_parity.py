@@ -439,3 +439,32 @@ def test_group_by_expression_programs_at_the_kernel_seam(ctx):
         for got, want in zip(res, exp[1]):
             assert (np.asarray(got)[order] == np.asarray(want)[eo]).all()
 
+
+
+def test_group_by_computed_key_at_the_kernel_seam(ctx):
+    # olap_group_by_expr_i64: GROUP BY a * 3 + b evaluated inside the aggregation kernel (no key column) == the oracle's group-by over the
+    # materialised key; shared regime, global regime (many groups, few rows), with a fused filter and a value program next to it
+    import gpu_olap_engine_b200 as g
+    for n, da_, db_, hint in ((500_003, 40, 3, 200), (60_001, 30_000, 3, 100_000)):
+        a = O.gen_uniform_i64(n, 90, da_) - da_ // 2; b = O.gen_uniform_i64(n, 91, db_)
+        v = O.gen_uniform_i64(n, 92, 1 << 20); f = O.gen_dyadic_f64(n, 93, 1 << 12)
+        key = O.project_i64(O.project_i64(a, "*", literal=3), "+", r=b)
+        dA, dB, dV, dF = dev(ctx, a), dev(ctx, b), dev(ctx, v), dev(ctx, f)
+        kprog = [("c", dA), ("l", 3), "*", ("c", dB), "+"]
+        aggs = [(g.SUM, dV, g.I64), (g.COUNT, None, g.I64), (g.MAX, None, g.F64), (g.AVG, dV, g.I64)]
+        progs = [None, None, [("c", dF), ("l", 2.0), "*"], None]
+        keep = v > (1 << 19)
+        for terms, mask in ((None, np.ones(n, bool)), ([g.Term(dV, g.GT, 1 << 19)], keep)):
+            ek, er = O.group_by_i64(key[mask], [v[mask], v[mask], (f * 2.0)[mask], v[mask]], [O.SUM, O.COUNT, O.MAX, O.AVG])
+            ng, ok, oa, cap = ctx.group_by_i64(None, n, aggs, hint, terms=terms, progs=progs, key_prog=kprog)
+            assert ng == len(ek)
+            gk = ok.to_numpy(ng); order = np.argsort(gk)
+            assert (gk[order] == ek).all()
+            for i, (got, want) in enumerate(zip(g.typed_agg_results(oa.to_numpy(), cap, ng, aggs), er)):
+                assert np.allclose(np.asarray(got)[order], want, rtol=1e-12, atol=0) if i == 3 else (np.asarray(got)[order] == want).all(), i
+    # a cardinality that needs the partitioned regime is refused (the caller materialises the key), as for value programs
+    n = 1 << 21
+    a = O.gen_uniform_i64(n, 94, 1 << 40); dA = dev(ctx, a)
+    with pytest.raises(g.OlapError) as ei:
+        ctx.group_by_i64(None, n, [(g.COUNT, None, g.I64)], n, key_prog=[("c", dA), ("l", 1), "+"])
+    assert ei.value.status == 5
