@@ -562,8 +562,12 @@ static olap_status estimate_groups(olap_ctx* ctx, const uint64_t* keys, const ol
     }
     g = hi;
   }
+  // No floor beyond the "+ 16": a handful of groups (Q1 has six) must be told as such -- the shared-memory regime turns a small hint
+  // into MORE table copies per CTA, and with a floor of 64 groups Q1 ran on 8 copies of a 128-slot table: lanes 0, 8, 16, 24 of every
+  // warp shared a copy, and the f64 atomicAdd on shared memory (a CAS loop) went round 3.6 times per add (ncu: 48 % of the stall
+  // samples, profiles/r02_ncu_q1_before.txt).
   g = g * 1.25 + 16;
-  *est = (uint64_t)std::min<double>((double)n, std::max<double>(g, 64.0));
+  *est = (uint64_t)std::min<double>((double)n, g);
   return OLAP_OK;
 }
 
