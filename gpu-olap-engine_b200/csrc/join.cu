@@ -1173,7 +1173,9 @@ static olap_status build_side_probe(BuildSide& b, const uint64_t* pk, uint64_t n
   OLAP_TRY(partition_side(ctx, pk, np, bits, pkp, pip, d_pb, hp, sc, s, "hist_probe", "partition_probe", direct ? &b.range : nullptr, &range_overflow));
   if (range_overflow) return OLAP_ERR_INTERNAL_RETRY;
   const uint32_t* hb = b.hb.data();
-  const uint32_t load_pct = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(env_u64("OLAP_JOIN_LOAD", 100), 50), 400);
+  // buckets per 100 build rows.  150: measured in round 1 on sparse random keys (13.9 ms vs 15.5 ms at 100; dense keys preferred 100,
+  // 11.4 vs 12.3 ms) -- and dense unique keys no longer come here, they take the shared-memory direct path (djoin.cu)
+  const uint32_t load_pct = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(env_u64("OLAP_JOIN_LOAD", 150), 50), 400);
   const uint32_t direct_entries = direct ? (1u << b.range.rshift) : 0;  // direct tables: one 4-byte row id per key of the range
   const uint64_t nbk = direct ? direct_entries / 8 : table_buckets((uint32_t)b.max_part, load_pct);  // 32-byte units per table slot
   auto work = [&](uint32_t p) { return part_work(hb[p], hb[P + p], hp[p], hp[P + p], load_pct, direct_entries); };

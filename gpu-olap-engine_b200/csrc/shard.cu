@@ -64,7 +64,7 @@ struct olap_shard {
   int group = 1, last_group = 1;   // chunks per group; the LAST group is short: its join is the tail nothing overlaps
   // heavy hitters: hot = [kHotSlots keys | kHotSlots ids | u64 merged[kHotSlots] | sampling scratch]
   uint32_t* hot = nullptr;
-  bool hot_on = false, hot_ready = false;
+  bool hot_on = false, hot_ready = false, skew_room = false;   // skew_room: plan(hot != 0) -- wider regions, with (1) or without (2) a heavy-hitter table
   olap_pair* hot_pairs = nullptr; uint64_t hot_max = 0;
   uint32_t* hot_keys() const { return hot; }
   uint32_t* hot_ids() const { return hot + hot_table_slots(); }
@@ -282,7 +282,7 @@ olap_status olap_shard_plan(olap_shard* sh, int64_t global_min, int64_t global_m
     sh->bcap = cap_of(sh->build_cap, sh->words_b);
     sh->pcap = cap_of(sh->chunk_cap, sh->words_p);
   }
-  sh->hot_on = hot != 0; sh->hot_ready = false; sh->hot_pairs = nullptr; sh->hot_max = 0;
+  sh->hot_on = hot == 1; sh->skew_room = hot != 0; sh->hot_ready = false; sh->hot_pairs = nullptr; sh->hot_max = 0;
   std::lock_guard<std::mutex> g(ctx->mu);
   OLAP_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t s = ctx->stream_of(stream);
@@ -395,7 +395,7 @@ olap_status olap_shard_build(olap_shard* sh, void* stream) {
   // warm keys still load single key ranges unevenly, so the ranges get three times the room (hot = 2: 200 % slack)
   const double share = std::min(1.0, (double)sh->slice / (double)sh->grange);
   const uint64_t per_chunk = (uint64_t)((double)sh->chunk_cap * sh->world * share) + 1;
-  return dj_probe_begin(sh->dj, per_chunk * (uint64_t)std::max(sh->group, sh->last_group), sh->hot_on ? 2 : 0, s, &sh->pg);
+  return dj_probe_begin(sh->dj, per_chunk * (uint64_t)std::max(sh->group, sh->last_group), sh->skew_room ? 2 : 0, s, &sh->pg);
 }
 
 // join probe chunk `chunk` against the shard's build side; pairs are APPENDED behind those of the earlier chunks of this join

@@ -243,6 +243,9 @@ OLAP_API olap_status olap_shard_barrier(olap_shard* shard, void* stream);
 OLAP_API olap_status olap_shard_signal(olap_shard* shard, void* stream);
 OLAP_API olap_status olap_shard_wait(olap_shard* shard, void* stream);
 OLAP_API olap_status olap_shard_key_range(olap_shard* shard, const int64_t* keys, uint64_t n_rows, int64_t* out_min, int64_t* out_max, void* stream);
+/* hot: 0 = uniform-ish probe keys (regions 5 % above an even share); 1 = heavy hitters: the olap_shard_hot_* sequence below is
+ * mandatory and the regions get 25 % of room for the warm keys; 2 = the same room WITHOUT a heavy-hitter table -- for skew so mild
+ * (no key carries more than ~0.02 % of the probe rows) that the lookups would only cost time.                                */
 OLAP_API olap_status olap_shard_plan(olap_shard* shard, int64_t global_min, int64_t global_max, uint64_t global_build_rows, int32_t hot, void* stream);
 OLAP_API olap_status olap_shard_scatter(olap_shard* shard, int32_t side, int32_t chunk, const int64_t* keys, uint64_t n_rows, uint32_t row_base,
                                         void* stream);
