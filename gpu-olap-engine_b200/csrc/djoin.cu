@@ -79,8 +79,9 @@ struct RPartArgs {
 
 // peer_subw = F << 15 with F <= 256, offsets < 2^32: (offset >> 15) < 2^17 and (x * ceil(2^32 / F)) >> 32 == x / F exactly (the error
 // term x / 2^32 < 2^-15 < 1 / F); partitions < 256: (p * ceil(2^24 / Q)) >> 24 == p / Q exactly
-__device__ __forceinline__ uint32_t peer_part(const RPartArgs& a, uint32_t d) { return (uint32_t)(((uint64_t)(d >> kRShift) * a.peer_mf) >> 32); }
-__device__ __forceinline__ uint32_t peer_dest(const RPartArgs& a, uint32_t part) { return (part * a.peer_mq) >> 24; }
+static_assert(kRShift == 15, "route_part (djoin.cuh) shifts by 15");
+__device__ __forceinline__ uint32_t peer_part(const RPartArgs& a, uint32_t d) { return route_part(d, a.peer_mf); }
+__device__ __forceinline__ uint32_t peer_dest(const RPartArgs& a, uint32_t part) { return route_dest(part, a.peer_mq); }
 
 __host__ __device__ __forceinline__ uint32_t hot_b1(uint32_t d) { return (d * 0x9E3779B1u) >> (32 - kHotBucketBits); }
 __host__ __device__ __forceinline__ uint32_t hot_b2(uint32_t d) { return ((d ^ 0x5BD1E995u) * 0x85EBCA6Bu) >> (32 - kHotBucketBits); }
@@ -888,8 +889,8 @@ olap_status range_shuffle(olap_ctx* ctx, const uint64_t* keys, uint64_t n, uint3
   {
     const uint64_t F = subw >> kRShift;
     if (F == 0 || F > 256 || (F << kRShift) != subw || q == 0 || q > 256) { set_error("shuffle sub-ranges must be F x 2^15 keys wide, F <= 256"); return OLAP_ERR_BAD_ARG; }
-    a.peer_mf = ((1ULL << 32) + F - 1) / F;
-    a.peer_mq = (uint32_t)(((1u << 24) + q - 1) / q);
+    a.peer_mf = route_mul_f(F);
+    a.peer_mq = route_mul_q(q);
   }
   if (hot && hot->hot_keys) { a.hot_keys = hot->hot_keys; a.hot_ids = hot->hot_ids; a.pairs = hot->pairs; a.max_matches = hot->max_matches; a.count = hot->count; }
   if (!tma) {  // plain stores from the partition kernel at full occupancy: the rows go to local memory (outbox / own slab)

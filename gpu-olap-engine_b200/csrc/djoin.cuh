@@ -44,6 +44,15 @@ olap_status dj_probe_join(DJProbe& p, olap_pair* out, uint64_t max_matches, unsi
                           uint32_t* d_flags);
 void dj_probe_end(DJProbe& p, cudaStream_t s);
 
+// Routing arithmetic of the multi-GPU shuffle, shared by the kernels (djoin.cu) and the host-side olap_shard_route (shard.cu), which
+// the CPU suite checks against plain integer division.  Exact division by multiplication: sub-ranges are F x 2^15 keys wide with
+// F <= 256 and offsets < 2^32, so x = offset >> 15 < 2^17 and (x * ceil(2^32 / F)) >> 32 == x / F (the error term x / 2^32 < 2^-15 < 1 / F);
+// partitions < 256: (p * ceil(2^24 / Q)) >> 24 == p / Q.
+__host__ __device__ __forceinline__ uint64_t route_mul_f(uint64_t F) { return ((1ULL << 32) + F - 1) / F; }
+__host__ __device__ __forceinline__ uint32_t route_mul_q(uint32_t Q) { return (uint32_t)(((1u << 24) + Q - 1) / Q); }
+__host__ __device__ __forceinline__ uint32_t route_part(uint32_t offset, uint64_t mf) { return (uint32_t)(((uint64_t)(offset >> 15) * mf) >> 32); }
+__host__ __device__ __forceinline__ uint32_t route_dest(uint32_t part, uint32_t mq) { return (part * mq) >> 24; }
+
 // heavy-hitter table handed to a pass over raw probe keys: rows whose key is in it are joined on the spot
 struct HotRef { const uint32_t* hot_keys = nullptr; const uint32_t* hot_ids = nullptr; olap_pair* pairs = nullptr; uint64_t max_matches = 0; unsigned long long* count = nullptr; };
 uint32_t hot_table_slots();

@@ -84,6 +84,20 @@ struct olap_shard {
   unsigned long long* hot_count() const { return pair_count() + 1; }
 };
 
+// Geometry of the range sharding for a dense key domain of `grange` keys over `world` ranks: one contiguous slice per rank, cut into Q
+// sub-ranges of F x 2^15 keys (F <= 256, world x Q <= 256 regions per slab side).  Host arithmetic only.
+struct ShardGeometry { uint32_t Q = 0, F = 0, subw = 0; uint64_t slice = 0; };
+static olap_status shard_geometry(int world, uint64_t grange, ShardGeometry* g) {
+  const uint64_t W = (uint64_t)world;
+  const uint64_t slice_min = (grange + W - 1) / W;
+  const uint64_t pl = std::max<uint64_t>((slice_min + (1ULL << 15) - 1) >> 15, 1);
+  const uint64_t Q = (pl + 255) / 256, F = (pl + Q - 1) / Q;
+  if (W * Q > kShardRegions) { set_error("key domain too wide for the range-sharded join: %llu sub-ranges per rank", (unsigned long long)Q); return OLAP_ERR_UNSUPPORTED; }
+  g->Q = (uint32_t)Q; g->F = (uint32_t)F; g->subw = (uint32_t)(F << 15); g->slice = Q * F << 15;
+  if (g->slice * W >= 0xFFFFFFFFULL) { set_error("key domain too wide for 32-bit offsets"); return OLAP_ERR_UNSUPPORTED; }
+  return OLAP_OK;
+}
+
 static uint64_t reserve_words(uint64_t rows) { return (rows + rows * kShardSlackPct / 100 + kShardRegions * 4096ULL + 3) & ~3ULL; }
 
 static unsigned shuffle_grid(olap_ctx* ctx) {
@@ -258,12 +272,10 @@ olap_status olap_shard_plan(olap_shard* sh, int64_t global_min, int64_t global_m
     set_error("range sharding needs a dense build-key domain (range <= 5 x rows, < 2^32)"); return OLAP_ERR_UNSUPPORTED;
   }
   const uint64_t grange = span + 1, W = (uint64_t)sh->world;
-  const uint64_t slice_min = (grange + W - 1) / W;
-  const uint64_t pl = std::max<uint64_t>((slice_min + (1ULL << 15) - 1) >> 15, 1);
-  const uint64_t Q = (pl + 255) / 256, F = (pl + Q - 1) / Q;
-  if (W * Q > kShardRegions) { set_error("key domain too wide for the range-sharded join: %llu sub-ranges per rank", (unsigned long long)Q); return OLAP_ERR_UNSUPPORTED; }
-  sh->Q = (uint32_t)Q; sh->F = (uint32_t)F; sh->subw = (uint32_t)(F << 15); sh->slice = Q * F << 15;
-  if (sh->slice * W >= 0xFFFFFFFFULL) { set_error("key domain too wide for 32-bit offsets"); return OLAP_ERR_UNSUPPORTED; }
+  ShardGeometry geo;
+  OLAP_TRY(shard_geometry(sh->world, grange, &geo));
+  const uint64_t Q = geo.Q;
+  sh->Q = geo.Q; sh->F = geo.F; sh->subw = geo.subw; sh->slice = geo.slice;
   sh->gmin = global_min; sh->grange = grange;
   const uint64_t regions = W * Q;
   {
@@ -574,6 +586,33 @@ olap_status olap_shard_key_range(olap_shard* sh, const int64_t* keys, uint64_t n
   OLAP_CUDA(cudaSetDevice(ctx->device));
   if (n_rows == 0) { *out_min = INT64_MAX; *out_max = INT64_MIN; return OLAP_OK; }
   return key_min_max(ctx, (const uint64_t*)keys, n_rows, ctx->stream_of(stream), out_min, out_max);
+}
+
+// Host-only: where the shuffle sends a key.  For every keys[i] (host array) in the planned domain [global_min, global_max]: the owning
+// rank, the sub-range (region index modulo Q) inside that rank's slab side and the offset the row carries there (key - slice start);
+// keys outside the domain get rank -1 (the shuffle drops them: they cannot match).  Runs the SAME routing arithmetic as the kernels
+// (route_part / route_dest, djoin.cuh: exact division by multiplication) -- no GPU needed, which is how the CPU suite checks that
+// arithmetic against plain integer division.  out_geometry (nullable): {Q, F, sub-range width, slice width}.
+olap_status olap_shard_route_i64(int32_t world, int64_t global_min, int64_t global_max, const int64_t* keys, uint64_t n, int32_t* out_rank,
+                                 uint32_t* out_sub_range, uint32_t* out_offset, uint64_t* out_geometry) {
+  OLAP_REQUIRE(world >= 1 && world <= kShardMaxWorld, "1 <= world <= 8");
+  OLAP_REQUIRE(n == 0 || (keys && out_rank && out_sub_range && out_offset), "NULL argument");
+  const uint64_t span = (uint64_t)global_max - (uint64_t)global_min;
+  OLAP_REQUIRE(global_max >= global_min && span < 0xFFFFFFF0ULL, "the key domain must be non-empty and narrower than 2^32");
+  ShardGeometry g;
+  OLAP_TRY(shard_geometry(world, span + 1, &g));
+  if (out_geometry) { out_geometry[0] = g.Q; out_geometry[1] = g.F; out_geometry[2] = g.subw; out_geometry[3] = g.slice; }
+  const uint64_t mf = route_mul_f(g.F);
+  const uint32_t mq = route_mul_q(g.Q);
+  for (uint64_t i = 0; i < n; i++) {
+    const uint64_t off = (uint64_t)keys[i] - (uint64_t)global_min;
+    if (off > span) { out_rank[i] = -1; out_sub_range[i] = 0; out_offset[i] = 0; continue; }
+    const uint32_t d = (uint32_t)off, part = route_part(d, mf), dest = route_dest(part, mq);
+    out_rank[i] = (int32_t)dest;
+    out_sub_range[i] = part - dest * g.Q;
+    out_offset[i] = d - dest * (g.Q * g.subw);
+  }
+  return OLAP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------- one process, all ranks

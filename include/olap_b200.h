@@ -275,6 +275,11 @@ OLAP_API olap_status olap_shard_pairs_to_global(olap_shard* shard, const olap_pa
 OLAP_API olap_status olap_shard_layout(const olap_shard* shard, uint64_t* out8);
 /* rows this rank stored into every rank's slab during the current join (the NVLink volume); synchronises the stream */
 OLAP_API olap_status olap_shard_sent_rows(olap_shard* shard, uint64_t* host_rows_per_dest /* [world] */, void* stream);
+/* Host-only (no GPU, no context): where the range shuffle sends keys of the dense domain [global_min, global_max] shared by `world`
+ * ranks -- owning rank (-1: outside the domain, dropped), sub-range inside the owner's slab side, offset carried (key - slice start).
+ * The same routing arithmetic as the kernels; out_geometry (nullable, 4 x u64): {Q, F, sub-range width in keys, slice width in keys}. */
+OLAP_API olap_status olap_shard_route_i64(int32_t world, int64_t global_min, int64_t global_max, const int64_t* keys, uint64_t n,
+                                          int32_t* out_rank, uint32_t* out_sub_range, uint32_t* out_offset, uint64_t* out_geometry);
 OLAP_API olap_status olap_shard_ctx_create_all(int32_t n_ranks, const int32_t* devices, uint64_t max_gpu_memory, uint64_t build_rows_cap,
                                                uint64_t probe_rows_cap, int32_t probe_chunks, olap_ctx** out_ctxs, olap_shard** out_shards);
 /* hot_pairs / max_hot_pairs / host_hot_counts: all NULL = no heavy-hitter handling; else per-rank buffers for the {hot slot, local
