@@ -97,6 +97,7 @@ SIGNATURES = {
     "olap_shard_pairs_to_global": (i32, [vp, vp, u64, vp, vp, vp, vp, vp]),
     "olap_shard_layout": (i32, [vp, pu64]),
     "olap_shard_sent_rows": (i32, [vp, pu64, vp]),
+    "olap_shard_hot_table_host": (i32, [vp, u32, vp, vp, vp, u32, vp]),
     "olap_shard_route_i64": (i32, [i32, i64, i64, vp, u64, vp, vp, vp, vp]),
     "olap_shard_ctx_create_all": (i32, [i32, C.POINTER(i32), u64, u64, u64, i32, pvp, pvp]),
     "olap_sharded_hash_join_i64": (i32, [pvp, i32, pvp, pu64, pvp, pu64, pvp, pu64, pu64, pvp, pu64, pu64]),

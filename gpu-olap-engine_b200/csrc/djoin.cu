@@ -934,6 +934,16 @@ olap_status range_shuffle_publish(olap_ctx* ctx, const uint32_t* cursor, uint32_
 }
 
 // ------------------------------------------------------------------------------------------- heavy hitters across ranks
+// Host restatement of hot_lookup's rule, for the CPU suite: the slot of `want` (= offset + 1) in a table built by
+// hot_table_build_host / hot_select_kernel, or ~0.  Same hashes (hot_b1 / hot_b2), same "second bucket only when the first is full".
+uint32_t hot_lookup_host(const uint32_t* tab, uint32_t want) {
+  const uint32_t d = want - 1u, b1 = hot_b1(d);
+  for (int j = 0; j < 4; j++) if (tab[4 * b1 + j] == want) return 4 * b1 + j;
+  if (tab[4 * b1 + 3] == 0u) return 0xFFFFFFFFu;
+  const uint32_t b2 = hot_b2(d);
+  for (int j = 0; j < 4; j++) if (tab[4 * b2 + j] == want) return 4 * b2 + j;
+  return 0xFFFFFFFFu;
+}
 uint32_t hot_table_slots() { return kHotSlots; }
 uint32_t hot_max_keys() { return kHotMaxKeys; }
 // Host-side build of the same table, sequentially over the caller's (sorted) keys so that every rank ends up with the same slot for

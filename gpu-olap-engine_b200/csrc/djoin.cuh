@@ -58,6 +58,7 @@ struct HotRef { const uint32_t* hot_keys = nullptr; const uint32_t* hot_ids = nu
 uint32_t hot_table_slots();
 uint32_t hot_max_keys();   // at most a quarter of the slots hold a key
 uint32_t hot_table_build_host(const uint32_t* keys_plus1, uint32_t n, uint32_t* tab);
+uint32_t hot_lookup_host(const uint32_t* tab, uint32_t want);
 uint32_t hot_sample_slots();
 olap_status hot_candidates(olap_ctx* ctx, const uint64_t* keys, uint64_t n, int64_t gmin, uint64_t grange, uint32_t* scratch, uint32_t cap,
                            uint32_t** out_key, uint32_t** out_cnt, uint32_t** out_n, cudaStream_t s);

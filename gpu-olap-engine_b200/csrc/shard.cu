@@ -588,6 +588,24 @@ olap_status olap_shard_key_range(olap_shard* sh, const int64_t* keys, uint64_t n
   return key_min_max(ctx, (const uint64_t*)keys, n_rows, ctx->stream_of(stream), out_min, out_max);
 }
 
+// Host-only: the heavy-hitter table as olap_shard_hot_set builds it (sorted, de-duplicated keys_plus1 = key - global_min + 1; 2048
+// buckets of 4 slots, second-choice bucket when the first is full) into out_table[8192], and the slot the kernels' lookup rule finds
+// for each probe_plus1[i] (0xFFFFFFFF: not a heavy hitter).  *out_placed = keys that found a slot (a key whose two buckets are both
+// full is simply not a heavy hitter).  No GPU: the CPU suite checks builder and lookup against each other.
+olap_status olap_shard_hot_table_host(const uint32_t* keys_plus1, uint32_t n_keys, uint32_t* out_table, uint32_t* out_placed,
+                                      const uint32_t* probe_plus1, uint32_t n_probe, uint32_t* out_slots) {
+  OLAP_REQUIRE(out_table && (n_keys == 0 || keys_plus1) && (n_probe == 0 || (probe_plus1 && out_slots)), "NULL argument");
+  OLAP_REQUIRE(n_keys <= hot_max_keys(), "at most 2048 hot keys (a quarter of the table's slots)");
+  std::vector<uint32_t> keys(keys_plus1, keys_plus1 + n_keys);
+  std::sort(keys.begin(), keys.end());
+  keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+  memset(out_table, 0, (size_t)hot_table_slots() * 4);
+  const uint32_t placed = hot_table_build_host(keys.data(), (uint32_t)keys.size(), out_table);
+  if (out_placed) *out_placed = placed;
+  for (uint32_t i = 0; i < n_probe; i++) out_slots[i] = (probe_plus1[i] == 0u || probe_plus1[i] == 0xFFFFFFFFu) ? 0xFFFFFFFFu : hot_lookup_host(out_table, probe_plus1[i]);
+  return OLAP_OK;
+}
+
 // Host-only: where the shuffle sends a key.  For every keys[i] (host array) in the planned domain [global_min, global_max]: the owning
 // rank, the sub-range (region index modulo Q) inside that rank's slab side and the offset the row carries there (key - slice start);
 // keys outside the domain get rank -1 (the shuffle drops them: they cannot match).  Runs the SAME routing arithmetic as the kernels

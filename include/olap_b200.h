@@ -275,6 +275,10 @@ OLAP_API olap_status olap_shard_pairs_to_global(olap_shard* shard, const olap_pa
 OLAP_API olap_status olap_shard_layout(const olap_shard* shard, uint64_t* out8);
 /* rows this rank stored into every rank's slab during the current join (the NVLink volume); synchronises the stream */
 OLAP_API olap_status olap_shard_sent_rows(olap_shard* shard, uint64_t* host_rows_per_dest /* [world] */, void* stream);
+/* Host-only (no GPU, no context): the heavy-hitter table exactly as olap_shard_hot_set lays it out (out_table: 8192 u32), the number
+ * of keys placed, and the slot the kernels' lookup rule finds for every probe_plus1[i] (0xFFFFFFFF = not a heavy hitter).       */
+OLAP_API olap_status olap_shard_hot_table_host(const uint32_t* keys_plus1, uint32_t n_keys, uint32_t* out_table, uint32_t* out_placed,
+                                               const uint32_t* probe_plus1, uint32_t n_probe, uint32_t* out_slots);
 /* Host-only (no GPU, no context): where the range shuffle sends keys of the dense domain [global_min, global_max] shared by `world`
  * ranks -- owning rank (-1: outside the domain, dropped), sub-range inside the owner's slab side, offset carried (key - slice start).
  * The same routing arithmetic as the kernels; out_geometry (nullable, 4 x u64): {Q, F, sub-range width in keys, slice width in keys}. */

@@ -98,3 +98,45 @@ def test_route_refuses_what_the_plan_refuses():
     assert st == 1
     st, *_ = route(9, 0, 100, np.zeros(0, np.int64))
     assert st == 1
+
+
+def hot_table(keys_plus1, probe_plus1):
+    import gpu_olap_engine_b200 as g
+    lib = g.load()
+    k = np.ascontiguousarray(keys_plus1, np.uint32); p = np.ascontiguousarray(probe_plus1, np.uint32)
+    tab = np.zeros(8192, np.uint32); slots = np.empty(len(p), np.uint32); placed = C.c_uint32()
+    st = lib.olap_shard_hot_table_host(k.ctypes.data, len(k), tab.ctypes.data, C.byref(placed), p.ctypes.data, len(p), slots.ctypes.data)
+    return st, tab, placed.value, slots
+
+
+@pytest.mark.parametrize("n_keys,dense", [(0, False), (1, False), (500, False), (2048, False), (2048, True)])
+def test_heavy_hitter_table_builder_and_lookup_agree(n_keys, dense):
+    # the 2048-bucket x 4-slot table of the Zipf path (csrc/djoin.cu): every key that was placed is found at its slot, nothing else is found,
+    # slots fill in order inside a bucket (the lookup's "second bucket only when the first is full" rule depends on it)
+    rng = np.random.default_rng(n_keys + dense)
+    keys = (np.arange(n_keys, dtype=np.uint32) * 7 + 1) if dense else (rng.choice(1 << 31, n_keys, replace=False).astype(np.uint32) + 1)
+    others = np.setdiff1d(rng.integers(1, 1 << 32, 50_000, dtype=np.uint64).astype(np.uint32), keys)
+    others = others[(others != 0) & (others != 0xFFFFFFFF)]
+    st, tab, placed, slots = hot_table(np.concatenate([keys, keys[:10]]) if n_keys else keys, np.concatenate([keys, others]))   # duplicates are dropped
+    if n_keys + min(n_keys, 10) > 2048:
+        assert st == 1                                                  # more than a quarter of the slots: refused
+        st, tab, placed, slots = hot_table(keys, np.concatenate([keys, others]))
+    assert st == 0
+    stored = tab[tab != 0]
+    assert len(stored) == placed == len(np.unique(stored)) and set(stored.tolist()) <= set(keys.tolist())
+    assert placed >= n_keys - 2                                         # both buckets full is rare at a quarter of the capacity
+    found = slots[:n_keys]
+    was_placed = np.isin(keys, stored)
+    assert (found[was_placed] != 0xFFFFFFFF).all() and (tab[found[was_placed]] == keys[was_placed]).all()
+    assert (found[~was_placed] == 0xFFFFFFFF).all() and (slots[n_keys:] == 0xFFFFFFFF).all()
+    b = tab.reshape(2048, 4)
+    assert ((b[:, 1:] == 0) | (b[:, :-1] != 0)).all()                   # no hole before a taken slot
+
+
+def test_heavy_hitter_table_same_layout_for_any_key_order():
+    # every rank must end up with the same slot for the same key whatever order the host language hands the keys over in
+    rng = np.random.default_rng(3)
+    keys = rng.choice(1 << 30, 2000, replace=False).astype(np.uint32) + 1
+    _, t1, _, _ = hot_table(keys, keys[:1])
+    _, t2, _, _ = hot_table(rng.permutation(keys), keys[:1])
+    assert (t1 == t2).all()
