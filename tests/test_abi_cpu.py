@@ -111,3 +111,19 @@ int main(void) {
     assert got["olap_expr_prog"] == [C.sizeof(pr), pr.n_ops.offset, pr.op.offset, pr.column.offset, pr.literal_bits.offset]
     assert got["olap_pair"] == [8, _lib.PROG_MAX_OPS]
 
+
+
+def test_header_is_plain_c_and_declares_the_multi_gpu_group(tmp_path):
+    # the drop-in boundary is a C ABI: the header must compile as C99 (and as C++) on its own, and carry SURVEY 8(b)'s multi-GPU group
+    import shutil
+    import subprocess
+    src = tmp_path / "h.c"
+    src.write_text('#include "olap_b200.h"\nint main(void) { return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    if shutil.which("gcc"):
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    if shutil.which("g++"):
+        subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
+    syms = set(_declared_symbols())
+    assert {"olap_shard_ctx_create_all", "olap_sharded_hash_join_i64", "olap_sharded_group_by_i64", "olap_shard_route_i64",
+            "olap_join_unmatched_rows", "olap_join_gather_8b", "olap_group_by_expr_i64", "olap_register_device_batch"} <= syms
