@@ -52,6 +52,18 @@ class GpuExecutor:
             finally:
                 pa.Schema._import_from_c(c.schema_ptr)  # releases the exported schema
 
+    def load_table(self, table_name: str, path: str, batch_size: int = 1 << 20):
+        """Catalog::load_table (catalog.rs:32-73) wired to the device: read the Parquet file (cached below 10 M rows, streamed row group
+        by row group above) and register every batch, so that GpuTableScan(table_name) has device-resident columns to scan."""
+        from .catalog import Catalog
+        if not hasattr(self, "catalog"):
+            self.catalog = Catalog()
+        md = self.catalog.load_table(table_name, path, batch_size)
+        self.drop_table(table_name)
+        for b in self.catalog.iter_batches(table_name, batch_size):
+            self.register_table(table_name, b)
+        return md
+
     def register_device_table(self, table_name: str, columns, n_rows: int) -> None:
         """Append one batch of device-resident columns ({name: (DeviceBuffer, OLAP_I64 | OLAP_F64)}) to ``table_name`` -- copied device
         to device, no host round trip (olap_register_device_batch)."""
