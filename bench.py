@@ -4,16 +4,19 @@
 Metric (BASELINE.json): join rows/sec, rows = |build| + |probe|, on the single-GPU radix hash join
 2^27 unique-key build x 2^29 FK probe, int64 keys (configs[1]); % of HBM roofline for the dominant kernel.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2-build B --log2-probe P]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log2-build B --log2-probe P] [--zipf S]
 
-* value     device-resident inputs, CUDA events around K joins on the launching stream, max over ranks
+* value     device-resident inputs, CUDA events around K joins on the launching stream, max over ranks; every pair verified afterwards
 * e2e       the same join through the C-ABI with HOST (pinned) buffers: H2D of both key columns, join, D2H of the
             count and of the row-id pairs, all inside the timed region
-* roofline  dominant kernel (join_pipeline_kernel: one persistent launch per step): algorithmic bytes / its CUDA-event
-            duration in the timed region, against MEASURED_PEAKS.json's hbm_gbs; the partition kernel next to it
+* roofline  the kernel with the largest share of the step (djoin_kernel on the dense-key path): algorithmic bytes / its CUDA-event
+            duration in the timed region, against MEASURED_PEAKS.json's hbm_gbs; roofline_kernels lists every phase the same way
+* value_with_payload / value_general / group_by   the same line also carries the payload-materialising join (BASELINE config 2's "int64
+            payload"), the sparse-key (bucket-table) path, and BASELINE config 3's group-by sweep (G = 1e2 / 1e5 / 1e8 at 2^30 rows)
 * cpu_baseline / --impl reference   the oracle's multi-threaded port of the reference CPU path on this box's cores
-N > 1: weak scaling, one process per GPU (torchrun); the join is key-sharded with an NCCL all-to-all shuffle
-(gpu_olap_engine_b200/sharded.py); value = rows of all ranks / max-over-ranks time.
+N > 1: weak scaling, one process per GPU (torchrun), per GPU 2^28 x 2^30 (BASELINE config 5); the join is key-RANGE-sharded over NVLink
+peer memory (gpu_olap_engine_b200/shard.py + sharded.py::bench_sharded_join), NCCL carries only the tiny reductions;
+value = rows of all ranks / max-over-ranks time; --zipf S skews the probe keys (heavy hitters are replicated).
 """
 import argparse
 import json
